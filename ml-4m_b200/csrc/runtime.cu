@@ -1,0 +1,80 @@
+// Host runtime glue for the C ABI: last-error string, device properties, TMA descriptor encoding.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/b200fm.h"
+#include "common.cuh"
+#include "tmap.cuh"
+
+namespace b200fm {
+
+static thread_local char g_err[1024] = "";
+
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, TmapDtype dt, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                 uint32_t box_inner, uint32_t box_outer, bool swizzle128) {
+    EncodeTiledFn fn = get_encode_fn();
+    B200FM_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+    const uint32_t es = dt == TmapDtype::BF16 ? 2 : 4;
+    B200FM_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer %p not 16-byte aligned", base);
+    B200FM_CHECK(row_stride_bytes % 16 == 0, "TMA row stride %llu B not a multiple of 16", (unsigned long long)row_stride_bytes);
+    B200FM_CHECK(!swizzle128 || box_inner * es == 128, "128B swizzle needs a 128-byte inner box (got %u)", box_inner * es);
+    B200FM_CHECK(box_inner <= 256 && box_outer <= 256, "TMA box dims must be <= 256");
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, dt == TmapDtype::BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200FM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu stride=%llu box=%ux%u)",
+                 (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes, box_inner,
+                 box_outer);
+    return 0;
+}
+
+}  // namespace b200fm
+
+extern "C" {
+
+const char* b200fm_last_error(void) { return b200fm::g_err; }
+
+int b200fm_abi_version(void) { return B200FM_ABI_VERSION; }
+
+int b200fm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin) {
+    cudaDeviceProp p;
+    B200FM_CUDA(cudaGetDeviceProperties(&p, device));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (smem_optin) *smem_optin = p.sharedMemPerBlockOptin;
+    return 0;
+}
+
+}  // extern "C"

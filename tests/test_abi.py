@@ -1,0 +1,47 @@
+"""C-ABI library: loads and exports every symbol include/b200fm.h declares (no compute calls; runs without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b200fm.h")).read()
+    return sorted(set(re.findall(r"\b(b200fm_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+    from b200fm import lib
+    return lib
+
+
+def test_library_exports_every_declared_symbol(built):
+    lib = built.load()
+    syms = _declared_symbols()
+    assert len(syms) >= 8
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/b200fm.h but not exported"
+    assert lib.b200fm_abi_version() == 1
+    assert set(built.SIGNATURES) | {"b200fm_last_error"} == set(syms), "ctypes table out of sync with the header"
+
+
+def test_argument_validation_without_gpu(built):
+    lib = built.load()
+    # bad arguments are rejected before any CUDA call
+    rc = lib.b200fm_gemm_bf16(0, 0, 0, 0, 0, None, 8, None, 8, None, 8, None, 0, None, None, 0, 1.0, None, None)
+    assert rc != 0 and b"empty problem" in lib.b200fm_last_error()
+    rc = lib.b200fm_vq_argmax(None, None, None, None, 5, 16, 7, 1, None)
+    assert rc != 0 and b"latent dim" in lib.b200fm_last_error()
+
+
+def test_ops_refuse_cpu_tensors(built):
+    import torch
+    from b200fm import ops
+    with pytest.raises(built.B200FMError):
+        ops.vq_argmax(torch.zeros(4, 32), torch.zeros(8, 32))

@@ -1,0 +1,96 @@
+"""tcgen05 GEMM (through the C ABI) vs a plain fp32 torch reference on the same bf16 inputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).cuda()
+
+
+def _ref(a, b, layout):
+    a32, b32 = a.float(), b.float()
+    if layout == 0:
+        return a32 @ b32.t()
+    if layout == 1:
+        return a32 @ b32
+    return a32.t() @ b32
+
+
+SHAPES = [(128, 128, 64), (128, 256, 64), (256, 256, 128), (384, 768, 768), (1000, 520, 200), (130, 72, 72), (16384, 768, 768)]
+
+
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_f32_out(layout, M, N, K):
+    from b200fm import ops
+    if layout == 0:
+        a, b = _mk((M, K), 1), _mk((N, K), 2)
+    elif layout == 1:
+        a, b = _mk((M, K), 1), _mk((K, N), 2)
+    else:
+        a, b = _mk((K, M), 1), _mk((K, N), 2)
+    out = ops.gemm(a, b, layout=layout, epilogue=ops.EPI_F32)
+    torch.cuda.synchronize()
+    ref = _ref(a, b, layout)
+    # bf16 products are exact in fp32; only the accumulation order differs
+    torch.testing.assert_close(out, ref, rtol=2e-4, atol=2e-3 * (K ** 0.5) / 8)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (1000, 520, 200), (16384, 2304, 768)])
+def test_gemm_bf16_bias_alpha(M, N, K):
+    from b200fm import ops
+    a, b = _mk((M, K), 3), _mk((N, K), 4)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(5)).cuda()
+    adev = torch.tensor([0.5], device="cuda")
+    out = ops.gemm(a, b, epilogue=ops.EPI_BF16, bias=bias, alpha=2.0, alpha_dev=adev)
+    ref = ((a.float() @ b.float().t() + bias) * 1.0).to(torch.bfloat16)
+    torch.testing.assert_close(out.float(), ref.float(), rtol=1e-2, atol=1e-2 * (K ** 0.5) / 8)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (16384, 768, 2048), (300, 392, 136)])
+def test_gemm_residual(M, N, K):
+    from b200fm import ops
+    a, b = _mk((M, K), 6, 0.5), _mk((N, K), 7, 0.5)
+    resid = torch.randn(M, N, generator=torch.Generator().manual_seed(8)).cuda()
+    out = ops.gemm(a, b, epilogue=ops.EPI_RESID, resid=resid)
+    ref = resid + (a.float() @ b.float().t()).to(torch.bfloat16).float()
+    torch.testing.assert_close(out, ref, rtol=1e-2, atol=2e-2 * (K ** 0.5) / 8)
+
+
+@pytest.mark.parametrize("M,H,K", [(256, 128, 128), (512, 1024, 384), (16384, 2048, 768), (200, 344, 128)])
+def test_gemm_swiglu(M, H, K):
+    from b200fm import ops
+    x = _mk((M, K), 9, 0.5)
+    w13 = _mk((2 * H, K), 10, 0.2)
+    ab, g = ops.gemm(x, w13, epilogue=ops.EPI_SWIGLU)
+    ref = x.float() @ w13.float().t()
+    a_ref, b_ref = ref[:, :H].to(torch.bfloat16), ref[:, H:].to(torch.bfloat16)
+    torch.testing.assert_close(ab[:, :H].float(), a_ref.float(), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(ab[:, H:].float(), b_ref.float(), rtol=1e-2, atol=1e-2)
+    # gate computed from the kernel's own (bf16-rounded) a, b exactly as the reference's autocast chain
+    g_ref = (torch.nn.functional.silu(ab[:, :H]) * ab[:, H:])
+    torch.testing.assert_close(g.float(), g_ref.float(), rtol=2e-2, atol=2e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (4096, 3072, 768)])
+def test_gemm_gelu(M, N, K):
+    from b200fm import ops
+    x, w = _mk((M, K), 11, 0.5), _mk((N, K), 12, 0.2)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(13)).cuda() * 0.1
+    pre, act = ops.gemm(x, w, epilogue=ops.EPI_GELU, bias=bias)
+    ref = (x.float() @ w.float().t() + bias).to(torch.bfloat16)
+    torch.testing.assert_close(pre.float(), ref.float(), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(act.float(), torch.nn.functional.gelu(pre.float()).to(torch.bfloat16).float(), rtol=1e-2, atol=1e-3)
+
+
+def test_gemm_strided_views():
+    """q/k/v style column slices of a packed buffer as operands (row stride != K)."""
+    from b200fm import ops
+    big = _mk((512, 768), 14)
+    a = big[:, 256:512]                   # [512, 256] with row stride 768
+    b = _mk((384, 256), 15)
+    out = ops.gemm(a, b, epilogue=ops.EPI_F32)
+    torch.testing.assert_close(out, a.float() @ b.float().t(), rtol=2e-4, atol=5e-3)
