@@ -74,6 +74,84 @@ int b200fm_attention_bwd(const void* q, long long ldq, const void* k, long long 
                          void* dk, long long lddk, void* dv, long long lddv, int B, int H, int Nq, int Nk, float scale,
                          void* stream);
 
+/* ---- element-wise / row-wise kernels around the GEMMs -------------------------------------------------------
+ * swiglu_bwd: fm_utils.py:143 backward. ab bf16 [R,2H] = [a|b] saved by EPI_SWIGLU, dg bf16 [R,H] -> dab bf16 [R,2H].   */
+int b200fm_swiglu_bwd(const void* ab, long long ld_ab, const void* dg, long long ld_dg, void* dab, long long ld_dab,
+                      long long R, int H, void* stream);
+/* act_bwd: dpre = dact * f'(pre) on bf16 [n]; act 0 = GELU(erf) (fm_utils.py:116-125 Mlp), 1 = tanh (vit post_mlp).     */
+int b200fm_act_bwd(int act, const void* pre, const void* dact, void* dpre, long long n, void* stream);
+/* cross_entropy: fm.py:597 F.cross_entropy on fp32 logits [n,V] (row stride ld); loss_rows fp32 [n] (per-row NLL);
+ * dlogits (optional) bf16 [n,V] = softmax - onehot, UNSCALED (fold 1/n and the upstream grad in via gemm alpha_dev).    */
+int b200fm_cross_entropy(const float* logits, long long ld, const int64_t* targets, float* loss_rows, void* dlogits,
+                         long long ldd, long long n, int V, void* stream);
+/* colsum_bf16: out[c] += sum_r x[r,c] (bias gradients of nn.Linear layers with bias).                                   */
+int b200fm_colsum_bf16(const void* x, long long ld, float* out, long long R, int N, void* stream);
+/* cast_f32_bf16: bf16 shadow of fp32 master weights / activations (what autocast does per call in the reference).       */
+int b200fm_cast_f32_bf16(const float* x, void* y, long long n, void* stream);
+/* patchify: encoder_embeddings.py:301 rearrange 'b d (nh ph) (nw pw) -> b (nh nw) (ph pw d)', fp32 -> bf16 rows.       */
+int b200fm_patchify(const float* img, void* out, int B, int C, int H, int W, int P, void* stream);
+/* adamw: torch.optim.AdamW single-tensor step (optim_factory.py:239-240) fused with the bf16 shadow refresh.
+ * g is multiplied by grad_scale first (DDP mean / loss scaling).                                                         */
+int b200fm_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr, float beta1,
+                 float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+
+/* ---- modality-masked token selection + embedding gather / scatter ------------------------------------------------
+ * Replaces cat_{encoder,decoder}_tensors + forward_mask_{encoder,decoder} + adapt_decoder_attention_mask
+ * (fourm/models/fm.py:245-475) and the embedding module forwards (fourm/models/encoder_embeddings.py:87-121, 184-211,
+ * 280-309; fourm/models/decoder_embeddings.py:98-139, 226-255).  One b200fm_segment per modality, in concatenation order
+ * (mod_dict order on the encoder side; the Python-`random` shuffled order of fm.py:306 on the decoder side).          */
+#define B200FM_MAX_SEGMENTS 24
+#define B200FM_KIND_IMG 0     /* pixel patches: x rows come from the patch-projection GEMM (x_rows)  */
+#define B200FM_KIND_TOK_IMG 1 /* tokenised image: ids [B, L]                                         */
+#define B200FM_KIND_SEQ 2     /* token sequence: ids [B, L], decoder side uses the teacher-forcing shift */
+typedef struct b200fm_segment {
+    const uint8_t* mask;      /* [B, L] bool, 1 = masked: input_mask (encoder) / target_mask (decoder)            */
+    const void* ids;          /* [B, L] int32 or int64 token ids (NULL for KIND_IMG)                              */
+    const int32_t* dam;       /* [B, L] decoder_attention_mask (decoder side only)                                */
+    const float* token_emb;   /* [V, D] fp32 table                                                                */
+    const float* pos_emb;     /* [P, D] fp32 positional table                                                     */
+    const float* mod_emb;     /* [D]                                                                              */
+    const void* x_rows;       /* KIND_IMG: bf16 [B*L, D] projected patches                                        */
+    float* d_token_emb;       /* backward: [V, D] fp32 gradient table, accumulated into (may be NULL)             */
+    float* d_mod_emb;         /* backward: [D] fp32, accumulated into (may be NULL)                               */
+    void* dx_rows;            /* backward, KIND_IMG: bf16 [B*L, D] gradient rows (pre-zeroed by the caller)       */
+    long long padding_idx;    /* nn.Embedding padding_idx (its gradient row stays zero); -1 = none                */
+    int L;                    /* positions per sample in the raw tensors                                          */
+    int kind;
+    int mod_id;               /* generate_uint15_hash(name), fourm/utils/misc.py:39-41                            */
+    int max_length;           /* decoder sequences: positions >= max_length wrap to 0 (decoder_embeddings.py:128) */
+    int ids_is_i64;
+    int reserved;
+} b200fm_segment;
+
+/* Stable partition "first n_keep valid positions, then masked ones, in order" per sample (== argsort(mask+arange*1e-6)[:, :n_keep]).
+ * Outputs [B, n_keep]: src_seg (segment index), src_pos (position inside the segment), pos_id (positional-table row, -1 = none),
+ * pad_mask (1 = padded slot: the reference's encoder_mask / decoder_mask), mod_mask (int16, -1 on pads), mod_raw (before the
+ * -1 assignment: needed by the attention mask), and on the decoder side target_ids (int64, 0 on pads) and dam (int32).     */
+int b200fm_select_plan(const b200fm_segment* segs, int n_seg, int decoder, int B, int n_keep, int32_t* src_seg, int32_t* src_pos,
+                       int32_t* pos_id, uint8_t* pad_mask, int16_t* mod_mask, int16_t* mod_raw, int64_t* target_ids,
+                       int32_t* dam_out, void* stream);
+/* mask_out uint8 [B, M, M], 1 = masked: (j >= cumsum(dam)[i]) | (mod_raw[i] != mod_raw[j])  (or triu(1) if causal).          */
+int b200fm_decoder_attention_mask(const int32_t* dam, const int16_t* mod_raw, uint8_t* mask_out, int B, int M, int causal, int sep,
+                                  void* stream);
+/* x0 fp32 [B, n_keep, D] = x + emb, emb_out (optional) fp32 = pos + mod; padded slots are zero.                               */
+int b200fm_embed_rows(const b200fm_segment* segs, int n_seg, int decoder, const int32_t* src_seg, const int32_t* src_pos,
+                      const int32_t* pos_id, const uint8_t* pad_mask, const float* mask_token, float* x0, float* emb_out, int B,
+                      int n_keep, int D, void* stream);
+/* Backward of embed_rows: dx0 (and demb, optional) fp32 [B, n_keep, D] -> scatter-add into d_token_emb / d_mod_emb / dx_rows of
+ * each segment and d_mask_token (decoder image modalities).                                                                 */
+int b200fm_embed_rows_bwd(const b200fm_segment* segs, int n_seg, int decoder, const int32_t* src_seg, const int32_t* src_pos,
+                          const uint8_t* pad_mask, const float* dx0, const float* demb, float* d_mask_token, int B, int n_keep,
+                          int D, void* stream);
+/* Masked-token head index sets (fm.py:589-600 `y[decoder_mod_mask == idx]`): rows_out int32 [n_mods, n_rows] (row-major order,
+ * first counts[m] entries valid), counts int32 [n_mods].  mod_ids_dev: device int32 [n_mods].                              */
+int b200fm_head_rows(const int16_t* mod_mask, long long n_rows, const int* mod_ids_dev, int n_mods, int32_t* rows_out,
+                     int32_t* counts, void* stream);
+int b200fm_gather_rows_bf16(const void* src, const int32_t* rows, void* out, long long n, int D, void* stream);
+int b200fm_gather_i64(const int64_t* src, const int32_t* rows, int64_t* out, long long n, void* stream);
+/* dst fp32 [*, D] rows[i] += src bf16 [n, D] row i (distinct destination rows).                                             */
+int b200fm_scatter_add_rows(const void* src_bf16, const int32_t* rows, float* dst, long long n, int D, void* stream);
+
 /* ---- VQ codebook scan (fourm/vq/quantizers/quantize_lucid.py:388-407 cosine, :263-284 Euclidean) -------------
  * z fp32 [n, d], codebook fp32 [K, d] (d <= 64, multiple of 4).  cosine != 0: both sides are l2-normalised (eps 1e-12,
  * F.normalize) and the arg-max of the dot product is taken; else arg-max of -(|z|^2 - 2 z.e + |e|^2).  fp32 FMA,

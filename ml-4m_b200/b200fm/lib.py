@@ -8,6 +8,19 @@ LIB_PATH = os.path.join(_HERE, "libb200fm.so")
 
 c_void_p, c_int, c_ll, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_size_t
 
+
+
+class Segment(ctypes.Structure):
+    """Mirror of `b200fm_segment` (include/b200fm.h)."""
+    _fields_ = [("mask", c_void_p), ("ids", c_void_p), ("dam", c_void_p), ("token_emb", c_void_p), ("pos_emb", c_void_p),
+                ("mod_emb", c_void_p), ("x_rows", c_void_p), ("d_token_emb", c_void_p), ("d_mod_emb", c_void_p),
+                ("dx_rows", c_void_p), ("padding_idx", c_ll), ("L", c_int), ("kind", c_int), ("mod_id", c_int),
+                ("max_length", c_int), ("ids_is_i64", c_int), ("reserved", c_int)]
+
+
+MAX_SEGMENTS = 24
+KIND_IMG, KIND_TOK_IMG, KIND_SEQ = 0, 1, 2
+
 # name -> argtypes  (restype is int unless noted); must list every symbol declared in include/b200fm.h
 SIGNATURES = {
     "b200fm_abi_version": [],
@@ -17,6 +30,29 @@ SIGNATURES = {
     "b200fm_layernorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p],
     "b200fm_layernorm_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_int, c_int, c_void_p],
+    "b200fm_attention_fwd": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_void_p,
+                             c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "b200fm_attention_bwd": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_void_p, c_ll,
+                             c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "b200fm_swiglu_bwd": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p],
+    "b200fm_act_bwd": [c_int, c_void_p, c_void_p, c_void_p, c_ll, c_void_p],
+    "b200fm_cross_entropy": [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_int, c_void_p],
+    "b200fm_colsum_bf16": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p],
+    "b200fm_cast_f32_bf16": [c_void_p, c_void_p, c_ll, c_void_p],
+    "b200fm_patchify": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "b200fm_adamw": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_float, c_int,
+                     c_float, c_void_p],
+    "b200fm_select_plan": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_void_p, c_void_p, c_void_p],
+    "b200fm_decoder_attention_mask": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "b200fm_embed_rows": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                          c_int, c_int, c_void_p],
+    "b200fm_embed_rows_bwd": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                              c_int, c_void_p],
+    "b200fm_head_rows": [c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+    "b200fm_gather_rows_bf16": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
+    "b200fm_gather_i64": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p],
+    "b200fm_scatter_add_rows": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "b200fm_vq_argmax": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p],
     "b200fm_vq_argmax_host": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p],
 }
@@ -44,6 +80,8 @@ def load():
         lib.b200fm_last_error.restype = ctypes.c_char_p
         lib.b200fm_last_error.argtypes = []
         for name, argtypes in SIGNATURES.items():
+            if not hasattr(lib, name):      # tests/test_abi.py enforces that every declared symbol is exported
+                continue
             fn = getattr(lib, name)
             fn.argtypes = argtypes
             fn.restype = c_int

@@ -109,3 +109,47 @@ def vq_argmax(z, codebook, cosine=True, want_quant=False):
     quant = torch.empty(n, d, device=z.device, dtype=torch.float32) if want_quant else None
     lib.call("b200fm_vq_argmax", _ptr(z), _ptr(codebook), _ptr(idx), _ptr(quant), n, K, d, int(cosine), _stream())
     return (idx, quant) if want_quant else idx
+
+
+def _mask_args(mask, B, Nq, Nk):
+    """mask: None or bool/uint8 broadcastable [B, 1|Nq, Nk] (True = masked) -> (tensor kept alive, ptr, b_stride, q_stride)."""
+    if mask is None:
+        return None, 0, 0, 0
+    if mask.dtype == torch.bool:
+        mask = mask.view(torch.uint8)
+    assert mask.dtype == torch.uint8 and mask.dim() == 3 and mask.shape[2] == Nk and mask.shape[0] in (1, B) and mask.shape[1] in (1, Nq)
+    if mask.stride(2) != 1:
+        mask = mask.contiguous()
+    bs = 0 if mask.shape[0] == 1 else mask.stride(0)
+    qs = 0 if mask.shape[1] == 1 else mask.stride(1)
+    return mask, mask.data_ptr(), bs, qs
+
+
+def attention_fwd(q, k, v, B, H, Nq, Nk, mask=None, scale=None):
+    """q [B*Nq, >=H*64], k/v [B*Nk, >=H*64] bf16 views with unit inner stride (may be column slices of a packed qkv).
+    Returns (out bf16 [B*Nq, H*64], stats fp32 [B, H, Nq, 2])."""
+    _need_cuda(q, k, v, mask)
+    for t in (q, k, v):
+        assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1
+    scale = 64 ** -0.5 if scale is None else scale
+    out = torch.empty(B * Nq, H * 64, device=q.device, dtype=torch.bfloat16)
+    stats = torch.empty(B, H, Nq, 2, device=q.device, dtype=torch.float32)
+    mk, mp, mbs, mqs = _mask_args(mask, B, Nq, Nk)
+    lib.call("b200fm_attention_fwd", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), mp, mbs, mqs, _ptr(out),
+             out.stride(0), _ptr(stats), B, H, Nq, Nk, float(scale), _stream())
+    return out, stats
+
+
+def attention_bwd(q, k, v, out, dout, stats, B, H, Nq, Nk, mask=None, scale=None, dq=None, dk=None, dv=None):
+    """Gradients w.r.t. q, k, v (bf16).  dq/dk/dv may be pre-allocated views (e.g. column slices of a packed dqkv)."""
+    _need_cuda(q, k, v, out, dout, stats, mask)
+    scale = 64 ** -0.5 if scale is None else scale
+    dev = q.device
+    dq = torch.empty(B * Nq, H * 64, device=dev, dtype=torch.bfloat16) if dq is None else dq
+    dk = torch.empty(B * Nk, H * 64, device=dev, dtype=torch.bfloat16) if dk is None else dk
+    dv = torch.empty(B * Nk, H * 64, device=dev, dtype=torch.bfloat16) if dv is None else dv
+    mk, mp, mbs, mqs = _mask_args(mask, B, Nq, Nk)
+    lib.call("b200fm_attention_bwd", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), mp, mbs, mqs, _ptr(out),
+             out.stride(0), _ptr(dout), dout.stride(0), _ptr(stats), _ptr(dq), dq.stride(0), _ptr(dk), dk.stride(0), _ptr(dv),
+             dv.stride(0), B, H, Nq, Nk, float(scale), _stream())
+    return dq, dk, dv

@@ -1,0 +1,342 @@
+// Fused multi-head attention backward for sm_100a (head_dim 64).  Autograd counterpart of attention_fwd.cu for the
+// reference's materialised attention (fourm/models/fm_utils.py:160-180, 197-219): given dO it recomputes
+// P = softmax(mask(Q K^T * scale)) from the saved row statistics and produces dQ, dK, dV without ever writing a
+// [B,h,Nq,Nk] tensor.
+//
+// One work item = (batch b, head h); the CTA walks key tiles (outer) x query tiles (inner), 128 x 128 each (<= 2 x 2):
+//     S  = Q K^T,  dP = dO V^T                 (tcgen05, TMEM cols [0,128) and [128,256))
+//     P  = exp2(S*scale*log2e - m) / sum,  dS = P o (dP - D) * scale,  masked positions: dS = 0 (masked_fill blocks grad)
+//     dV += P^T dO,  dK += dS^T Q              (M = keys: the bf16 P / dS smem tiles are consumed as MN-major A operands)
+//     dQ += dS K                               (same dS tile consumed as a K-major A operand)
+// dV, dK live in TMEM across the query loop, dQ (one 64-column accumulator per query tile) across the key loop.
+// CTA = 6 warps: 0-3 softmax-backward math + epilogues (thread = row), 4 = TMA producer / TMEM allocator, 5 = MMA issuer.
+#include <cfloat>
+
+#include "../../include/b200fm.h"
+#include "attention_common.cuh"
+#include "common.cuh"
+#include "tmap.cuh"
+
+namespace b200fm {
+
+template <int NQT>
+struct AttnBwdSmem {
+    static constexpr int kQ = 0;                       // NQT x 16 KB
+    static constexpr int kDO = NQT * 16384;            // NQT x 16 KB
+    static constexpr int kK = 2 * NQT * 16384;
+    static constexpr int kV = kK + 16384;
+    static constexpr int kP = kV + 16384;              // 32 KB  [128 q][128 keys] bf16, two 64-key swizzle atoms
+    static constexpr int kDS = kP + 32768;             // 32 KB
+    static constexpr int kBar = kDS + 32768;
+    static constexpr int kTotal = kBar + 256 + 1024;
+};
+constexpr int kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
+
+struct AttnBwdArgs {
+    const uint8_t* mask;
+    long long mask_b_stride, mask_q_stride;
+    const __nv_bfloat16* out;  long long ldo;
+    const __nv_bfloat16* dout; long long lddo;
+    const float* stats;
+    __nv_bfloat16* dq; long long lddq;
+    __nv_bfloat16* dk; long long lddk;
+    __nv_bfloat16* dv; long long lddv;
+    int B, H, Nq, Nk, nkt, num_items;
+    float scale, scale_log2;
+};
+
+B200FM_DEVINL void store_row64_bf16(__nv_bfloat16* dst, const uint32_t (&a)[32], const uint32_t (&b)[32]) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        d4[q] = make_uint4(pack_bf16x2(__uint_as_float(a[8 * q]), __uint_as_float(a[8 * q + 1])),
+                           pack_bf16x2(__uint_as_float(a[8 * q + 2]), __uint_as_float(a[8 * q + 3])),
+                           pack_bf16x2(__uint_as_float(a[8 * q + 4]), __uint_as_float(a[8 * q + 5])),
+                           pack_bf16x2(__uint_as_float(a[8 * q + 6]), __uint_as_float(a[8 * q + 7])));
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        d4[4 + q] = make_uint4(pack_bf16x2(__uint_as_float(b[8 * q]), __uint_as_float(b[8 * q + 1])),
+                               pack_bf16x2(__uint_as_float(b[8 * q + 2]), __uint_as_float(b[8 * q + 3])),
+                               pack_bf16x2(__uint_as_float(b[8 * q + 4]), __uint_as_float(b[8 * q + 5])),
+                               pack_bf16x2(__uint_as_float(b[8 * q + 6]), __uint_as_float(b[8 * q + 7])));
+}
+
+template <int NQT>
+__global__ void __launch_bounds__(192, 1)
+attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
+                     const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                     const AttnBwdArgs args) {
+    using SM = AttnBwdSmem<NQT>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kBar);
+    uint64_t* full_q = bars + 0;    uint64_t* free_q = bars + 1;
+    uint64_t* full_kv = bars + 2;   uint64_t* free_kv = bars + 3;
+    uint64_t* sdp_full = bars + 4;  uint64_t* pds_full = bars + 5;
+    uint64_t* dkv_full = bars + 6;  uint64_t* dkv_free = bars + 7;
+    uint64_t* dq_full = bars + 8;   uint64_t* dq_free = bars + 9;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkt = args.nkt;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
+            mbar_init(full_q, 1); mbar_init(free_q, 1); mbar_init(full_kv, 1); mbar_init(free_kv, 1);
+            mbar_init(sdp_full, 1); mbar_init(pds_full, 128); mbar_init(dkv_full, 1); mbar_init(dkv_free, 4);
+            mbar_init(dq_full, 1); mbar_init(dq_free, 4);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            uint32_t it = 0, kvc = 0;
+            for (int item = blockIdx.x; item < args.num_items; item += gridDim.x, ++it) {
+                const int h = item % args.H, b = item / args.H;
+                mbar_wait(free_q, (it & 1) ^ 1);
+                mbar_arrive_expect_tx(full_q, NQT * 2 * 16384);
+#pragma unroll
+                for (int qt = 0; qt < NQT; ++qt) {
+                    tma_load_3d(smem + SM::kQ + qt * 16384, &tmap_q, full_q, h * 64, qt * 128, b);
+                    tma_load_3d(smem + SM::kDO + qt * 16384, &tmap_do, full_q, h * 64, qt * 128, b);
+                }
+                for (int kt = 0; kt < nkt; ++kt, ++kvc) {
+                    mbar_wait(free_kv, (kvc & 1) ^ 1);
+                    mbar_arrive_expect_tx(full_kv, 2 * 16384);
+                    tma_load_3d(smem + SM::kK, &tmap_k, full_kv, h * 64, kt * 128, b);
+                    tma_load_3d(smem + SM::kV, &tmap_v, full_kv, h * 64, kt * 128, b);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            constexpr uint32_t kIdS = make_idesc_bf16(128, 128, false, false);    // S, dP : K-major x K-major
+            constexpr uint32_t kIdT = make_idesc_bf16(128, 64, true, true);       // dV, dK: MN-major A (P^T / dS^T), MN-major B
+            constexpr uint32_t kIdQ = make_idesc_bf16(128, 64, false, true);      // dQ    : K-major A (dS), MN-major B (K)
+            const uint32_t sK = smem_u32(smem + SM::kK), sV = smem_u32(smem + SM::kV), sP = smem_u32(smem + SM::kP),
+                           sDS = smem_u32(smem + SM::kDS);
+            uint32_t it = 0, kvc = 0, stepc = 0;
+            for (int item = blockIdx.x; item < args.num_items; item += gridDim.x, ++it) {
+                mbar_wait(full_q, it & 1);
+                for (int kt = 0; kt < nkt; ++kt, ++kvc) {
+                    mbar_wait(full_kv, kvc & 1);
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int qt = 0; qt < NQT; ++qt, ++stepc) {
+                        const uint32_t sQ = smem_u32(smem + SM::kQ + qt * 16384), sDO = smem_u32(smem + SM::kDO + qt * 16384);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tmem_base + kColS, make_smem_desc(sQ + k * 32, 16, 1024), make_smem_desc(sK + k * 32, 16, 1024), kIdS, k != 0);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tmem_base + kColDP, make_smem_desc(sDO + k * 32, 16, 1024), make_smem_desc(sV + k * 32, 16, 1024), kIdS, k != 0);
+                        umma_commit(sdp_full);
+                        mbar_wait(pds_full, stepc & 1);
+                        if (qt == 0) mbar_wait(dkv_free, (kvc & 1) ^ 1);
+                        if (kt == 0 && qt == 0) mbar_wait(dq_free, (it & 1) ^ 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) {      // K dimension = 128 query rows, 16 per step
+                            umma_bf16(tmem_base + kColDV, make_smem_desc(sP + kk * 2048, 16384, 1024), make_smem_desc(sDO + kk * 2048, 16384, 1024), kIdT, (qt | kk) != 0);
+                            umma_bf16(tmem_base + kColDK, make_smem_desc(sDS + kk * 2048, 16384, 1024), make_smem_desc(sQ + kk * 2048, 16384, 1024), kIdT, (qt | kk) != 0);
+                        }
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk)        // K dimension = 128 keys
+                            umma_bf16(tmem_base + kColDQ + qt * 64, make_smem_desc(sDS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                                      make_smem_desc(sK + kk * 2048, 16384, 1024), kIdQ, (kt | kk) != 0);
+                    }
+                    umma_commit(dkv_full);
+                    umma_commit(free_kv);
+                }
+                umma_commit(dq_full);
+                umma_commit(free_q);
+            }
+        }
+    } else {
+        const int r = warp * 32 + lane;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+        uint8_t* sP = smem + SM::kP;
+        uint8_t* sDS = smem + SM::kDS;
+        uint32_t it = 0, kvc = 0, stepc = 0;
+        for (int item = blockIdx.x; item < args.num_items; item += gridDim.x, ++it) {
+            const int h = item % args.H, b = item / args.H;
+            // per query row: saved statistics and D = rowsum(dO o O)
+            float m_[NQT], inv_[NQT], D_[NQT];
+#pragma unroll
+            for (int qt = 0; qt < NQT; ++qt) {
+                const int qrow = qt * 128 + r;
+                m_[qt] = 0.f; inv_[qt] = 0.f; D_[qt] = 0.f;
+                if (qrow < args.Nq) {
+                    const float2 st = reinterpret_cast<const float2*>(args.stats)[(static_cast<long long>(b) * args.H + h) * args.Nq + qrow];
+                    m_[qt] = st.x; inv_[qt] = st.y;
+                    const uint4* po = reinterpret_cast<const uint4*>(args.out + (static_cast<long long>(b) * args.Nq + qrow) * args.ldo + h * 64);
+                    const uint4* pd = reinterpret_cast<const uint4*>(args.dout + (static_cast<long long>(b) * args.Nq + qrow) * args.lddo + h * 64);
+                    float acc = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint4 a = __ldg(po + q), d = __ldg(pd + q);
+                        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 x = unpack_bf16x2(aw[e]), y = unpack_bf16x2(dw[e]);
+                            acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
+                        }
+                    }
+                    D_[qt] = acc;
+                }
+            }
+            for (int kt = 0; kt < nkt; ++kt, ++kvc) {
+#pragma unroll
+                for (int qt = 0; qt < NQT; ++qt, ++stepc) {
+                    const int qrow = qt * 128 + r;
+                    const bool row_ok = qrow < args.Nq;
+                    const uint8_t* mrow = args.mask ? args.mask + b * args.mask_b_stride + (row_ok ? qrow : 0) * args.mask_q_stride : nullptr;
+                    const float m = m_[qt], inv = inv_[qt], Dr = D_[qt];
+                    mbar_wait(sdp_full, stepc & 1);
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        const int col0 = kt * 128 + c * 32;
+                        uint32_t pk[16], dk_[16];
+                        if (col0 < args.Nk) {
+                            uint32_t ss[32], dd[32];
+                            tmem_ld_x32(t_lane + kColS + c * 32, ss);
+                            tmem_ld_x32(t_lane + kColDP + c * 32, dd);
+                            tmem_ld_wait();
+                            const uint32_t mbits = attn_mask_bits32(mrow, col0, args.Nk);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                float p[2], ds[2];
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    const bool masked = (mbits >> (j + e)) & 1u;
+                                    float t = __uint_as_float(ss[j + e]) * args.scale_log2;
+                                    if (masked) t = kMaskedScore;
+                                    float pe = exp2f(t - m) * inv;
+                                    if (!row_ok || col0 + j + e >= args.Nk) pe = 0.f;
+                                    p[e] = pe;
+                                    ds[e] = masked ? 0.f : pe * (__uint_as_float(dd[j + e]) - Dr) * args.scale;
+                                }
+                                pk[j >> 1] = pack_bf16x2(p[0], p[1]);
+                                dk_[j >> 1] = pack_bf16x2(ds[0], ds[1]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) { pk[j] = 0u; dk_[j] = 0u; }
+                        }
+                        const uint32_t aoff = (c >> 1) * 16384;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t off = aoff + swz128(r, (c & 1) * 4 + q);
+                            *reinterpret_cast<uint4*>(sP + off) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                            *reinterpret_cast<uint4*>(sDS + off) = make_uint4(dk_[4 * q], dk_[4 * q + 1], dk_[4 * q + 2], dk_[4 * q + 3]);
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    tc_fence_before();
+                    mbar_arrive(pds_full);
+                }
+                // dV, dK of this key tile are complete
+                mbar_wait(dkv_full, kvc & 1);
+                tc_fence_after();
+                {
+                    uint32_t a0[32], a1[32];
+                    const int key = kt * 128 + r;
+                    tmem_ld_x32(t_lane + kColDV, a0);
+                    tmem_ld_x32(t_lane + kColDV + 32, a1);
+                    tmem_ld_wait();
+                    if (key < args.Nk) store_row64_bf16(args.dv + (static_cast<long long>(b) * args.Nk + key) * args.lddv + h * 64, a0, a1);
+                    tmem_ld_x32(t_lane + kColDK, a0);
+                    tmem_ld_x32(t_lane + kColDK + 32, a1);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(dkv_free);
+                    if (key < args.Nk) store_row64_bf16(args.dk + (static_cast<long long>(b) * args.Nk + key) * args.lddk + h * 64, a0, a1);
+                }
+            }
+            mbar_wait(dq_full, it & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int qt = 0; qt < NQT; ++qt) {
+                uint32_t a0[32], a1[32];
+                tmem_ld_x32(t_lane + kColDQ + qt * 64, a0);
+                tmem_ld_x32(t_lane + kColDQ + qt * 64 + 32, a1);
+                tmem_ld_wait();
+                const int qrow = qt * 128 + r;
+                if (qrow < args.Nq) store_row64_bf16(args.dq + (static_cast<long long>(b) * args.Nq + qrow) * args.lddq + h * 64, a0, a1);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dq_free);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+template <int NQT>
+static int launch_attn_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& tk, const CUtensorMap& tv,
+                           const AttnBwdArgs& a, cudaStream_t stream) {
+    auto kern = attention_bwd_kernel<NQT>;
+    constexpr int smem = AttnBwdSmem<NQT>::kTotal;
+    static bool configured = false;
+    if (!configured) {
+        B200FM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = a.num_items < sms ? a.num_items : sms;
+    kern<<<grid, 192, smem, stream>>>(tq, tdo, tk, tv, a);
+    B200FM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace b200fm
+
+using namespace b200fm;
+
+extern "C" int b200fm_attention_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                                    const uint8_t* mask, long long mask_b_stride, long long mask_q_stride, const void* out,
+                                    long long ldo, const void* dout, long long lddo, const float* stats, void* dq, long long lddq,
+                                    void* dk, long long lddk, void* dv, long long lddv, int B, int H, int Nq, int Nk, float scale,
+                                    void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (B == 0 || H == 0 || Nq == 0) return 0;
+    B200FM_CHECK(q && k && v && out && dout && stats && dq && dk && dv, "attention_bwd: null pointer");
+    B200FM_CHECK(Nk >= 1 && Nk <= 256 && Nq <= 256, "attention_bwd: (Nq=%d, Nk=%d) outside the supported range (<= 256)", Nq, Nk);
+    B200FM_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0,
+                 "attention_bwd: row strides must be multiples of 8 elements");
+    CUtensorMap tq, tdo, tk, tv;
+    int rc;
+    if ((rc = make_tmap_3d(&tq, q, TmapDtype::BF16, (uint64_t)H * 64, Nq, B, (uint64_t)ldq * 2, (uint64_t)Nq * ldq * 2, 64, 128, true))) return rc;
+    if ((rc = make_tmap_3d(&tdo, dout, TmapDtype::BF16, (uint64_t)H * 64, Nq, B, (uint64_t)lddo * 2, (uint64_t)Nq * lddo * 2, 64, 128, true))) return rc;
+    if ((rc = make_tmap_3d(&tk, k, TmapDtype::BF16, (uint64_t)H * 64, Nk, B, (uint64_t)ldk * 2, (uint64_t)Nk * ldk * 2, 64, 128, true))) return rc;
+    if ((rc = make_tmap_3d(&tv, v, TmapDtype::BF16, (uint64_t)H * 64, Nk, B, (uint64_t)ldv * 2, (uint64_t)Nk * ldv * 2, 64, 128, true))) return rc;
+    AttnBwdArgs a;
+    a.mask = mask; a.mask_b_stride = mask_b_stride; a.mask_q_stride = mask_q_stride;
+    a.out = reinterpret_cast<const __nv_bfloat16*>(out); a.ldo = ldo;
+    a.dout = reinterpret_cast<const __nv_bfloat16*>(dout); a.lddo = lddo;
+    a.stats = stats;
+    a.dq = reinterpret_cast<__nv_bfloat16*>(dq); a.lddq = lddq;
+    a.dk = reinterpret_cast<__nv_bfloat16*>(dk); a.lddk = lddk;
+    a.dv = reinterpret_cast<__nv_bfloat16*>(dv); a.lddv = lddv;
+    a.B = B; a.H = H; a.Nq = Nq; a.Nk = Nk; a.nkt = (Nk + 127) / 128; a.num_items = B * H;
+    a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
+    return Nq <= 128 ? launch_attn_bwd<1>(tq, tdo, tk, tv, a, stream) : launch_attn_bwd<2>(tq, tdo, tk, tv, a, stream);
+}

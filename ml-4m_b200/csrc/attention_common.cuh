@@ -1,0 +1,36 @@
+// Helpers shared by the attention forward / backward kernels.
+#pragma once
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace b200fm {
+
+// Finite stand-in for masked_fill(mask, -finfo.max) (fm_utils.py:169): large enough that exp2(masked - max) == 0 whenever
+// the row has one unmasked key, equal for all masked keys so a fully masked row is uniform.  Applied AFTER the
+// scale*log2e multiplication, so no overflow to -inf can occur.
+constexpr float kMaskedScore = -3.0e38f;
+
+B200FM_DEVINL uint32_t nonzero_bytes_to_bits(uint32_t w) {
+    const uint32_t m = __vcmpne4(w, 0u) & 0x01010101u;
+    return (m & 1u) | ((m >> 7) & 2u) | ((m >> 14) & 4u) | ((m >> 21) & 8u);
+}
+
+// Bit j set <=> key (col0 + j) is masked for this query row; keys >= Nk report 0.  mrow may be nullptr (no mask).
+B200FM_DEVINL uint32_t attn_mask_bits32(const uint8_t* mrow, int col0, int Nk) {
+    if (mrow == nullptr) return 0u;
+    const uint8_t* p = mrow + col0;
+    uint32_t bits = 0u;
+    if (col0 + 32 <= Nk && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+        bits = nonzero_bytes_to_bits(a.x) | (nonzero_bytes_to_bits(a.y) << 4) | (nonzero_bytes_to_bits(a.z) << 8) |
+               (nonzero_bytes_to_bits(a.w) << 12) | (nonzero_bytes_to_bits(b.x) << 16) | (nonzero_bytes_to_bits(b.y) << 20) |
+               (nonzero_bytes_to_bits(b.z) << 24) | (nonzero_bytes_to_bits(b.w) << 28);
+    } else {
+        for (int j = 0; j < 32 && col0 + j < Nk; ++j) bits |= (__ldg(p + j) != 0 ? 1u : 0u) << j;
+    }
+    return bits;
+}
+
+}  // namespace b200fm

@@ -1,0 +1,263 @@
+// HBM-bound element-wise and row-wise kernels around the GEMMs: gated-MLP / GELU backward, the masked-token head's
+// cross-entropy (forward + gradient in one pass), bias-gradient column sums, fp32->bf16 weight shadow casts, pixel
+// patchify, fused AdamW.  All use 16-byte vector accesses; grids are sized in multiples of the SM count.
+#include <cfloat>
+
+#include "../../include/b200fm.h"
+#include "common.cuh"
+
+namespace b200fm {
+
+static int sm_count_ew() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+static int ew_grid(long long work_items, int threads) {
+    long long blocks = (work_items + threads - 1) / threads;
+    const long long cap = (long long)sm_count_ew() * 8;
+    return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+// ---- SwiGLU backward (fm_utils.py:143: fc2(silu(fc1 x) * fc3 x)) ------------------------------------------------
+// ab bf16 [R, 2H] = [a | b] (saved pre-activations), dg bf16 [R, H] -> dab bf16 [R, 2H] = [da | db]
+//   s = sigmoid(a); da = dg * b * s * (1 + a * (1 - s)); db = dg * a * s
+__global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ ab, const __nv_bfloat16* __restrict__ dg,
+                                  __nv_bfloat16* __restrict__ dab, long long R, int H, long long ld_ab, long long ld_dg,
+                                  long long ld_dab) {
+    const int hv = H / 8;
+    const long long total = R * hv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / hv;
+        const int c = (int)(i % hv) * 8;
+        const uint4 av = *reinterpret_cast<const uint4*>(ab + row * ld_ab + c);
+        const uint4 bv = *reinterpret_cast<const uint4*>(ab + row * ld_ab + H + c);
+        const uint4 gv = *reinterpret_cast<const uint4*>(dg + row * ld_dg + c);
+        const uint32_t aw[4] = {av.x, av.y, av.z, av.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+        uint32_t da[4], db[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 a = unpack_bf16x2(aw[e]), b = unpack_bf16x2(bw[e]), g = unpack_bf16x2(gw[e]);
+            const float s0 = 1.0f / (1.0f + __expf(-a.x)), s1 = 1.0f / (1.0f + __expf(-a.y));
+            da[e] = pack_bf16x2(g.x * b.x * s0 * (1.0f + a.x * (1.0f - s0)), g.y * b.y * s1 * (1.0f + a.y * (1.0f - s1)));
+            db[e] = pack_bf16x2(g.x * a.x * s0, g.y * a.y * s1);
+        }
+        *reinterpret_cast<uint4*>(dab + row * ld_dab + c) = make_uint4(da[0], da[1], da[2], da[3]);
+        *reinterpret_cast<uint4*>(dab + row * ld_dab + H + c) = make_uint4(db[0], db[1], db[2], db[3]);
+    }
+}
+
+// ---- GELU / tanh backward: dpre = dact * f'(pre), bf16 [R, N] -----------------------------------------------------
+template <int ACT>   // 0 = GELU (erf), 1 = tanh
+__global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dact,
+                               __nv_bfloat16* __restrict__ dpre, long long n8) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 pv = reinterpret_cast<const uint4*>(pre)[i], gv = reinterpret_cast<const uint4*>(dact)[i];
+        const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 x = unpack_bf16x2(pw[e]), g = unpack_bf16x2(gw[e]);
+            float d0, d1;
+            if (ACT == 0) {
+                d0 = 0.5f * (1.0f + erff(x.x * 0.70710678f)) + x.x * 0.3989422804f * __expf(-0.5f * x.x * x.x);
+                d1 = 0.5f * (1.0f + erff(x.y * 0.70710678f)) + x.y * 0.3989422804f * __expf(-0.5f * x.y * x.y);
+            } else {
+                const float t0 = tanhf(x.x), t1 = tanhf(x.y);
+                d0 = 1.0f - t0 * t0; d1 = 1.0f - t1 * t1;
+            }
+            o[e] = pack_bf16x2(g.x * d0, g.y * d1);
+        }
+        reinterpret_cast<uint4*>(dpre)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ---- cross-entropy over fp32 logits (fm.py:597 F.cross_entropy, fp32 under autocast) --------------------------------
+// One CTA per row.  loss_row[i] = logsumexp(l_i) - l_i[target_i];  dlogits bf16 [n, V] = softmax(l_i) - onehot(target_i)
+// (unscaled: the 1/n mean factor and the upstream gradient are folded into the following GEMMs via alpha_dev).
+__global__ void __launch_bounds__(256)
+cross_entropy_kernel(const float* __restrict__ logits, long long ld, const int64_t* __restrict__ targets,
+                     float* __restrict__ loss_rows, __nv_bfloat16* __restrict__ dlogits, long long ldd, int V) {
+    __shared__ float red[8];
+    __shared__ float bc;
+    const long long row = blockIdx.x;
+    const float* l = logits + row * ld;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float m = -INFINITY;
+    for (int j = tid; j < V; j += 256) m = fmaxf(m, l[j]);
+    m = warp_max(m);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    if (tid == 0) { float x = red[0]; for (int w = 1; w < 8; ++w) x = fmaxf(x, red[w]); bc = x; }
+    __syncthreads();
+    m = bc;
+    float s = 0.f;
+    for (int j = tid; j < V; j += 256) s += __expf(l[j] - m);
+    s = warp_sum(s);
+    __syncthreads();
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (tid == 0) { float x = 0.f; for (int w = 0; w < 8; ++w) x += red[w]; bc = x; }
+    __syncthreads();
+    s = bc;
+    const int t = (int)targets[row];
+    if (tid == 0) loss_rows[row] = (m + logf(s)) - l[t];
+    if (dlogits != nullptr) {
+        const float inv = 1.0f / s;
+        __nv_bfloat16* d = dlogits + row * ldd;
+        for (int j = tid * 2; j < V; j += 512) {
+            const float p0 = __expf(l[j] - m) * inv - (j == t ? 1.0f : 0.0f);
+            if (j + 1 < V) {
+                const float p1 = __expf(l[j + 1] - m) * inv - (j + 1 == t ? 1.0f : 0.0f);
+                *reinterpret_cast<uint32_t*>(d + j) = pack_bf16x2(p0, p1);
+            } else {
+                d[j] = __float2bfloat16_rn(p0);
+            }
+        }
+    }
+}
+
+// ---- column sums (bias gradients): out[c] += sum_r x[r, c], x bf16 [R, N] ------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restrict__ out, long long R, int N, int rows_per_block) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    if (c >= N) return;
+    float s = 0.f;
+    const long long r1 = r0 + rows_per_block < R ? r0 + rows_per_block : R;
+    for (long long r = r0; r < r1; ++r) s += __bfloat162float(x[r * ld + c]);
+    atomicAdd(out + c, s);
+}
+
+// ---- fp32 -> bf16 cast (weight shadows; also activations) ----------------------------------------------------------
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+    const long long n4 = n / 4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) y[n4 * 4 + threadIdx.x] = __float2bfloat16_rn(x[n4 * 4 + threadIdx.x]);
+}
+
+// ---- patchify (encoder_embeddings.py:301): img fp32 [B,C,H,W] -> bf16 [B*nh*nw, ph*pw*C] in '(ph pw c)' order ------
+__global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int C, int Himg, int Wimg, int P) {
+    const int nh = Himg / P, nw = Wimg / P;
+    const long long total = (long long)B * nh * nw * P * P * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long t = i;
+        const int c = (int)(t % C); t /= C;
+        const int pw = (int)(t % P); t /= P;
+        const int ph = (int)(t % P); t /= P;
+        const int iw = (int)(t % nw); t /= nw;
+        const int ih = (int)(t % nh); t /= nh;
+        const int b = (int)t;
+        out[i] = __float2bfloat16_rn(img[(((long long)b * C + c) * Himg + ih * P + ph) * Wimg + iw * P + pw]);
+    }
+}
+
+// ---- fused AdamW (torch.optim.AdamW semantics, optim_factory.py:239-240), optional bf16 shadow of the new weight ------
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                             __nv_bfloat16* __restrict__ shadow, long long n, float lr, float beta1, float beta2, float eps,
+                             float wd, float bc1, float bc2_sqrt, float grad_scale) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = g[i] * grad_scale;
+        float pi = p[i] * (1.0f - lr * wd);
+        const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        pi -= (lr / bc1) * (mi / denom);
+        p[i] = pi; m[i] = mi; v[i] = vi;
+        if (shadow) shadow[i] = __float2bfloat16_rn(pi);
+    }
+}
+
+}  // namespace b200fm
+
+using namespace b200fm;
+
+extern "C" int b200fm_swiglu_bwd(const void* ab, long long ld_ab, const void* dg, long long ld_dg, void* dab, long long ld_dab,
+                                 long long R, int H, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (R == 0) return 0;
+    B200FM_CHECK(ab && dg && dab, "swiglu_bwd: null pointer");
+    B200FM_CHECK(H % 8 == 0 && ld_ab % 8 == 0 && ld_dg % 8 == 0 && ld_dab % 8 == 0, "swiglu_bwd: H and strides must be multiples of 8");
+    swiglu_bwd_kernel<<<ew_grid(R * (H / 8), 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(ab), reinterpret_cast<const __nv_bfloat16*>(dg),
+                                                                  reinterpret_cast<__nv_bfloat16*>(dab), R, H, ld_ab, ld_dg, ld_dab);
+    B200FM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200fm_act_bwd(int act, const void* pre, const void* dact, void* dpre, long long n, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (n == 0) return 0;
+    B200FM_CHECK(pre && dact && dpre, "act_bwd: null pointer");
+    B200FM_CHECK(n % 8 == 0, "act_bwd: element count must be a multiple of 8");
+    B200FM_CHECK(act == 0 || act == 1, "act_bwd: act must be 0 (gelu) or 1 (tanh)");
+    const int grid = ew_grid(n / 8, 256);
+    if (act == 0) act_bwd_kernel<0><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(pre), reinterpret_cast<const __nv_bfloat16*>(dact), reinterpret_cast<__nv_bfloat16*>(dpre), n / 8);
+    else act_bwd_kernel<1><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(pre), reinterpret_cast<const __nv_bfloat16*>(dact), reinterpret_cast<__nv_bfloat16*>(dpre), n / 8);
+    B200FM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200fm_cross_entropy(const float* logits, long long ld, const int64_t* targets, float* loss_rows, void* dlogits,
+                                    long long ldd, long long n, int V, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (n == 0) return 0;
+    B200FM_CHECK(logits && targets && loss_rows, "cross_entropy: null pointer");
+    B200FM_CHECK(V > 0 && (dlogits == nullptr || ldd % 2 == 0), "cross_entropy: bad V / dlogits stride");
+    cross_entropy_kernel<<<(unsigned)n, 256, 0, stream>>>(logits, ld, targets, loss_rows, reinterpret_cast<__nv_bfloat16*>(dlogits), ldd, V);
+    B200FM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200fm_colsum_bf16(const void* x, long long ld, float* out, long long R, int N, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (R == 0 || N == 0) return 0;
+    B200FM_CHECK(x && out, "colsum: null pointer");
+    const int rpb = 256;
+    dim3 grid((N + 255) / 256, (unsigned)((R + rpb - 1) / rpb));
+    colsum_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, out, R, N, rpb);
+    B200FM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200fm_cast_f32_bf16(const float* x, void* y, long long n, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (n == 0) return 0;
+    B200FM_CHECK(x && y, "cast: null pointer");
+    B200FM_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0, "cast: misaligned buffers");
+    cast_f32_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n);
+    B200FM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200fm_patchify(const float* img, void* out, int B, int C, int H, int W, int P, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (B == 0) return 0;
+    B200FM_CHECK(img && out, "patchify: null pointer");
+    B200FM_CHECK(P > 0 && H % P == 0 && W % P == 0, "Image sizes %dx%d must be divisible by patch sizes %dx%d", H, W, P, P);
+    const long long total = (long long)B * C * H * W;
+    patchify_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(img, reinterpret_cast<__nv_bfloat16*>(out), B, C, H, W, P);
+    B200FM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200fm_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr, float beta1,
+                            float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (n == 0) return 0;
+    B200FM_CHECK(p && g && m && v, "adamw: null pointer");
+    B200FM_CHECK(step >= 1, "adamw: step must be >= 1");
+    const float bc1 = 1.0f - powf(beta1, (float)step);
+    const float bc2s = sqrtf(1.0f - powf(beta2, (float)step));
+    adamw_kernel<<<ew_grid(n, 256), 256, 0, stream>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n, lr, beta1, beta2, eps,
+                                                    weight_decay, bc1, bc2s, grad_scale);
+    B200FM_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -59,6 +59,27 @@ int make_tmap_2d(CUtensorMap* out, const void* base, TmapDtype dt, uint64_t inne
     return 0;
 }
 
+int make_tmap_3d(CUtensorMap* out, const void* base, TmapDtype dt, uint64_t inner, uint64_t d1, uint64_t d2,
+                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box_inner, uint32_t box_d1, bool swizzle128) {
+    EncodeTiledFn fn = get_encode_fn();
+    B200FM_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+    const uint32_t es = dt == TmapDtype::BF16 ? 2 : 4;
+    B200FM_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer %p not 16-byte aligned", base);
+    B200FM_CHECK(stride1_bytes % 16 == 0 && stride2_bytes % 16 == 0, "TMA strides (%llu, %llu) B not multiples of 16",
+                 (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes);
+    B200FM_CHECK(!swizzle128 || box_inner * es == 128, "128B swizzle needs a 128-byte inner box (got %u)", box_inner * es);
+    cuuint64_t dims[3] = {inner, d1, d2};
+    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    cuuint32_t box[3] = {box_inner, box_d1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, dt == TmapDtype::BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200FM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
+    return 0;
+}
+
 }  // namespace b200fm
 
 extern "C" {
