@@ -101,6 +101,10 @@ int b200fm_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16
  * 280-309; fourm/models/decoder_embeddings.py:98-139, 226-255).  One b200fm_segment per modality, in concatenation order
  * (mod_dict order on the encoder side; the Python-`random` shuffled order of fm.py:306 on the decoder side).          */
 #define B200FM_MAX_SEGMENTS 24
+/* `mode` flags of select_plan / embed_rows / embed_rows_bwd */
+#define B200FM_MODE_DECODER 1  /* decoder side: teacher-forcing shift for sequences, mask token for images, targets + dam   */
+#define B200FM_MODE_IDENTITY 2 /* keep every position in place (materialise a whole modality: embedding modules' forward)    */
+#define B200FM_MODE_NO_SUM 4   /* x0 = x instead of x + emb                                                                 */
 #define B200FM_KIND_IMG 0     /* pixel patches: x rows come from the patch-projection GEMM (x_rows)  */
 #define B200FM_KIND_TOK_IMG 1 /* tokenised image: ids [B, L]                                         */
 #define B200FM_KIND_SEQ 2     /* token sequence: ids [B, L], decoder side uses the teacher-forcing shift */
@@ -128,19 +132,19 @@ typedef struct b200fm_segment {
  * Outputs [B, n_keep]: src_seg (segment index), src_pos (position inside the segment), pos_id (positional-table row, -1 = none),
  * pad_mask (1 = padded slot: the reference's encoder_mask / decoder_mask), mod_mask (int16, -1 on pads), mod_raw (before the
  * -1 assignment: needed by the attention mask), and on the decoder side target_ids (int64, 0 on pads) and dam (int32).     */
-int b200fm_select_plan(const b200fm_segment* segs, int n_seg, int decoder, int B, int n_keep, int32_t* src_seg, int32_t* src_pos,
+int b200fm_select_plan(const b200fm_segment* segs, int n_seg, int mode, int B, int n_keep, int32_t* src_seg, int32_t* src_pos,
                        int32_t* pos_id, uint8_t* pad_mask, int16_t* mod_mask, int16_t* mod_raw, int64_t* target_ids,
                        int32_t* dam_out, void* stream);
 /* mask_out uint8 [B, M, M], 1 = masked: (j >= cumsum(dam)[i]) | (mod_raw[i] != mod_raw[j])  (or triu(1) if causal).          */
 int b200fm_decoder_attention_mask(const int32_t* dam, const int16_t* mod_raw, uint8_t* mask_out, int B, int M, int causal, int sep,
                                   void* stream);
 /* x0 fp32 [B, n_keep, D] = x + emb, emb_out (optional) fp32 = pos + mod; padded slots are zero.                               */
-int b200fm_embed_rows(const b200fm_segment* segs, int n_seg, int decoder, const int32_t* src_seg, const int32_t* src_pos,
+int b200fm_embed_rows(const b200fm_segment* segs, int n_seg, int mode, const int32_t* src_seg, const int32_t* src_pos,
                       const int32_t* pos_id, const uint8_t* pad_mask, const float* mask_token, float* x0, float* emb_out, int B,
                       int n_keep, int D, void* stream);
 /* Backward of embed_rows: dx0 (and demb, optional) fp32 [B, n_keep, D] -> scatter-add into d_token_emb / d_mod_emb / dx_rows of
  * each segment and d_mask_token (decoder image modalities).                                                                 */
-int b200fm_embed_rows_bwd(const b200fm_segment* segs, int n_seg, int decoder, const int32_t* src_seg, const int32_t* src_pos,
+int b200fm_embed_rows_bwd(const b200fm_segment* segs, int n_seg, int mode, const int32_t* src_seg, const int32_t* src_pos,
                           const uint8_t* pad_mask, const float* dx0, const float* demb, float* d_mask_token, int B, int n_keep,
                           int D, void* stream);
 /* Masked-token head index sets (fm.py:589-600 `y[decoder_mod_mask == idx]`): rows_out int32 [n_mods, n_rows] (row-major order,
@@ -149,6 +153,8 @@ int b200fm_head_rows(const int16_t* mod_mask, long long n_rows, const int* mod_i
                      int32_t* counts, void* stream);
 int b200fm_gather_rows_bf16(const void* src, const int32_t* rows, void* out, long long n, int D, void* stream);
 int b200fm_gather_i64(const int64_t* src, const int32_t* rows, int64_t* out, long long n, void* stream);
+/* dst bf16 [*, D] row rows[i] = src bf16 [n, D] row i (backward of gather_rows_bf16; distinct destination rows).           */
+int b200fm_scatter_rows_bf16(const void* src, const int32_t* rows, void* dst, long long n, int D, void* stream);
 /* dst fp32 [*, D] rows[i] += src bf16 [n, D] row i (distinct destination rows).                                             */
 int b200fm_scatter_add_rows(const void* src_bf16, const int32_t* rows, float* dst, long long n, int D, void* stream);
 

@@ -1,0 +1,370 @@
+"""Autograd functions over the C-ABI kernels: the differentiable building blocks of the 4M block stack.
+
+Numerical contract (mirrors the reference under torch.autocast(bf16)): the residual stream is fp32;
+LayerNorm statistics are fp32 and its output is consumed as bf16; every Linear / attention contraction takes bf16
+operands with fp32 accumulation and produces bf16; weight gradients are produced in fp32 directly (the reference rounds
+them to bf16 first).  Master weights stay fp32 `nn.Parameter`s; their bf16 shadows are cached per parameter version.
+"""
+import torch
+
+from . import ops
+
+# ----------------------------------------------------------------------------------------------------------------------
+# bf16 weight shadows
+# ----------------------------------------------------------------------------------------------------------------------
+_shadow = {}
+
+
+def _pad_rows(n, mult=8):
+    return (n + mult - 1) // mult * mult
+
+
+def weight_bf16(*params):
+    """bf16 copy of one fp32 weight, or of several concatenated along dim 0 (e.g. [fc1; fc3]), refreshed when any
+    source tensor's version counter changes (optimizer steps, load_state_dict).  Rows are zero-padded to a multiple of 8."""
+    key = tuple(id(p) for p in params)
+    ver = tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)
+    hit = _shadow.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    with torch.no_grad():
+        rows = [p.shape[0] for p in params]
+        cols = params[0].shape[1]
+        prow = [_pad_rows(r) for r in rows] if len(params) > 1 else rows
+        buf = hit[1] if hit is not None and hit[1].shape == (sum(prow), cols) else None
+        if buf is None:
+            buf = torch.zeros(sum(prow), cols, device=params[0].device, dtype=torch.bfloat16)
+        off = 0
+        for p, r, pr in zip(params, rows, prow):
+            src = p.detach()
+            if src.dtype != torch.float32 or not src.is_contiguous():
+                src = src.float().contiguous()
+            ops.cast_bf16(src, buf[off:off + r])
+            off += pr
+    _shadow[key] = (ver, buf)
+    return buf
+
+
+def clear_weight_cache():
+    _shadow.clear()
+
+
+def _as2d(x):
+    return x.reshape(-1, x.shape[-1])
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# LayerNorm
+# ----------------------------------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    """y = LayerNorm(x) with fp32 statistics; y is bf16 (feeds a GEMM) or fp32.  (fm_utils.py:93-108)"""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_bf16):
+        x2 = _as2d(x).contiguous()
+        if x2.dtype != torch.float32:
+            x2 = x2.float()
+        y, mean, rstd = ops.layernorm_fwd(x2, weight, bias, eps, out_bf16=out_bf16)
+        ctx.save_for_backward(x2, weight, mean, rstd)
+        ctx.has_bias = bias is not None and bias.requires_grad
+        ctx.shape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight, mean, rstd = ctx.saved_tensors
+        dy2 = _as2d(dy).contiguous()
+        D = x2.shape[1]
+        dgamma = torch.zeros(D, device=x2.device, dtype=torch.float32) if weight.requires_grad else None
+        dbeta = torch.zeros(D, device=x2.device, dtype=torch.float32) if ctx.has_bias else None
+        dx, _ = ops.layernorm_bwd(dy2, x2, weight, mean, rstd, dgamma=dgamma, dbeta=dbeta)
+        return dx.view(ctx.shape), dgamma, dbeta, None, None
+
+
+def layer_norm(x, weight, bias, eps=1e-6, out_bf16=True):
+    return LayerNormFn.apply(x, weight, bias, eps, out_bf16)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Linear family
+# ----------------------------------------------------------------------------------------------------------------------
+def _to_bf16_2d(x):
+    x2 = _as2d(x)
+    if x2.dtype == torch.float32:
+        return ops.cast_bf16(x2.contiguous())
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    return x2
+
+
+def _linear_bwd(ctx, dy2, x2, weight, want_dx=True):
+    """dx = dy W (NN), dW = dy^T x (TN, fp32), db = colsum(dy)."""
+    wb = weight_bf16(weight)[:weight.shape[0]]
+    dx = ops.gemm(dy2, wb, layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16) if want_dx else None
+    dw = ops.gemm(dy2, x2, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if weight.requires_grad else None
+    return dx, dw
+
+
+class LinearFn(torch.autograd.Function):
+    """y(bf16) = x W^T (+ b).  nn.Linear under autocast (fm_utils.py:155-157 etc.)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2 = _to_bf16_2d(x)
+        y = ops.gemm(x2, weight_bf16(weight), epilogue=ops.EPI_BF16, bias=bias, n_out=weight.shape[0])
+        ctx.save_for_backward(x2, weight)
+        ctx.has_bias = bias is not None
+        ctx.in_shape = x.shape
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight = ctx.saved_tensors
+        dy2 = _to_bf16_2d(dy)
+        dx, dw = _linear_bwd(ctx, dy2, x2, weight, ctx.needs_input_grad[0])
+        db = ops.colsum_bf16(dy2) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return (dx.view(ctx.in_shape) if dx is not None else None), dw, db
+
+
+class LinearF32Fn(torch.autograd.Function):
+    """y(fp32) = x W^T : logits (decoder_embeddings.py:141-152) when the caller wants them materialised."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        x2 = _to_bf16_2d(x)
+        y = ops.gemm(x2, weight_bf16(weight), epilogue=ops.EPI_F32, n_out=weight.shape[0])
+        ctx.save_for_backward(x2, weight)
+        ctx.in_shape = x.shape
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight = ctx.saved_tensors
+        dy2 = _to_bf16_2d(dy)
+        dx, dw = _linear_bwd(ctx, dy2, x2, weight, ctx.needs_input_grad[0])
+        return (dx.view(ctx.in_shape) if dx is not None else None), dw
+
+
+class LinearResidualFn(torch.autograd.Function):
+    """out(fp32) = resid(fp32) + bf16(x W^T + b):   x = x + proj(...) / x = x + fc2(...) (fm_utils.py:332-334)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, resid):
+        x2 = _to_bf16_2d(x)
+        r2 = _as2d(resid).contiguous()
+        out = ops.gemm(x2, weight_bf16(weight), epilogue=ops.EPI_RESID, bias=bias, resid=r2, n_out=weight.shape[0])
+        ctx.save_for_backward(x2, weight)
+        ctx.has_bias = bias is not None
+        ctx.in_shape = x.shape
+        return out.view(resid.shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, weight = ctx.saved_tensors
+        d2 = _as2d(dout).contiguous()
+        dy2 = ops.cast_bf16(d2) if d2.dtype == torch.float32 else d2
+        dx, dw = _linear_bwd(ctx, dy2, x2, weight, ctx.needs_input_grad[0])
+        db = ops.colsum_bf16(dy2) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return (dx.view(ctx.in_shape) if dx is not None else None), dw, db, dout
+
+
+class SwiGLUFn(torch.autograd.Function):
+    """g(bf16) = silu(x W1^T) * (x W3^T) with [W1; W3] streamed as one B operand (fm_utils.py:129-144)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, w3, b1, b3):
+        x2 = _to_bf16_2d(x)
+        H = w1.shape[0]
+        Hp = _pad_rows(H)
+        w13 = weight_bf16(w1, w3)                                   # [2*Hp, D], rows zero-padded to a multiple of 8
+        bias = None
+        if b1 is not None:
+            bias = torch.zeros(2 * Hp, device=x2.device, dtype=torch.float32)
+            bias[:H] = b1
+            bias[Hp:Hp + H] = b3
+        ab, g = ops.gemm(x2, w13, epilogue=ops.EPI_SWIGLU, bias=bias)
+        ctx.save_for_backward(x2, w1, w3, ab)
+        ctx.H, ctx.Hp, ctx.has_bias, ctx.in_shape = H, Hp, b1 is not None, x.shape
+        return g[:, :H].view(*x.shape[:-1], H) if Hp != H else g.view(*x.shape[:-1], H)
+
+    @staticmethod
+    def backward(ctx, dg):
+        x2, w1, w3, ab = ctx.saved_tensors
+        H, Hp = ctx.H, ctx.Hp
+        dg2 = _as2d(dg)
+        if Hp != H:
+            pad = torch.zeros(dg2.shape[0], Hp, device=dg2.device, dtype=torch.bfloat16)
+            pad[:, :H] = dg2
+            dg2 = pad
+        elif dg2.stride(-1) != 1 or dg2.dtype != torch.bfloat16:
+            dg2 = _to_bf16_2d(dg2)
+        dab = ops.swiglu_bwd(ab, dg2)                               # [R, 2*Hp] = [da | db]
+        w13 = weight_bf16(w1, w3)
+        dx = ops.gemm(dab, w13, layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16) if ctx.needs_input_grad[0] else None
+        dw1 = dw3 = db1 = db3 = None
+        if w1.requires_grad or w3.requires_grad:
+            dw13 = ops.gemm(dab, x2, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32)      # [2*Hp, D]
+            dw1, dw3 = dw13[:H], dw13[Hp:Hp + H]
+        if ctx.has_bias:
+            dbias = ops.colsum_bf16(dab)
+            db1, db3 = dbias[:H], dbias[Hp:Hp + H]
+        return (dx.view(ctx.in_shape) if dx is not None else None), dw1, dw3, db1, db3
+
+
+class MlpActFn(torch.autograd.Function):
+    """act(bf16) = GELU(x W^T + b) with the pre-activation saved by the same GEMM epilogue (fm_utils.py:111-126)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2 = _to_bf16_2d(x)
+        pre, act = ops.gemm(x2, weight_bf16(weight), epilogue=ops.EPI_GELU, bias=bias, n_out=weight.shape[0])
+        ctx.save_for_backward(x2, weight, pre)
+        ctx.has_bias, ctx.in_shape = bias is not None, x.shape
+        return act.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dact):
+        x2, weight, pre = ctx.saved_tensors
+        dpre = ops.act_bwd(pre, _to_bf16_2d(dact).contiguous(), "gelu")
+        dx, dw = _linear_bwd(ctx, dpre, x2, weight, ctx.needs_input_grad[0])
+        db = ops.colsum_bf16(dpre) if ctx.has_bias else None
+        return (dx.view(ctx.in_shape) if dx is not None else None), dw, db
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# attention
+# ----------------------------------------------------------------------------------------------------------------------
+class AttentionFn(torch.autograd.Function):
+    """softmax(q k^T * scale, masked) v per head on 2-D row views (fm_utils.py:160-180 / 197-219).
+    q [B*Nq, H*64], k / v [B*Nk, H*64] bf16 (column slices of packed qkv / kv buffers are fine)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, mask, B, H, Nq, Nk, scale):
+        out, stats = ops.attention_fwd(q, k, v, B, H, Nq, Nk, mask, scale)
+        ctx.save_for_backward(q, k, v, out, stats, mask)
+        ctx.dims = (B, H, Nq, Nk, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, out, stats, mask = ctx.saved_tensors
+        B, H, Nq, Nk, scale = ctx.dims
+        if dout.stride(-1) != 1:
+            dout = dout.contiguous()
+        D = H * 64
+        # q/k/v that are slices of one packed buffer get their gradients written into one packed buffer too, so the
+        # following dgrad / wgrad GEMMs read a single [rows, 3D] (or [rows, 2D]) operand.
+        packed_qkv = (q.data_ptr() + 2 * D == k.data_ptr() and k.data_ptr() + 2 * D == v.data_ptr() and q.stride(0) == 3 * D)
+        packed_kv = (not packed_qkv) and (k.data_ptr() + 2 * D == v.data_ptr() and k.stride(0) == 2 * D)
+        if packed_qkv:
+            buf = torch.empty(q.shape[0], 3 * D, device=q.device, dtype=torch.bfloat16)
+            dq, dk, dv = buf[:, :D], buf[:, D:2 * D], buf[:, 2 * D:]
+        elif packed_kv:
+            dq = torch.empty(q.shape[0], D, device=q.device, dtype=torch.bfloat16)
+            buf = torch.empty(k.shape[0], 2 * D, device=q.device, dtype=torch.bfloat16)
+            dk, dv = buf[:, :D], buf[:, D:]
+        else:
+            dq = dk = dv = None
+        dq, dk, dv = ops.attention_bwd(q, k, v, out, dout, stats, B, H, Nq, Nk, mask, scale, dq, dk, dv)
+        return dq, dk, dv, None, None, None, None, None, None
+
+
+def attention(q, k, v, mask, B, H, Nq, Nk, scale):
+    return AttentionFn.apply(q, k, v, mask, B, H, Nq, Nk, scale)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# masked-token head: logits GEMM + cross-entropy, gradient kept as bf16 (softmax - onehot)
+# ----------------------------------------------------------------------------------------------------------------------
+class LinearCrossEntropyFn(torch.autograd.Function):
+    """mean_i CE(h_i W^T, t_i)  (fm.py:592-598).  h bf16 [n, D], W fp32 master [V, D], targets int64 [n]."""
+
+    @staticmethod
+    def forward(ctx, h, weight, targets):
+        wb = weight_bf16(weight)
+        logits = ops.gemm(h, wb, epilogue=ops.EPI_F32, n_out=weight.shape[0])
+        loss_rows, dlogits = ops.cross_entropy(logits, targets, want_grad=True)
+        del logits
+        ctx.save_for_backward(h, weight, dlogits)
+        return loss_rows.mean()
+
+    @staticmethod
+    def backward(ctx, dloss):
+        h, weight, dlogits = ctx.saved_tensors
+        n = h.shape[0]
+        coef = (dloss.float() / n).reshape(1).contiguous()             # stays on the device
+        wb = weight_bf16(weight)[:weight.shape[0]]
+        dh = ops.gemm(dlogits, wb, layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16, alpha_dev=coef) if ctx.needs_input_grad[0] else None
+        dw = ops.gemm(dlogits, h, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32, alpha_dev=coef) if weight.requires_grad else None
+        return dh, dw, None
+
+
+class HeadGatherFn(torch.autograd.Function):
+    """Per-modality row sets of the decoder output (y[decoder_mod_mask == idx], fm.py:591) in one autograd node:
+    src bf16 [R, D]; rows int32 [n_mods, R] device index lists; counts: python ints -> tuple of bf16 [n_m, D]."""
+
+    @staticmethod
+    def forward(ctx, src, rows, counts):
+        ctx.save_for_backward(rows)
+        ctx.counts, ctx.shape = counts, src.shape
+        return tuple(ops.gather_rows_bf16(src, rows[i], n) for i, n in enumerate(counts))
+
+    @staticmethod
+    def backward(ctx, *douts):
+        (rows,) = ctx.saved_tensors
+        d = torch.zeros(ctx.shape, device=rows.device, dtype=torch.bfloat16)
+        for i, (n, g) in enumerate(zip(ctx.counts, douts)):
+            if n > 0 and g is not None:
+                ops.scatter_rows_bf16(g.contiguous(), rows[i], d, n)
+        return d, None, None
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# embedding gather (forward) / scatter (backward) over a selection plan
+# ----------------------------------------------------------------------------------------------------------------------
+class EmbedRowsFn(torch.autograd.Function):
+    """x0 = x + emb and emb for the kept rows of one side.  `seg_static` holds the non-differentiable part of every
+    segment; the differentiable tensors arrive flat: mask_token, then per segment (token_emb | x_rows, mod_emb)."""
+
+    @staticmethod
+    def forward(ctx, plan, seg_static, D, want_emb, mask_token, *tensors):
+        segs = []
+        for i, st in enumerate(seg_static):
+            d = dict(st)
+            main, mod = tensors[2 * i], tensors[2 * i + 1]
+            if st["kind"] == 0:
+                d["x_rows"] = main
+            else:
+                d["token_emb"] = main
+            d["mod_emb"] = mod.reshape(-1)
+            segs.append(d)
+        x0, emb = ops.embed_rows(plan, segs, None if mask_token is None else mask_token.reshape(-1), D, want_emb)
+        ctx.plan, ctx.seg_static, ctx.D = plan, seg_static, D
+        ctx.shapes = [(t.shape, t.dtype) for t in tensors]
+        ctx.mask_token_shape = None if mask_token is None else mask_token.shape
+        return (x0, emb) if want_emb else (x0, None)
+
+    @staticmethod
+    def backward(ctx, dx0, demb):
+        plan, D = ctx.plan, ctx.D
+        dev = dx0.device
+        grads, segs = [], []
+        for i, st in enumerate(ctx.seg_static):
+            d = dict(st)
+            (mshape, _), (eshape, _) = ctx.shapes[2 * i], ctx.shapes[2 * i + 1]
+            need_main, need_mod = ctx.needs_input_grad[5 + 2 * i], ctx.needs_input_grad[5 + 2 * i + 1]
+            gm = None
+            if need_main:
+                if st["kind"] == 0:
+                    gm = torch.zeros(mshape, device=dev, dtype=torch.bfloat16)
+                    d["dx_rows"] = gm
+                else:
+                    gm = torch.zeros(mshape, device=dev, dtype=torch.float32)
+                    d["d_token_emb"] = gm
+            ge = torch.zeros(D, device=dev, dtype=torch.float32) if need_mod else None
+            d["d_mod_emb"] = ge
+            grads += [gm, None if ge is None else ge.view(eshape)]
+            segs.append(d)
+        dmt = torch.zeros(D, device=dev, dtype=torch.float32) if (ctx.mask_token_shape is not None and ctx.needs_input_grad[4]) else None
+        ops.embed_rows_bwd(plan, segs, dx0.contiguous(), None if demb is None else demb.contiguous(), dmt, D)
+        return (None, None, None, None, None if dmt is None else dmt.view(ctx.mask_token_shape), *grads)

@@ -52,6 +52,7 @@ SIGNATURES = {
     "b200fm_head_rows": [c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
     "b200fm_gather_rows_bf16": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "b200fm_gather_i64": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p],
+    "b200fm_scatter_rows_bf16": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "b200fm_scatter_add_rows": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "b200fm_vq_argmax": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p],
     "b200fm_vq_argmax_host": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p],

@@ -153,3 +153,190 @@ def attention_bwd(q, k, v, out, dout, stats, B, H, Nq, Nk, mask=None, scale=None
              out.stride(0), _ptr(dout), dout.stride(0), _ptr(stats), _ptr(dq), dq.stride(0), _ptr(dk), dk.stride(0), _ptr(dv),
              dv.stride(0), B, H, Nq, Nk, float(scale), _stream())
     return dq, dk, dv
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# element-wise / row-wise
+# ----------------------------------------------------------------------------------------------------------------------
+
+def swiglu_bwd(ab, dg):
+    _need_cuda(ab, dg)
+    R, H2 = ab.shape
+    H = H2 // 2
+    dab = torch.empty_like(ab)
+    lib.call("b200fm_swiglu_bwd", _ptr(ab), ab.stride(0), _ptr(dg), dg.stride(0), _ptr(dab), dab.stride(0), R, H, _stream())
+    return dab
+
+
+def act_bwd(pre, dact, act):
+    _need_cuda(pre, dact)
+    assert pre.is_contiguous() and dact.is_contiguous()
+    out = torch.empty_like(pre)
+    lib.call("b200fm_act_bwd", {"gelu": 0, "tanh": 1}[act], _ptr(pre), _ptr(dact), _ptr(out), pre.numel(), _stream())
+    return out
+
+
+def cross_entropy(logits, targets, want_grad=True):
+    """logits fp32 [n, V], targets int64 [n] -> (loss_rows fp32 [n], dlogits bf16 [n, V] = softmax - onehot | None)."""
+    _need_cuda(logits, targets)
+    n, V = logits.shape
+    assert logits.dtype == torch.float32 and logits.stride(1) == 1 and targets.dtype == torch.int64 and targets.is_contiguous()
+    loss = torch.empty(n, device=logits.device, dtype=torch.float32)
+    Vp = (V + 7) // 8 * 8
+    dl = torch.empty(n, Vp, device=logits.device, dtype=torch.bfloat16)[:, :V] if want_grad else None
+    lib.call("b200fm_cross_entropy", _ptr(logits), logits.stride(0), _ptr(targets), _ptr(loss), _ptr(dl), dl.stride(0) if want_grad else 0,
+             n, V, _stream())
+    return loss, dl
+
+
+def colsum_bf16(x, out=None):
+    _need_cuda(x, out)
+    R, N = x.shape
+    if out is None:
+        out = torch.zeros(N, device=x.device, dtype=torch.float32)
+    lib.call("b200fm_colsum_bf16", _ptr(x), x.stride(0), _ptr(out), R, N, _stream())
+    return out
+
+
+def cast_bf16(x, out=None):
+    _need_cuda(x, out)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    lib.call("b200fm_cast_f32_bf16", _ptr(x), _ptr(out), x.numel(), _stream())
+    return out
+
+
+def patchify(img, patch):
+    _need_cuda(img)
+    assert img.dtype == torch.float32 and img.is_contiguous()
+    B, C, H, W = img.shape
+    if H % patch or W % patch:
+        raise AssertionError(f"Image sizes {H}x{W} must be divisible by patch sizes {patch}x{patch}")
+    out = torch.empty(B * (H // patch) * (W // patch), patch * patch * C, device=img.device, dtype=torch.bfloat16)
+    lib.call("b200fm_patchify", _ptr(img), _ptr(out), B, C, H, W, patch, _stream())
+    return out
+
+
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, shadow=None):
+    _need_cuda(p, g, m, v, shadow)
+    lib.call("b200fm_adamw", _ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(shadow), p.numel(), float(lr), float(beta1), float(beta2),
+             float(eps), float(weight_decay), int(step), float(grad_scale), _stream())
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# selection plan / embedding gather-scatter
+# ----------------------------------------------------------------------------------------------------------------------
+
+class SelectionPlan:
+    """Device-side result of b200fm_select_plan for one side (encoder / decoder) of one forward call."""
+    __slots__ = ("segs", "n_seg", "decoder", "B", "n_keep", "src_seg", "src_pos", "pos_id", "pad_mask", "mod_mask", "mod_raw",
+                 "target_ids", "dam", "keepalive")
+
+
+def make_segments(seg_dicts):
+    """seg_dicts: list of dicts with tensors/ints per include/b200fm.h b200fm_segment.  Returns (ctypes array, keepalive list)."""
+    n = len(seg_dicts)
+    if not 1 <= n <= lib.MAX_SEGMENTS:
+        raise ValueError(f"{n} modalities: supported range is 1..{lib.MAX_SEGMENTS}")
+    arr = (lib.Segment * n)()
+    keep = []
+    for i, d in enumerate(seg_dicts):
+        s = arr[i]
+        for name in ("mask", "ids", "dam", "token_emb", "pos_emb", "mod_emb", "x_rows", "d_token_emb", "d_mod_emb", "dx_rows"):
+            t = d.get(name)
+            if t is not None:
+                _need_cuda(t)
+                keep.append(t)
+            setattr(s, name, _ptr(t))
+        s.padding_idx = d.get("padding_idx", -1) if d.get("padding_idx") is not None else -1
+        s.L, s.kind, s.mod_id = int(d["L"]), int(d["kind"]), int(d["mod_id"])
+        s.max_length = int(d.get("max_length", 0))
+        ids = d.get("ids")
+        s.ids_is_i64 = int(ids is not None and ids.dtype == torch.int64)
+        s.reserved = 0
+    return arr, keep
+
+
+MODE_DECODER, MODE_IDENTITY, MODE_NO_SUM = 1, 2, 4
+
+
+def select_plan(seg_dicts, mode, B, n_keep, device):
+    """mode: bit flags MODE_DECODER | MODE_IDENTITY | MODE_NO_SUM (include/b200fm.h)."""
+    import ctypes
+    arr, keep = make_segments(seg_dicts)
+    p = SelectionPlan()
+    decoder = mode & MODE_DECODER
+    p.segs, p.n_seg, p.decoder, p.B, p.n_keep, p.keepalive = seg_dicts, len(seg_dicts), int(mode), B, n_keep, keep
+    i32 = dict(device=device, dtype=torch.int32)
+    p.src_seg = torch.empty(B, n_keep, **i32)
+    p.src_pos = torch.empty(B, n_keep, **i32)
+    p.pos_id = torch.empty(B, n_keep, **i32)
+    p.pad_mask = torch.empty(B, n_keep, device=device, dtype=torch.bool)
+    p.mod_mask = torch.empty(B, n_keep, device=device, dtype=torch.int16)
+    p.mod_raw = torch.empty(B, n_keep, device=device, dtype=torch.int16)
+    p.target_ids = torch.empty(B, n_keep, device=device, dtype=torch.int64) if decoder else None
+    p.dam = torch.empty(B, n_keep, **i32) if decoder else None
+    lib.call("b200fm_select_plan", ctypes.addressof(arr), p.n_seg, p.decoder, B, n_keep, _ptr(p.src_seg), _ptr(p.src_pos),
+             _ptr(p.pos_id), _ptr(p.pad_mask), _ptr(p.mod_mask), _ptr(p.mod_raw), _ptr(p.target_ids), _ptr(p.dam), _stream())
+    return p
+
+
+def decoder_attention_mask(dam, mod_raw, causal=False, sep=True):
+    _need_cuda(dam, mod_raw)
+    B, M = dam.shape
+    out = torch.empty(B, M, M, device=dam.device, dtype=torch.bool)
+    lib.call("b200fm_decoder_attention_mask", _ptr(dam), _ptr(mod_raw), _ptr(out), B, M, int(causal), int(sep), _stream())
+    return out
+
+
+def embed_rows(plan, seg_dicts, mask_token, D, want_emb):
+    import ctypes
+    arr, keep = make_segments(seg_dicts)
+    dev = plan.src_seg.device
+    x0 = torch.empty(plan.B, plan.n_keep, D, device=dev, dtype=torch.float32)
+    emb = torch.empty(plan.B, plan.n_keep, D, device=dev, dtype=torch.float32) if want_emb else None
+    lib.call("b200fm_embed_rows", ctypes.addressof(arr), len(seg_dicts), plan.decoder, _ptr(plan.src_seg), _ptr(plan.src_pos),
+             _ptr(plan.pos_id), _ptr(plan.pad_mask), _ptr(mask_token), _ptr(x0), _ptr(emb), plan.B, plan.n_keep, D, _stream())
+    return x0, emb
+
+
+def embed_rows_bwd(plan, seg_dicts, dx0, demb, d_mask_token, D):
+    import ctypes
+    arr, keep = make_segments(seg_dicts)
+    assert dx0.is_contiguous() and dx0.dtype == torch.float32 and (demb is None or (demb.is_contiguous() and demb.dtype == torch.float32))
+    lib.call("b200fm_embed_rows_bwd", ctypes.addressof(arr), len(seg_dicts), plan.decoder, _ptr(plan.src_seg), _ptr(plan.src_pos),
+             _ptr(plan.pad_mask), _ptr(dx0), _ptr(demb), _ptr(d_mask_token), plan.B, plan.n_keep, D, _stream())
+
+
+def head_rows(mod_mask, mod_ids_dev):
+    """-> (rows int32 [n_mods, n_rows], counts int32 [n_mods]) on device."""
+    _need_cuda(mod_mask, mod_ids_dev)
+    n_rows = mod_mask.numel()
+    n_mods = mod_ids_dev.numel()
+    rows = torch.empty(n_mods, n_rows, device=mod_mask.device, dtype=torch.int32)
+    counts = torch.empty(n_mods, device=mod_mask.device, dtype=torch.int32)
+    lib.call("b200fm_head_rows", _ptr(mod_mask), n_rows, _ptr(mod_ids_dev), n_mods, _ptr(rows), _ptr(counts), _stream())
+    return rows, counts
+
+
+def gather_rows_bf16(src, rows, n):
+    _need_cuda(src, rows)
+    D = src.shape[-1]
+    out = torch.empty(n, D, device=src.device, dtype=torch.bfloat16)
+    lib.call("b200fm_gather_rows_bf16", _ptr(src), _ptr(rows), _ptr(out), n, D, _stream())
+    return out
+
+
+def gather_i64(src, rows, n):
+    out = torch.empty(n, device=src.device, dtype=torch.int64)
+    lib.call("b200fm_gather_i64", _ptr(src), _ptr(rows), _ptr(out), n, _stream())
+    return out
+
+
+def scatter_add_rows(src_bf16, rows, dst, n):
+    lib.call("b200fm_scatter_add_rows", _ptr(src_bf16), _ptr(rows), _ptr(dst), n, dst.shape[-1], _stream())
+
+
+def scatter_rows_bf16(src, rows, dst, n):
+    lib.call("b200fm_scatter_rows_bf16", _ptr(src), _ptr(rows), _ptr(dst), n, dst.shape[-1], _stream())

@@ -17,7 +17,9 @@ struct SegTable {
     b200fm_segment seg[B200FM_MAX_SEGMENTS];
     int offset[B200FM_MAX_SEGMENTS + 1];   // start of each segment in the concatenated position space
     int n_seg;
-    int decoder;                           // 0: encoder side (input_mask), 1: decoder side (shifted target_mask)
+    int decoder;                           // 1: decoder side (teacher-forcing shift, mask token, targets); 0: encoder side
+    int identity;                          // 1: keep every position in place (materialise a whole modality, generation path)
+    int sum_mode;                          // 1: x0 = x + emb (training path); 0: x0 = x (embedding modules' own forward)
 };
 
 // effective number of positions a segment contributes: decoder sequences lose one (teacher-forcing shift, fm.py:312-319)
@@ -73,15 +75,15 @@ plan_kernel(const SegTable tab, int n_keep, int32_t* __restrict__ src_seg, int32
         const int carry = carry_s;
         const int rank_valid = carry + wbase + incl - valid;          // exclusive rank among valid positions
         if (p < total) {
-            const int slot = valid ? rank_valid : n_valid + (p - rank_valid);     // masked: rank among masked = p - #valid before p
+            const int slot = tab.identity ? p : (valid ? rank_valid : n_valid + (p - rank_valid));   // masked: rank among masked = p - #valid before p
             if (slot < n_keep) {
                 const b200fm_segment& sg = tab.seg[s];
                 const long long o = (long long)b * n_keep + slot;
                 src_seg[o] = s;
                 src_pos[o] = l;
-                pad_mask[o] = valid ? 0 : 1;
+                pad_mask[o] = (valid || tab.identity) ? 0 : 1;
                 mod_raw[o] = (int16_t)sg.mod_id;
-                mod_mask[o] = valid ? (int16_t)sg.mod_id : (int16_t)-1;             // fm.py:387 / 432
+                mod_mask[o] = (valid || tab.identity) ? (int16_t)sg.mod_id : (int16_t)-1;   // fm.py:387 / 432
                 // positional index: rank among the segment's valid RAW positions (encoder: input_mask, decoder: target_mask),
                 // encoder_embeddings.py:110-112, decoder_embeddings.py:125-128; image modalities use the patch index.
                 int pid = l;
@@ -90,7 +92,7 @@ plan_kernel(const SegTable tab, int n_keep, int32_t* __restrict__ src_seg, int32
                     int rk = 0;
                     for (int i = 0; i <= l; ++i) rk += m[i] ? 0 : 1;
                     pid = m[l] ? -1 : rk - 1;                                    // -1: positional part zeroed (masked raw position)
-                    if (tab.decoder && pid >= sg.max_length) pid = 0;              // decoder_embeddings.py:128
+                    if (sg.max_length > 0 && pid >= sg.max_length) pid = 0;       // decoder_embeddings.py:128 (encoder passes 0)
                 }
                 pos_id[o] = pid;
                 if (tab.decoder) {
@@ -181,7 +183,7 @@ embed_kernel(const SegTable tab, const int32_t* __restrict__ src_seg, const int3
             } else {
                 x = xs[c];
             }
-            xo[c] = make_float4(x.x + e.x, x.y + e.y, x.z + e.z, x.w + e.w);
+            xo[c] = tab.sum_mode ? make_float4(x.x + e.x, x.y + e.y, x.z + e.z, x.w + e.w) : x;
             if (eo) eo[c] = e;
         }
     }
@@ -232,7 +234,7 @@ embed_bwd_modsum_kernel(const SegTable tab, const int32_t* __restrict__ src_seg,
         if (pad_mask[r] || src_seg[r] != s) continue;
         const float g = dx0[r * D + col];
         acc_tok += g;
-        acc_mod += g + (demb ? demb[r * D + col] : 0.f);
+        acc_mod += (tab.sum_mode ? g : 0.f) + (demb ? demb[r * D + col] : 0.f);
     }
     const b200fm_segment& sg = tab.seg[s];
     if (sg.d_mod_emb != nullptr && acc_mod != 0.f) atomicAdd(sg.d_mod_emb + col, acc_mod);
@@ -299,9 +301,21 @@ __global__ void scatter_add_rows_kernel(const __nv_bfloat16* __restrict__ src, c
     }
 }
 
-static int fill_table(SegTable& t, const b200fm_segment* segs, int n_seg, int decoder) {
+// dst[rows[i]] = src[i] for bf16 rows (destination rows are distinct)
+__global__ void scatter_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ rows, __nv_bfloat16* __restrict__ dst,
+                                         long long n, int D8) {
+    const long long total = n * D8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / D8; const int c = (int)(i % D8);
+        reinterpret_cast<uint4*>(dst)[(long long)rows[r] * D8 + c] = reinterpret_cast<const uint4*>(src)[i];
+    }
+}
+
+static int fill_table(SegTable& t, const b200fm_segment* segs, int n_seg, int mode) {
     B200FM_CHECK(n_seg >= 1 && n_seg <= B200FM_MAX_SEGMENTS, "segment count %d outside [1, %d]", n_seg, B200FM_MAX_SEGMENTS);
-    t.n_seg = n_seg; t.decoder = decoder;
+    B200FM_CHECK(mode >= 0 && mode < 8, "bad mode flags %d", mode);
+    const int decoder = (mode & B200FM_MODE_DECODER) ? 1 : 0;
+    t.n_seg = n_seg; t.decoder = decoder; t.identity = (mode & B200FM_MODE_IDENTITY) ? 1 : 0; t.sum_mode = (mode & B200FM_MODE_NO_SUM) ? 0 : 1;
     int off = 0;
     for (int i = 0; i < n_seg; ++i) {
         t.seg[i] = segs[i];
@@ -317,13 +331,14 @@ static int fill_table(SegTable& t, const b200fm_segment* segs, int n_seg, int de
 
 using namespace b200fm;
 
-extern "C" int b200fm_select_plan(const b200fm_segment* segs, int n_seg, int decoder, int B, int n_keep, int32_t* src_seg,
+extern "C" int b200fm_select_plan(const b200fm_segment* segs, int n_seg, int mode, int B, int n_keep, int32_t* src_seg,
                                   int32_t* src_pos, int32_t* pos_id, uint8_t* pad_mask, int16_t* mod_mask, int16_t* mod_raw,
                                   int64_t* target_ids, int32_t* dam_out, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (B == 0) return 0;
     SegTable t;
-    if (int rc = fill_table(t, segs, n_seg, decoder)) return rc;
+    if (int rc = fill_table(t, segs, n_seg, mode)) return rc;
+    const int decoder = t.decoder;
     B200FM_CHECK(n_keep >= 1 && n_keep <= t.offset[n_seg], "select_plan: n_keep=%d exceeds the %d available positions", n_keep, t.offset[n_seg]);
     B200FM_CHECK(src_seg && src_pos && pos_id && pad_mask && mod_mask && mod_raw, "select_plan: null output");
     if (decoder) {
@@ -356,13 +371,14 @@ extern "C" int b200fm_decoder_attention_mask(const int32_t* dam, const int16_t* 
         default: B200FM_CHECK(false, "embedding dim %d has no instantiation", (D));                    \
     }
 
-extern "C" int b200fm_embed_rows(const b200fm_segment* segs, int n_seg, int decoder, const int32_t* src_seg, const int32_t* src_pos,
+extern "C" int b200fm_embed_rows(const b200fm_segment* segs, int n_seg, int mode, const int32_t* src_seg, const int32_t* src_pos,
                                  const int32_t* pos_id, const uint8_t* pad_mask, const float* mask_token, float* x0, float* emb_out,
                                  int B, int n_keep, int D, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (B == 0) return 0;
     SegTable t;
-    if (int rc = fill_table(t, segs, n_seg, decoder)) return rc;
+    if (int rc = fill_table(t, segs, n_seg, mode)) return rc;
+    const int decoder = t.decoder;
     B200FM_CHECK(D % 128 == 0, "embed_rows: D=%d must be a multiple of 128", D);
     B200FM_CHECK(src_seg && src_pos && pos_id && pad_mask && x0, "embed_rows: null pointer");
     B200FM_CHECK(!decoder || mask_token, "embed_rows: decoder side needs the mask token");
@@ -373,13 +389,13 @@ extern "C" int b200fm_embed_rows(const b200fm_segment* segs, int n_seg, int deco
     return 0;
 }
 
-extern "C" int b200fm_embed_rows_bwd(const b200fm_segment* segs, int n_seg, int decoder, const int32_t* src_seg, const int32_t* src_pos,
+extern "C" int b200fm_embed_rows_bwd(const b200fm_segment* segs, int n_seg, int mode, const int32_t* src_seg, const int32_t* src_pos,
                                      const uint8_t* pad_mask, const float* dx0, const float* demb, float* d_mask_token, int B, int n_keep,
                                      int D, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (B == 0) return 0;
     SegTable t;
-    if (int rc = fill_table(t, segs, n_seg, decoder)) return rc;
+    if (int rc = fill_table(t, segs, n_seg, mode)) return rc;
     B200FM_CHECK(D % 128 == 0, "embed_rows_bwd: D=%d must be a multiple of 128", D);
     B200FM_CHECK(src_seg && src_pos && pad_mask && dx0, "embed_rows_bwd: null pointer");
     const long long rows = (long long)B * n_keep;
@@ -429,6 +445,17 @@ extern "C" int b200fm_scatter_add_rows(const void* src_bf16, const int32_t* rows
     const long long total = n * (D / 4);
     const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
     scatter_add_rows_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src_bf16), rows, dst, n, D / 4);
+    B200FM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200fm_scatter_rows_bf16(const void* src, const int32_t* rows, void* dst, long long n, int D, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (n == 0) return 0;
+    B200FM_CHECK(src && rows && dst && D % 8 == 0, "scatter_rows_bf16: bad arguments");
+    const long long total = n * (D / 8);
+    const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+    scatter_rows_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), rows, reinterpret_cast<__nv_bfloat16*>(dst), n, D / 8);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }

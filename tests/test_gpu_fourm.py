@@ -1,0 +1,132 @@
+"""FourM on the B200 kernels vs the golden outputs of the UNMODIFIED reference (4M-Tiny mod7, BASELINE configs[0] shape)
+and vs the oracle.  Integer/bool artefacts must be exact; floating point is compared with the tolerances stated inline:
+the product computes its contractions in bf16 (fp32 accumulate) like the reference under autocast(bf16), so the yardstick
+is the reference's own fp32-vs-bf16 gap."""
+import random
+
+import pytest
+import torch
+
+from oracle import fourm_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    from b200fm.compat import build_mod7_embeddings, create_model
+    gold = H.load_golden("fourm_tiny_golden.pt")
+    specs = O.mod7_specs()
+    sd = H.fill_fourm_buffers(H.golden_state_dict(gold), specs, 384)
+    enc, dec, info = build_mod7_embeddings()
+    model = create_model(gold["model"], encoder_embeddings=enc, decoder_embeddings=dec, modality_info=info)
+    missing, unexpected = model.load_state_dict(sd, strict=True)
+    return gold, specs, sd, model.cuda()
+
+
+def _to_cuda(batch):
+    return {m: {k: v.cuda() for k, v in d.items()} for m, d in batch.items()}
+
+
+def test_state_dict_contract(tiny):
+    gold, specs, sd, model = tiny
+    msd = model.state_dict()
+    assert list(msd.keys()) == list(gold["shapes"].keys())
+    assert all(tuple(v.shape) == gold["shapes"][k] for k, v in msd.items())
+    assert [k for k, _ in model.named_parameters(remove_duplicate=False)] == gold["param_names"]
+    # sharing (fm.py:176-180, decoder_embeddings.py:89-91)
+    assert model.decoder_embeddings["caption"].mod_emb is model.encoder_embeddings["caption"].mod_emb
+    assert model.decoder_embeddings["tok_rgb@224"].to_logits.weight is model.decoder_embeddings["tok_rgb@224"].token_emb.weight
+
+
+@pytest.mark.parametrize("tag", ["fp32_128", "fp32_trunc", "fp32_pad"])
+def test_selection_is_bit_exact(tiny, tag):
+    """PLAN + EMBED kernels vs the reference's cat/argsort/gather/mask path: masks, modality ids, targets, decoder attention
+    mask are integer-exact; gathered fp32 rows are bit-exact (same operation order)."""
+    from b200fm import ops
+    gold, specs, sd, model = tiny
+    c = gold["cases"][tag]
+    batch = _to_cuda(O.synthetic_mod7_batch(2, seed=c["batch_seed"], extra_valid=c["extra_valid"]))
+    enc_mods = [m for m in batch if m in model.encoder_embeddings]
+    with torch.no_grad():
+        x0, emb, ep = model._embed_side(batch, False, c["N"], enc_mods)
+        y0, _, dp = model._embed_side(batch, True, c["M"], c["decoder_order"])
+        amask = ops.decoder_attention_mask(dp.dam, dp.mod_raw, False, True)
+    assert torch.equal(ep.pad_mask[:, None].cpu(), c["enc_mask"])
+    assert torch.equal(ep.mod_mask.cpu(), c["enc_mod"])
+    assert torch.equal(dp.pad_mask[:, None].cpu(), c["dec_mask"])
+    assert torch.equal(dp.mod_mask.cpu(), c["dec_mod"])
+    assert torch.equal(dp.target_ids.cpu(), c["target_ids"].long())
+    assert torch.equal(amask.cpu(), c["dec_attn_mask"])
+    # decoder rows never touch the bf16 patch projection -> bit-exact against the fp32 reference
+    assert torch.equal(y0.double().sum(-1).cpu(), c["dec_y0_sum"])
+    # encoder rows: exact except the rgb rows, whose patch projection is a bf16 GEMM (autocast contract)
+    rgb = ep.mod_mask.cpu() == specs["rgb@224"]["id"]
+    got, ref = x0.double().sum(-1).cpu(), c["enc_x0_sum"]
+    assert torch.equal(got[~rgb], ref[~rgb])
+    torch.testing.assert_close(got[rgb], ref[rgb], rtol=0, atol=0.5)
+
+
+@pytest.mark.parametrize("tag", ["fp32_128", "bf16_128", "fp32_trunc", "fp32_pad"])
+def test_forward_loss_and_logits(tiny, tag):
+    gold, specs, sd, model = tiny
+    c = gold["cases"][tag]
+    batch = O.synthetic_mod7_batch(2, seed=c["batch_seed"], extra_valid=c["extra_valid"])
+    random.seed(c["py_seed"])
+    with torch.no_grad():
+        loss, mod_loss = model(_to_cuda(batch), num_encoder_tokens=c["N"], num_decoder_tokens=c["M"], loss_type="mod")
+    random.seed(c["py_seed"])
+    with torch.no_grad():
+        tl, _ = model(_to_cuda(batch), num_encoder_tokens=c["N"], num_decoder_tokens=c["M"], loss_type="token")
+    random.seed(c["py_seed"])
+    with torch.no_grad():
+        logits = model(_to_cuda(batch), num_encoder_tokens=c["N"], num_decoder_tokens=c["M"], return_logits=True)
+    # tolerance: 5e-3 absolute on ~9.5 nats (the reference's own fp32-vs-bf16 autocast gap on this case is 4e-5 .. 3e-4 per modality)
+    assert loss.dim() == 0 and loss.dtype == torch.float32
+    assert abs(float(loss) - float(c["loss"])) <= 5e-3
+    assert abs(float(tl) - float(c["token_loss"])) <= 5e-3
+    for m, v in c["mod_loss"].items():
+        assert abs(float(mod_loss[m]) - float(v)) <= 1e-2, m
+        if float(v) == 0.0:                      # empty modality -> zeros(1) (fm.py:593-595)
+            assert float(mod_loss[m]) == 0.0
+    for m, v in c["logits_slices"].items():
+        assert logits[m].shape[:2] == (2, c["M"])
+        torch.testing.assert_close(logits[m][:, :4, :32].float().cpu(), v, rtol=5e-2, atol=2e-2)
+
+
+def test_backward_matches_reference(tiny):
+    gold, specs, sd, model = tiny
+    c = gold["cases"]["fp32_128"]
+    batch = O.synthetic_mod7_batch(2, seed=c["batch_seed"])
+    model.zero_grad(set_to_none=True)
+    random.seed(c["py_seed"])
+    loss, _ = model(_to_cuda(batch), num_encoder_tokens=c["N"], num_decoder_tokens=c["M"])
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    worst = 0.0
+    for k, ref_norm in c["grads"]["norm"].items():
+        g = grads[k]
+        assert g is not None, k
+        rel = abs(float(g.float().norm()) - ref_norm) / max(ref_norm, 1e-6)
+        worst = max(worst, rel)
+        # bf16 contractions in fwd and bwd: per-tensor gradient norms within 3 % of the fp32 reference
+        assert rel <= 3e-2, f"{k}: grad norm {float(g.norm())} vs {ref_norm}"
+    for k, sl in c["grads"]["slices"].items():
+        got = grads[k].flatten()[:64].float().cpu()
+        scale = sl.abs().max().item() + 1e-12
+        assert (got - sl).abs().max().item() <= 8e-2 * scale + 1e-7, k
+
+
+def test_loss_invariant_to_decoder_shuffle_when_no_truncation(tiny):
+    """identical loss across Python-random modality shuffles when #valid <= budget."""
+    gold, specs, sd, model = tiny
+    batch = _to_cuda(O.synthetic_mod7_batch(2, seed=5))
+    vals = []
+    for s in (0, 1, 2):
+        random.seed(s)
+        with torch.no_grad():
+            loss, _ = model({m: dict(d) for m, d in batch.items()}, 128, 128)
+        vals.append(float(loss))
+    assert max(vals) - min(vals) <= 2e-3
