@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native 4M hot path (contract: see the task statement / DESIGN.md "Measurement").
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                     # one GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W                      # N GPUs, one rank each (data parallel, NCCL)
+    python bench.py --impl reference --steps 2 --warmup 1              # the reference algorithm on the host CPU cores
+
+A step = one full training step of 4M-B mod7 (BASELINE.json configs[1]): forward + backward + gradient all-reduce (DDP)
++ AdamW, per-GPU batch 128, 128 encoder + 128 decoder tokens per sample, synthetic data, random-init weights.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "ml-4m_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+MODEL = "fm_base_12e_12d_swiglu_nobias"
+DIMS = dict(D=768, Le=12, Ld=12, heads=12, H=2048)
+VBAR = (16384 + 8192 + 8192 + 4096 + 8192) * 22 / 128 + 30000 * 18 / 128      # token-weighted mean target vocab
+
+
+def flops_per_sample_fwd(N, M, D=768, Le=12, Ld=12, H=2048):
+    """SURVEY.md 8d algorithmic FLOPs (multiply-add = 2)."""
+    enc = 8 * N * D * D + 4 * N * N * D + 6 * N * D * H
+    dec = (8 * M * D * D + 4 * M * M * D) + (4 * M * D * D + 4 * N * D * D + 4 * M * N * D) + 6 * M * D * H
+    blocks = Le * enc + Ld * dec
+    extras = 2 * N * D * D + 2 * M * D * VBAR + 2 * 196 * 768 * D
+    return blocks, blocks + extras
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(bf16=float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1590.0))), hbm=float(p.get("hbm_gbs", 6650.0)), src="measured")
+    return dict(bf16=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = max((int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()), default=None)
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the reference algorithm on the host CPU (oracle port): cpu_baseline leg and `--impl reference`
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps, warmup, sample_B, n_tok):
+    """Times fwd+bwd of the oracle restatement of FourM.forward (4M-B mod7, fp32, all host threads)."""
+    import random
+    from oracle import fourm_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    specs = O.mod7_specs()
+    cfg = O.PRESETS[MODEL]
+    g = torch.Generator().manual_seed(0)
+    sd = {}
+    D = cfg["dim"]
+
+    def w(*shape, std=0.02):
+        return (torch.randn(*shape, generator=g) * std).requires_grad_(True)
+    for name, s in specs.items():
+        for side in ("encoder_embeddings", "decoder_embeddings"):
+            if side == "decoder_embeddings" and s["kind"] == "img":
+                continue
+            p = f"{side}.{name}."
+            sd[p + "mod_emb"] = w(1, 1, D) if side == "encoder_embeddings" else sd[f"encoder_embeddings.{name}.mod_emb"]
+            sd[p + "pos_emb"] = O.sincos_1d(512, D) if s["kind"] == "seq" else O.sincos_2d(14, 14, D)
+            if s["kind"] == "img":
+                sd[p + "proj.weight"] = w(D, 768)
+            else:
+                sd[p + "token_emb.weight"] = w(s["vocab"], D)
+                if side == "decoder_embeddings":
+                    sd[p + "to_logits.weight"] = sd[p + "token_emb.weight"]
+    H = int(2 * 4 * D / 3)
+    for i in range(cfg["enc_depth"]):
+        p = f"encoder.{i}."
+        for n in ("norm1", "norm2"):
+            sd[p + n + ".weight"] = torch.ones(D, requires_grad=True); sd[p + n + ".bias"] = torch.zeros(D)
+        sd[p + "attn.qkv.weight"] = w(3 * D, D); sd[p + "attn.proj.weight"] = w(D, D)
+        sd[p + "mlp.fc1.weight"] = w(H, D); sd[p + "mlp.fc3.weight"] = w(H, D); sd[p + "mlp.fc2.weight"] = w(D, H)
+    for i in range(cfg["dec_depth"]):
+        p = f"decoder.{i}."
+        for n in ("norm1", "norm2", "query_norm", "context_norm"):
+            sd[p + n + ".weight"] = torch.ones(D, requires_grad=True); sd[p + n + ".bias"] = torch.zeros(D)
+        sd[p + "self_attn.qkv.weight"] = w(3 * D, D); sd[p + "self_attn.proj.weight"] = w(D, D)
+        sd[p + "cross_attn.q.weight"] = w(D, D); sd[p + "cross_attn.kv.weight"] = w(2 * D, D); sd[p + "cross_attn.proj.weight"] = w(D, D)
+        sd[p + "mlp.fc1.weight"] = w(H, D); sd[p + "mlp.fc3.weight"] = w(H, D); sd[p + "mlp.fc2.weight"] = w(D, H)
+    for n in ("encoder_norm", "decoder_norm"):
+        sd[n + ".weight"] = torch.ones(D, requires_grad=True); sd[n + ".bias"] = torch.zeros(D)
+    sd["decoder_proj_context.weight"] = w(D, D); sd["decoder_proj_context.bias"] = torch.zeros(D, requires_grad=True)
+    sd["mask_token"] = w(1, 1, D)
+    from b200fm.synthetic import budgets_for
+    a, b, c, d = budgets_for(n_tok)
+    batch = O.synthetic_mod7_batch(sample_B, a, b, c, d, seed=1234)
+    dec_names = [m for m, s in specs.items() if s["kind"] != "img"]
+    leaves = [t for t in {id(v): v for v in sd.values()}.values() if t.requires_grad]
+    times = []
+    for it in range(warmup + steps):
+        random.seed(it)
+        order = random.sample(dec_names, len(dec_names))
+        t0 = time.perf_counter()
+        loss, _ = O.fourm_forward(sd, cfg, specs, batch, n_tok, n_tok, order)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        for t in leaves:
+            t.grad = None
+        if it >= warmup:
+            times.append(dt)
+    tok = sample_B * 2 * n_tok
+    return tok / (sum(times) / len(times)), sum(times) / len(times), os.cpu_count() or 1
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_tok = 128
+    B = 4
+    tps, sec, cores = cpu_reference_steps(args.steps, args.warmup, B, n_tok)
+    line = dict(metric="tokens_per_sec", value=tps, unit="tokens/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                impl="reference",
+                config=dict(workload="4M-B mod7 train step fwd+bwd (oracle port of FourM.forward on host CPU, fp32)", model=MODEL,
+                            global_batch=B, seq_len=2 * n_tok, parallelism="cpu"),
+                cpu_baseline=dict(value=tps, unit="tokens/s", cores=cores, kind="port",
+                                  sample=f"fwd+bwd of B={B} samples x {2 * n_tok} tokens per step, fp32, torch CPU {torch.get_num_threads()} threads"),
+                e2e=dict(value=tps, unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch.distributed as dist
+    from b200fm import lib, ops
+    from b200fm.compat import build_mod7_embeddings, create_model
+    from b200fm.optim import FusedAdamW, param_groups_like_reference
+    from b200fm.synthetic import batch_bytes, budgets_for, mod7_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (B200 arm) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+
+    B, n_tok = args.batch, args.tokens
+    torch.manual_seed(0)
+    enc, dec, info = build_mod7_embeddings()
+    model = create_model(args.model, encoder_embeddings=enc, decoder_embeddings=dec, modality_info=info).to(dev)
+    n_params = sum(p.numel() for p in model.parameters())
+    lr = 1e-4 * B * world / 256                                 # run_training_4m.py:496-503 scaling rule
+    opt = FusedAdamW(param_groups_like_reference(model, 0.05), lr=lr, betas=(0.9, 0.95), eps=1e-8)
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False,
+                                                        gradient_as_bucket_view=True, broadcast_buffers=False)
+    import random
+    random.seed(rank)
+    a, b, c, d = budgets_for(n_tok)
+    host_batches = [mod7_batch(B, a, b, c, d, seed=1234 + rank + 17 * i, pin_memory=True) for i in range(2)]
+    dev_batches = [{m: {k: v.to(dev) for k, v in dd.items()} for m, dd in hb.items()} for hb in host_batches]
+    h2d = batch_bytes(host_batches[0])
+
+    def step(batch):
+        loss, mod_loss = net(batch, num_encoder_tokens=n_tok, num_decoder_tokens=n_tok, loss_type="mod")
+        loss.backward()
+        grads = [p.grad for p in model.parameters() if p.grad is not None]
+        gnorm = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(grads)))       # logged grad norm (native_scaler.py:56-65)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss, mod_loss, gnorm
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(n_steps, e2e):
+        calls0 = lib.CALLS["n"]
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for i in range(n_steps):
+            if e2e:
+                hb = host_batches[i % 2]
+                batch = {m: {k: v.to(dev, non_blocking=True) for k, v in dd.items()} for m, dd in hb.items()}
+                loss, mod_loss, gnorm = step(batch)
+                last = loss.item()                        # device -> host read of the step's result
+            else:
+                loss, mod_loss, gnorm = step(dev_batches[i % 2])
+        e1.record()
+        sync()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, lib.CALLS["n"] - calls0, (last if last is not None else float(loss.item()))
+
+    for _ in range(max(args.warmup, 3)):
+        step(dev_batches[0])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches, loss_val = timed(args.steps, e2e=False)
+    ms_e2e, _, loss_e2e = timed(args.steps, e2e=True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # roofline of the dominant kernel family (tcgen05 GEMM): CUDA events around every launch during extra steps
+    ops.PROFILE = []
+    step(dev_batches[0]); step(dev_batches[1])
+    torch.cuda.synchronize()
+    gemm_ms = sum(s.elapsed_time(e) for s, e, _ in ops.PROFILE)
+    gemm_flops = sum(f for _, _, f in ops.PROFILE)
+    n_gemm = len(ops.PROFILE)
+    ops.PROFILE = None
+    step_ms_prof = None
+
+    if rank == 0:
+        peaks = measured_peaks()
+        tokens_per_step = world * B * 2 * n_tok
+        tps = tokens_per_step / (ms / args.steps / 1e3)
+        tps_e2e = tokens_per_step / (ms_e2e / args.steps / 1e3)
+        blocks, total = flops_per_sample_fwd(n_tok, n_tok)
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        model_tflops = 3 * total * B * world / (ms / args.steps / 1e3) / 1e12
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, sec, cores = cpu_reference_steps(2, 1, 4, n_tok)
+            cpu = dict(value=v, unit="tokens/s", cores=cores, kind="port",
+                       sample=f"2 timed fwd+bwd steps of B=4 x {2 * n_tok} tokens, oracle port of FourM.forward, fp32, {torch.get_num_threads()} threads")
+        line = dict(metric="tokens_per_sec", value=tps, unit="tokens/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                    config=dict(workload="4M-B mod7 full train step (fwd+bwd+DDP all-reduce+AdamW), BASELINE.json configs[1]",
+                                model=args.model, global_batch=B * world, per_gpu_batch=B, seq_len=2 * n_tok, encoder_tokens=n_tok,
+                                decoder_tokens=n_tok, parallelism=f"dp{world}", params_m=round(n_params / 1e6, 1),
+                                l2_policy="per-step working set (activations+grads > 2 GB) exceeds the 126 MB L2; two alternating input batches"),
+                    e2e=dict(value=tps_e2e, unit="tokens/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
+                    gpu_launches=launches, loss=loss_val,
+                    model_tflops_per_gpu=model_tflops / world,
+                    frac_of_bf16_peak=model_tflops / world / peaks["bf16"],
+                    roofline=dict(bound="tensor", kernel="gemm_kernel<BN,LAYOUT,EPI> (all tcgen05 GEMM launches of a step)", achieved=achieved,
+                                  peak=peaks["bf16"], unit="TFLOP/s", frac=achieved / peaks["bf16"], traffic=None, peak_source=peaks["src"],
+                                  launches_per_step=n_gemm // 2, gemm_ms_per_step=gemm_ms / 2),
+                    clocks=clocks)
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default=MODEL)
+    ap.add_argument("--batch", type=int, default=128, help="per-GPU batch (cfgs/default/4m/models/main/4m-b_mod7_500b.yaml:28)")
+    ap.add_argument("--tokens", type=int, default=128, help="encoder tokens = decoder tokens per sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -13,6 +13,7 @@ from . import ops
 # bf16 weight shadows
 # ----------------------------------------------------------------------------------------------------------------------
 _shadow = {}
+_shadow_views = {}      # id(param) -> list of bf16 row-slices that mirror it (lets the fused optimizer refresh them in its own pass)
 
 
 def _pad_rows(n, mult=8):
@@ -39,14 +40,24 @@ def weight_bf16(*params):
             src = p.detach()
             if src.dtype != torch.float32 or not src.is_contiguous():
                 src = src.float().contiguous()
-            ops.cast_bf16(src, buf[off:off + r])
+            view = buf[off:off + r]
+            ops.cast_bf16(src, view)
+            views = _shadow_views.setdefault(id(p), [])
+            if not any(v.data_ptr() == view.data_ptr() for v in views):
+                views.append(view)
             off += pr
     _shadow[key] = (ver, buf)
     return buf
 
 
+def shadow_views(param):
+    """bf16 mirrors of `param` currently cached (the fused AdamW kernel writes the first one itself)."""
+    return _shadow_views.get(id(param), [])
+
+
 def clear_weight_cache():
     _shadow.clear()
+    _shadow_views.clear()
 
 
 def _as2d(x):

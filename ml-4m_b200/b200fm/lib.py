@@ -97,5 +97,9 @@ def check(rc, what):
         raise B200FMError(f"{what} failed (rc={rc}): {load().b200fm_last_error().decode(errors='replace')}")
 
 
+CALLS = {"n": 0}      # kernel-launching C-ABI calls issued by this process (bench.py reports it as gpu_launches)
+
+
 def call(name, *args):
+    CALLS["n"] += 1
     check(getattr(load(), name)(*args), name)

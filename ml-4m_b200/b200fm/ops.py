@@ -7,6 +7,9 @@ LAYOUT_NT, LAYOUT_NN, LAYOUT_TN = 0, 1, 2
 EPI_BF16, EPI_F32, EPI_RESID, EPI_SWIGLU, EPI_GELU = 0, 1, 2, 3, 4
 
 
+PROFILE = None     # bench.py sets this to a list: (start_event, end_event, flops) per GEMM launch
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -65,8 +68,14 @@ def gemm(a, b, layout=LAYOUT_NT, epilogue=EPI_BF16, out=None, out1=None, bias=No
         assert bias.dtype == torch.float32 and bias.is_contiguous()
     if resid is not None:
         assert resid.dtype == torch.float32
+    if PROFILE is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     lib.call("b200fm_gemm_bf16", layout, epilogue, M, N, K, _ptr(a), lda, _ptr(b), ldb, _ptr(out), ld0, _ptr(out1), ld1,
              _ptr(bias), _ptr(resid), ldr, float(alpha), _ptr(alpha_dev), _stream())
+    if PROFILE is not None:
+        ev1.record()
+        PROFILE.append((ev0, ev1, 2.0 * M * K * (2 * N if epilogue == EPI_SWIGLU else N)))
     return (out, out1) if epilogue in (EPI_SWIGLU, EPI_GELU) else out
 
 
