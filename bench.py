@@ -245,6 +245,13 @@ def run_b200_arm(args):
 
     for _ in range(max(args.warmup, 3)):
         step(dev_batches[0])
+    if os.environ.get("B200FM_NCU_ONE_STEP"):      # ncu --profile-from-start off: exactly one steady-state step is profiled
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(dev_batches[1])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

@@ -32,6 +32,7 @@ extern "C" {
 #define B200FM_EPI_RESID 2  /* out0 fp32 [M,N] = resid fp32 + bf16(acc (+bias))      (x = x + proj(...))          */
 #define B200FM_EPI_SWIGLU 3 /* B = [fc1; fc3] [2N,K]; out0 bf16 [M,2N] = [a | b]; out1 bf16 [M,N] = silu(a) * b   */
 #define B200FM_EPI_GELU 4   /* out0 bf16 [M,N] = pre-activation; out1 bf16 [M,N] = gelu(out0)                     */
+#define B200FM_EPI_TANH 5   /* as EPI_GELU with tanh (ViT tokenizer post_mlp, vq/models/vit_models.py:494-496)     */
 
 const char* b200fm_last_error(void);
 int b200fm_abi_version(void);

@@ -223,23 +223,24 @@ class SwiGLUFn(torch.autograd.Function):
 
 
 class MlpActFn(torch.autograd.Function):
-    """act(bf16) = GELU(x W^T + b) with the pre-activation saved by the same GEMM epilogue (fm_utils.py:111-126)."""
+    """act(bf16) = GELU|tanh(x W^T + b) with the pre-activation saved by the same GEMM epilogue (fm_utils.py:111-126)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, act_name="gelu"):
         x2 = _to_bf16_2d(x)
-        pre, act = ops.gemm(x2, weight_bf16(weight), epilogue=ops.EPI_GELU, bias=bias, n_out=weight.shape[0])
+        epi = ops.EPI_GELU if act_name == "gelu" else ops.EPI_TANH
+        pre, act = ops.gemm(x2, weight_bf16(weight), epilogue=epi, bias=bias, n_out=weight.shape[0])
         ctx.save_for_backward(x2, weight, pre)
-        ctx.has_bias, ctx.in_shape = bias is not None, x.shape
+        ctx.has_bias, ctx.in_shape, ctx.act_name = bias is not None, x.shape, act_name
         return act.view(*x.shape[:-1], weight.shape[0])
 
     @staticmethod
     def backward(ctx, dact):
         x2, weight, pre = ctx.saved_tensors
-        dpre = ops.act_bwd(pre, _to_bf16_2d(dact).contiguous(), "gelu")
+        dpre = ops.act_bwd(pre, _to_bf16_2d(dact).contiguous(), ctx.act_name)
         dx, dw = _linear_bwd(ctx, dpre, x2, weight, ctx.needs_input_grad[0])
         db = ops.colsum_bf16(dpre) if ctx.has_bias else None
-        return (dx.view(ctx.in_shape) if dx is not None else None), dw, db
+        return (dx.view(ctx.in_shape) if dx is not None else None), dw, db, None
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -4,7 +4,7 @@ import torch
 from . import lib
 
 LAYOUT_NT, LAYOUT_NN, LAYOUT_TN = 0, 1, 2
-EPI_BF16, EPI_F32, EPI_RESID, EPI_SWIGLU, EPI_GELU = 0, 1, 2, 3, 4
+EPI_BF16, EPI_F32, EPI_RESID, EPI_SWIGLU, EPI_GELU, EPI_TANH = 0, 1, 2, 3, 4, 5
 
 
 PROFILE = None     # bench.py sets this to a list: (start_event, end_event, flops) per GEMM launch
@@ -59,7 +59,7 @@ def gemm(a, b, layout=LAYOUT_NT, epilogue=EPI_BF16, out=None, out1=None, bias=No
             out = torch.empty(M, 2 * N, device=dev, dtype=torch.bfloat16)
         else:
             out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    if out1 is None and epilogue in (EPI_SWIGLU, EPI_GELU):
+    if out1 is None and epilogue in (EPI_SWIGLU, EPI_GELU, EPI_TANH):
         out1 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     ld0 = _rowmajor2d(out, "out")
     ld1 = _rowmajor2d(out1, "out1") if out1 is not None else 0
@@ -76,7 +76,7 @@ def gemm(a, b, layout=LAYOUT_NT, epilogue=EPI_BF16, out=None, out1=None, bias=No
     if PROFILE is not None:
         ev1.record()
         PROFILE.append((ev0, ev1, 2.0 * M * K * (2 * N if epilogue == EPI_SWIGLU else N)))
-    return (out, out1) if epilogue in (EPI_SWIGLU, EPI_GELU) else out
+    return (out, out1) if epilogue in (EPI_SWIGLU, EPI_GELU, EPI_TANH) else out
 
 
 def layernorm_fwd(x, gamma, beta, eps, out_bf16=True, save_stats=True):

@@ -37,6 +37,7 @@ struct GemmArgs {
     int n_half;          // EPI_SWIGLU: H (B rows [0,H) = fc1, [H,2H) = fc3); N must equal H
     float alpha;         // EPI_F32 / EPI_BF16: out = alpha * (acc + bias)
     const float* alpha_dev;   // optional device scalar folded into alpha
+    int act;             // EPI_GELU family: 0 = GELU(erf), 1 = tanh
 };
 
 template <int BN>
@@ -257,7 +258,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
                                 const float2 pr = unpack_bf16x2(p[j]);       // activation sees the bf16-rounded pre-activation
-                                g[j] = pack_bf16x2(gelu_erf(pr.x), gelu_erf(pr.y));
+                                g[j] = args.act == 0 ? pack_bf16x2(gelu_erf(pr.x), gelu_erf(pr.y)) : pack_bf16x2(tanhf(pr.x), tanhf(pr.y));
                             }
                             if (full) {
 #pragma unroll
@@ -347,7 +348,9 @@ extern "C" int b200fm_gemm_bf16(int layout, int epilogue, int M, int N, int K, c
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     B200FM_CHECK(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
     B200FM_CHECK(layout >= 0 && layout <= 2, "gemm: bad layout %d", layout);
-    B200FM_CHECK(epilogue >= 0 && epilogue <= 4, "gemm: bad epilogue %d", epilogue);
+    B200FM_CHECK(epilogue >= 0 && epilogue <= 5, "gemm: bad epilogue %d", epilogue);
+    const int act = (epilogue == B200FM_EPI_TANH) ? 1 : 0;
+    if (epilogue == B200FM_EPI_TANH) epilogue = B200FM_EPI_GELU;
     B200FM_CHECK(A && B && out0, "gemm: null pointer");
     B200FM_CHECK((lda % 8) == 0 && (ldb % 8) == 0, "gemm: lda/ldb must be multiples of 8 elements (16 B rows) for TMA, got %lld %lld", lda, ldb);
     if (epilogue == B200FM_EPI_BF16 || epilogue == B200FM_EPI_GELU || epilogue == B200FM_EPI_SWIGLU)
@@ -360,7 +363,7 @@ extern "C" int b200fm_gemm_bf16(int layout, int epilogue, int M, int N, int K, c
     GemmArgs a;
     a.M = M; a.N = N; a.K = K;
     a.out0 = out0; a.ld0 = ld0; a.out1 = out1; a.ld1 = ld1; a.bias = bias; a.resid = resid; a.ldr = ldr;
-    a.n_half = N; a.alpha = alpha; a.alpha_dev = alpha_dev;
+    a.n_half = N; a.alpha = alpha; a.alpha_dev = alpha_dev; a.act = act;
     a.num_m_blocks = (M + kBM - 1) / kBM;
 
     // tile width: 256 when there is enough N to fill it and enough tiles to fill the machine, else 128

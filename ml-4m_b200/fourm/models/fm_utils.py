@@ -124,7 +124,7 @@ class Mlp(nn.Module):
 
     def hidden(self, x):
         if _plain_linear(self.fc1) and type(self.act) is nn.GELU and getattr(self.act, "approximate", "none") == "none":
-            return BF.MlpActFn.apply(x, self.fc1.weight, self.fc1.bias)
+            return BF.MlpActFn.apply(x, self.fc1.weight, self.fc1.bias, "gelu")
         return self.act(_linear(self.fc1, x))
 
     def forward(self, x):
