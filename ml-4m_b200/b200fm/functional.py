@@ -380,3 +380,212 @@ class EmbedRowsFn(torch.autograd.Function):
         dmt = torch.zeros(D, device=dev, dtype=torch.float32) if (ctx.mask_token_shape is not None and ctx.needs_input_grad[4]) else None
         ops.embed_rows_bwd(plan, segs, dx0.contiguous(), None if demb is None else demb.contiguous(), dmt, D)
         return (None, None, None, None, None if dmt is None else dmt.view(ctx.mask_token_shape), *grads)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# fused sub-layers: one autograd node per residual branch.  The backward chains the kernels by hand so that
+#   * the residual-stream gradient add is done inside the LayerNorm-backward kernel (dres),
+#   * that kernel also emits the bf16 copy of the new residual gradient that the next (earlier) sub-layer's dgrad / wgrad
+#     GEMMs consume (handed over as an attribute of the fp32 gradient tensor; absent -> one cast kernel),
+# which removes every framework element-wise kernel from the block stack's backward.
+# ----------------------------------------------------------------------------------------------------------------------
+def _grad_bf16(dout2, dout):
+    b = getattr(dout, "_b200fm_bf16", None)
+    if b is not None and b.shape == dout2.shape:
+        return b
+    return ops.cast_bf16(dout2) if dout2.dtype == torch.float32 else dout2
+
+
+def _hand_over(dx, dxb, shape):
+    out = dx.view(shape)
+    out._b200fm_bf16 = dxb
+    return out
+
+
+class SelfAttnSubLayerFn(torch.autograd.Function):
+    """x + proj(attention(qkv(LN(x)))) -- fm_utils.py:332 / 363 with Attention.forward (:160-180)."""
+
+    @staticmethod
+    def forward(ctx, x, mask, nw, nb, qkv_w, qkv_b, proj_w, proj_b, eps, heads, scale):
+        B, N, D = x.shape
+        x2 = x.reshape(B * N, D)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        h, mean, rstd = ops.layernorm_fwd(x2, nw, nb, eps, out_bf16=True)
+        qkv = ops.gemm(h, weight_bf16(qkv_w), epilogue=ops.EPI_BF16, bias=qkv_b, n_out=3 * D)
+        o, stats = ops.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, heads, N, N, mask, scale)
+        out = ops.gemm(o, weight_bf16(proj_w), epilogue=ops.EPI_RESID, bias=proj_b, resid=x2, n_out=D)
+        ctx.save_for_backward(x2, mean, rstd, h, qkv, o, stats, mask, nw, qkv_w, proj_w)
+        ctx.cfg = (B, N, D, heads, scale, qkv_b is not None, proj_b is not None, nb is not None and nb.requires_grad)
+        return out.view(B, N, D)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, mean, rstd, h, qkv, o, stats, mask, nw, qkv_w, proj_w = ctx.saved_tensors
+        B, N, D, heads, scale, has_qb, has_pb, nb_grad = ctx.cfg
+        d2 = dout.reshape(B * N, D)
+        if not d2.is_contiguous():
+            d2 = d2.contiguous()
+        db = _grad_bf16(d2, dout)
+        do = ops.gemm(db, weight_bf16(proj_w)[:D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
+        dproj_w = ops.gemm(db, o, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if proj_w.requires_grad else None
+        dproj_b = ops.colsum_bf16(db) if has_pb else None
+        dqkv = torch.empty_like(qkv)
+        ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o, do, stats, B, heads, N, N, mask, scale,
+                          dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:])
+        dh = ops.gemm(dqkv, weight_bf16(qkv_w)[:3 * D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
+        dqkv_w = ops.gemm(dqkv, h, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if qkv_w.requires_grad else None
+        dqkv_b = ops.colsum_bf16(dqkv) if has_qb else None
+        dgamma = torch.zeros(D, device=x2.device, dtype=torch.float32) if nw.requires_grad else None
+        dbeta = torch.zeros(D, device=x2.device, dtype=torch.float32) if nb_grad else None
+        dx, dxb = ops.layernorm_bwd(dh, x2, nw, mean, rstd, dres=d2, want_bf16=True, dgamma=dgamma, dbeta=dbeta)
+        return _hand_over(dx, dxb, (B, N, D)), None, dgamma, dbeta, dqkv_w, dqkv_b, dproj_w, dproj_b, None, None, None
+
+
+class CrossAttnSubLayerFn(torch.autograd.Function):
+    """x + proj(attention(q(LNq(x)), kv(LNc(context)))) -- fm_utils.py:364 with CrossAttention.forward (:197-219)."""
+
+    @staticmethod
+    def forward(ctx, x, context, mask, qnw, qnb, cnw, cnb, q_w, q_b, kv_w, kv_b, proj_w, proj_b, eps_q, eps_c, heads, scale):
+        B, N, D = x.shape
+        M = context.shape[1]
+        x2 = x.reshape(B * N, D)
+        c2 = context.reshape(B * M, D)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        if not c2.is_contiguous():
+            c2 = c2.contiguous()
+        hq, qmean, qrstd = ops.layernorm_fwd(x2, qnw, qnb, eps_q, out_bf16=True)
+        hc, cmean, crstd = ops.layernorm_fwd(c2, cnw, cnb, eps_c, out_bf16=True)
+        q = ops.gemm(hq, weight_bf16(q_w), epilogue=ops.EPI_BF16, bias=q_b, n_out=D)
+        kv = ops.gemm(hc, weight_bf16(kv_w), epilogue=ops.EPI_BF16, bias=kv_b, n_out=2 * D)
+        o, stats = ops.attention_fwd(q, kv[:, :D], kv[:, D:], B, heads, N, M, mask, scale)
+        out = ops.gemm(o, weight_bf16(proj_w), epilogue=ops.EPI_RESID, bias=proj_b, resid=x2, n_out=D)
+        ctx.save_for_backward(x2, c2, qmean, qrstd, cmean, crstd, hq, hc, q, kv, o, stats, mask, qnw, cnw, q_w, kv_w, proj_w)
+        ctx.cfg = (B, N, M, D, heads, scale, q_b is not None, kv_b is not None, proj_b is not None,
+                   qnb is not None and qnb.requires_grad, cnb is not None and cnb.requires_grad)
+        return out.view(B, N, D)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x2, c2, qmean, qrstd, cmean, crstd, hq, hc, q, kv, o, stats, mask, qnw, cnw, q_w, kv_w, proj_w) = ctx.saved_tensors
+        B, N, M, D, heads, scale, has_qb, has_kvb, has_pb, qnb_grad, cnb_grad = ctx.cfg
+        dev = x2.device
+        d2 = dout.reshape(B * N, D)
+        if not d2.is_contiguous():
+            d2 = d2.contiguous()
+        db = _grad_bf16(d2, dout)
+        do = ops.gemm(db, weight_bf16(proj_w)[:D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
+        dproj_w = ops.gemm(db, o, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if proj_w.requires_grad else None
+        dproj_b = ops.colsum_bf16(db) if has_pb else None
+        dq = torch.empty_like(q)
+        dkv = torch.empty_like(kv)
+        ops.attention_bwd(q, kv[:, :D], kv[:, D:], o, do, stats, B, heads, N, M, mask, scale, dq, dkv[:, :D], dkv[:, D:])
+        dhq = ops.gemm(dq, weight_bf16(q_w)[:D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
+        dq_w = ops.gemm(dq, hq, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if q_w.requires_grad else None
+        dq_b = ops.colsum_bf16(dq) if has_qb else None
+        dkv_w = ops.gemm(dkv, hc, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if kv_w.requires_grad else None
+        dkv_b = ops.colsum_bf16(dkv) if has_kvb else None
+        dqg = torch.zeros(D, device=dev, dtype=torch.float32) if qnw.requires_grad else None
+        dqb = torch.zeros(D, device=dev, dtype=torch.float32) if qnb_grad else None
+        dx, dxb = ops.layernorm_bwd(dhq, x2, qnw, qmean, qrstd, dres=d2, want_bf16=True, dgamma=dqg, dbeta=dqb)
+        dctx = dcg = dcb = None
+        if ctx.needs_input_grad[1]:
+            dhc = ops.gemm(dkv, weight_bf16(kv_w)[:2 * D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
+            dcg = torch.zeros(D, device=dev, dtype=torch.float32) if cnw.requires_grad else None
+            dcb = torch.zeros(D, device=dev, dtype=torch.float32) if cnb_grad else None
+            dctx, _ = ops.layernorm_bwd(dhc, c2, cnw, cmean, crstd, dgamma=dcg, dbeta=dcb)
+            dctx = dctx.view(B, M, D)
+        return (_hand_over(dx, dxb, (B, N, D)), dctx, None, dqg, dqb, dcg, dcb, dq_w, dq_b, dkv_w, dkv_b, dproj_w, dproj_b,
+                None, None, None, None)
+
+
+class GatedMlpSubLayerFn(torch.autograd.Function):
+    """x + fc2(silu(fc1 LN(x)) * fc3 LN(x)) -- fm_utils.py:333 / 365 with GatedMlp.forward (:142-144)."""
+
+    @staticmethod
+    def forward(ctx, x, nw, nb, w1, w3, w2, b1, b3, b2, eps):
+        shape = x.shape
+        D = shape[-1]
+        x2 = x.reshape(-1, D)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        H, Hp = w1.shape[0], _pad_rows(w1.shape[0])
+        h, mean, rstd = ops.layernorm_fwd(x2, nw, nb, eps, out_bf16=True)
+        bias13 = None
+        if b1 is not None:
+            bias13 = torch.zeros(2 * Hp, device=x2.device, dtype=torch.float32)
+            bias13[:H] = b1
+            bias13[Hp:Hp + H] = b3
+        ab, g = ops.gemm(h, weight_bf16(w1, w3), epilogue=ops.EPI_SWIGLU, bias=bias13)           # [R, 2Hp], [R, Hp]
+        w2b = weight_bf16(w2)
+        out = ops.gemm(g[:, :H] if Hp != H else g, w2b, epilogue=ops.EPI_RESID, bias=b2, resid=x2, n_out=D)
+        ctx.save_for_backward(x2, mean, rstd, h, ab, g, nw, w1, w3, w2)
+        ctx.cfg = (shape, D, H, Hp, b1 is not None, b2 is not None, nb is not None and nb.requires_grad)
+        return out.view(shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, mean, rstd, h, ab, g, nw, w1, w3, w2 = ctx.saved_tensors
+        shape, D, H, Hp, has_b13, has_b2, nb_grad = ctx.cfg
+        d2 = dout.reshape(-1, D)
+        if not d2.is_contiguous():
+            d2 = d2.contiguous()
+        db = _grad_bf16(d2, dout)
+        gH = g[:, :H] if Hp != H else g
+        if Hp != H:
+            dg = torch.zeros_like(g)
+            ops.gemm(db, weight_bf16(w2)[:D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16, out=dg[:, :H])
+        else:
+            dg = ops.gemm(db, weight_bf16(w2)[:D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
+        dw2 = ops.gemm(db, gH, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if w2.requires_grad else None
+        db2 = ops.colsum_bf16(db) if has_b2 else None
+        dab = ops.swiglu_bwd(ab, dg)
+        dh = ops.gemm(dab, weight_bf16(w1, w3), layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
+        dw1 = dw3 = db1 = db3 = None
+        if w1.requires_grad or w3.requires_grad:
+            dw13 = ops.gemm(dab, h, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32)
+            dw1, dw3 = dw13[:H], dw13[Hp:Hp + H]
+        if has_b13:
+            dbias = ops.colsum_bf16(dab)
+            db1, db3 = dbias[:H], dbias[Hp:Hp + H]
+        dgamma = torch.zeros(D, device=x2.device, dtype=torch.float32) if nw.requires_grad else None
+        dbeta = torch.zeros(D, device=x2.device, dtype=torch.float32) if nb_grad else None
+        dx, dxb = ops.layernorm_bwd(dh, x2, nw, mean, rstd, dres=d2, want_bf16=True, dgamma=dgamma, dbeta=dbeta)
+        return _hand_over(dx, dxb, shape), dgamma, dbeta, dw1, dw3, dw2, db1, db3, db2, None
+
+
+class NormLinearResidualFn(torch.autograd.Function):
+    """resid + bf16(LN(x) W^T + b):  decoder_proj_context(encoder_norm(x)) + encoder_emb  (fm.py:678-679)."""
+
+    @staticmethod
+    def forward(ctx, x, nw, nb, w, b, resid, eps):
+        D = x.shape[-1]
+        x2 = x.reshape(-1, D)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        r2 = resid.reshape(-1, w.shape[0])
+        if not r2.is_contiguous():
+            r2 = r2.contiguous()
+        h, mean, rstd = ops.layernorm_fwd(x2, nw, nb, eps, out_bf16=True)
+        out = ops.gemm(h, weight_bf16(w), epilogue=ops.EPI_RESID, bias=b, resid=r2, n_out=w.shape[0])
+        ctx.save_for_backward(x2, mean, rstd, h, nw, w)
+        ctx.cfg = (x.shape, resid.shape, b is not None, nb is not None and nb.requires_grad)
+        return out.view(resid.shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, mean, rstd, h, nw, w = ctx.saved_tensors
+        xshape, rshape, has_b, nb_grad = ctx.cfg
+        D = x2.shape[1]
+        d2 = dout.reshape(-1, w.shape[0])
+        if not d2.is_contiguous():
+            d2 = d2.contiguous()
+        db = _grad_bf16(d2, dout)
+        dh = ops.gemm(db, weight_bf16(w)[:w.shape[0]], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
+        dw = ops.gemm(db, h, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if w.requires_grad else None
+        dbias = ops.colsum_bf16(db) if has_b else None
+        dgamma = torch.zeros(D, device=x2.device, dtype=torch.float32) if nw.requires_grad else None
+        dbeta = torch.zeros(D, device=x2.device, dtype=torch.float32) if nb_grad else None
+        dx, dxb = ops.layernorm_bwd(dh, x2, nw, mean, rstd, want_bf16=True, dgamma=dgamma, dbeta=dbeta)
+        return _hand_over(dx, dxb, xshape), dgamma, dbeta, dw, dbias, dout.view(rshape), None

@@ -164,13 +164,27 @@ __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              __nv_bfloat16* __restrict__ shadow, long long n, float lr, float beta1, float beta2, float eps,
                              float wd, float bc1, float bc2_sqrt, float grad_scale) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float decay = 1.0f - lr * wd, step = lr / bc1, ob1 = 1.0f - beta1, ob2 = 1.0f - beta2;
+    const long long n4 = n >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+        float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+        float* pp = &p4.x; float* mm = &m4.x; float* vv = &v4.x; const float* gg = &g4.x;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float gi = gg[e] * grad_scale;
+            mm[e] = beta1 * mm[e] + ob1 * gi;
+            vv[e] = beta2 * vv[e] + ob2 * gi * gi;
+            pp[e] = pp[e] * decay - step * (mm[e] / (sqrtf(vv[e]) / bc2_sqrt + eps));
+        }
+        reinterpret_cast<float4*>(p)[i] = p4; reinterpret_cast<float4*>(m)[i] = m4; reinterpret_cast<float4*>(v)[i] = v4;
+        if (shadow) reinterpret_cast<uint2*>(shadow)[i] = make_uint2(pack_bf16x2(p4.x, p4.y), pack_bf16x2(p4.z, p4.w));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const long long i = n4 * 4 + threadIdx.x;
         const float gi = g[i] * grad_scale;
-        float pi = p[i] * (1.0f - lr * wd);
-        const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
-        const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
-        const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        pi -= (lr / bc1) * (mi / denom);
+        const float mi = beta1 * m[i] + ob1 * gi, vi = beta2 * v[i] + ob2 * gi * gi;
+        const float pi = p[i] * decay - step * (mi / (sqrtf(vi) / bc2_sqrt + eps));
         p[i] = pi; m[i] = mi; v[i] = vi;
         if (shadow) shadow[i] = __float2bfloat16_rn(pi);
     }
@@ -256,7 +270,9 @@ extern "C" int b200fm_adamw(float* p, const float* g, float* m, float* v, void* 
     B200FM_CHECK(step >= 1, "adamw: step must be >= 1");
     const float bc1 = 1.0f - powf(beta1, (float)step);
     const float bc2s = sqrtf(1.0f - powf(beta2, (float)step));
-    adamw_kernel<<<ew_grid(n, 256), 256, 0, stream>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n, lr, beta1, beta2, eps,
+    B200FM_CHECK(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
+                 (shadow_bf16 == nullptr || (reinterpret_cast<uintptr_t>(shadow_bf16) & 7) == 0), "adamw: buffers must be 16-byte aligned");
+    adamw_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, stream>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n, lr, beta1, beta2, eps,
                                                     weight_decay, bc1, bc2s, grad_scale);
     B200FM_CUDA(cudaGetLastError());
     return 0;

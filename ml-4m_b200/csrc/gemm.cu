@@ -38,6 +38,8 @@ struct GemmArgs {
     float alpha;         // EPI_F32 / EPI_BF16: out = alpha * (acc + bias)
     const float* alpha_dev;   // optional device scalar folded into alpha
     int act;             // EPI_GELU family: 0 = GELU(erf), 1 = tanh
+    int k_splits;        // EPI_F32 only: > 1 -> each work item covers a K slice and accumulates with fp32 atomics (out pre-zeroed)
+    int kb_per_split;
 };
 
 template <int BN>
@@ -73,8 +75,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = args.num_m_blocks * args.num_n_blocks;
-    const int num_kb = (args.K + kBK - 1) / kBK;
+    const int num_mn = args.num_m_blocks * args.num_n_blocks;
+    const int num_tiles = num_mn * args.k_splits;               // work items: (k slice, n block, m block), m fastest
+    const int num_kb_total = (args.K + kBK - 1) / kBK;
 
     if (warp == 4) {
         if (lane == 0) {
@@ -97,11 +100,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile % args.num_m_blocks;
-                const int n_blk = tile / args.num_m_blocks;
+                const int mn = tile % num_mn, ks = tile / num_mn;
+                const int m_blk = mn % args.num_m_blocks;
+                const int n_blk = mn / args.num_m_blocks;
                 const int m0 = m_blk * kBM;
                 const int n0 = (EPI == B200FM_EPI_SWIGLU) ? n_blk * (BN / 2) : n_blk * BN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb_begin = ks * args.kb_per_split;
+                const int kb_end = min(kb_begin + args.kb_per_split, num_kb_total);
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * SM::kStageBytes;
                     uint8_t* sb = sa + kABytes;
@@ -139,6 +145,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int ks = tile / num_mn;
+                const int kb_begin = ks * args.kb_per_split;
+                const int num_kb = min(kb_begin + args.kb_per_split, num_kb_total) - kb_begin;
                 mbar_wait(&tempty_bar[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
@@ -164,8 +173,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         // ------------------------------ epilogue warps 0..3 ------------------------------
         int as = 0; uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile % args.num_m_blocks;
-            const int n_blk = tile / args.num_m_blocks;
+            const int mn = tile % num_mn;
+            const int m_blk = mn % args.num_m_blocks;
+            const int n_blk = mn / args.num_m_blocks;
             const int row = m_blk * kBM + warp * 32 + lane;
             const bool row_ok = row < args.M;
             mbar_wait(&tfull_bar[as], aphase);
@@ -270,7 +280,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                         }
                     } else if constexpr (EPI == B200FM_EPI_F32) {
                         float* o0 = reinterpret_cast<float*>(args.out0) + static_cast<long long>(row) * args.ld0 + n;
-                        if (full && (args.ld0 & 3) == 0) {
+                        if (args.k_splits > 1) {
+                            if (full && (args.ld0 & 3) == 0) {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    atomicAdd(reinterpret_cast<float4*>(o0) + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+                            } else {
+                                for (int j = 0; j < 32 && n + j < args.N; ++j) atomicAdd(o0 + j, v[j]);
+                            }
+                        } else if (full && (args.ld0 & 3) == 0) {
 #pragma unroll
                             for (int q = 0; q < 8; ++q)
                                 reinterpret_cast<float4*>(o0)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -331,7 +349,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
         B200FM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    const int tiles = a.num_m_blocks * a.num_n_blocks;
+    const int tiles = a.num_m_blocks * a.num_n_blocks * a.k_splits;
     const int grid = tiles < sm_count() ? tiles : sm_count();
     kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, a);
     B200FM_CUDA(cudaGetLastError());
@@ -367,15 +385,29 @@ extern "C" int b200fm_gemm_bf16(int layout, int epilogue, int M, int N, int K, c
     a.num_m_blocks = (M + kBM - 1) / kBM;
 
     // tile width: 256 when there is enough N to fill it and enough tiles to fill the machine, else 128
+    a.k_splits = 1;
+    a.kb_per_split = (K + kBK - 1) / kBK;
     int BN = 256;
     if (epilogue == B200FM_EPI_SWIGLU) {
         BN = 256;                                   // 128 a-columns + 128 b-columns per tile
         a.num_n_blocks = (N + 127) / 128;
     } else {
         const int tiles256 = a.num_m_blocks * ((N + 255) / 256);
-        if (N <= 128 || tiles256 < sm_count()) BN = 128;
+        const int num_kb = (K + kBK - 1) / kBK;
+        if (epilogue == B200FM_EPI_F32 && bias == nullptr && N > 128 && tiles256 < 2 * sm_count() && num_kb >= 32) {
+            // few output tiles, long K (weight gradients): keep the 128x256 tile and split K across CTAs (fp32 atomics)
+            BN = 256;
+            int splits = (2 * sm_count() + tiles256 - 1) / tiles256;
+            if (splits > num_kb / 8) splits = num_kb / 8;
+            if (splits < 1) splits = 1;
+            a.kb_per_split = (num_kb + splits - 1) / splits;
+            a.k_splits = (num_kb + a.kb_per_split - 1) / a.kb_per_split;
+        } else if (N <= 128 || tiles256 < sm_count()) {
+            BN = 128;
+        }
         a.num_n_blocks = (N + BN - 1) / BN;
     }
+    if (a.k_splits > 1) B200FM_CUDA(cudaMemsetAsync(out0, 0, sizeof(float) * (size_t)M * (size_t)ld0 - sizeof(float) * (size_t)(ld0 - N), stream));
 
     CUtensorMap ta, tb;
     int rc;

@@ -28,7 +28,7 @@ from b200fm import functional as BF
 from b200fm import lib, ops
 from b200fm.compat import MODALITY_INFO, PyTorchModelHubMixin, register_model
 
-from .fm_utils import Block, DecoderBlock, LayerNorm, _linear_residual, _norm_bf16
+from .fm_utils import Block, DecoderBlock, LayerNorm, _linear_residual, _norm_bf16, _norm_params
 
 # the 13 registered model names of the reference (fm.py:33-50); `register_model` appends them to __all__
 _PRESET_NAMES = (
@@ -289,6 +289,10 @@ class FourM(nn.Module):
         emits the bf16 GEMM operand and the `+ encoder_emb` rides in the GEMM epilogue."""
         for blk in self.encoder:
             x = blk(x, mask=encoder_mask)
+        np_ = _norm_params(self.encoder_norm)
+        if np_ is not None and type(self.decoder_proj_context) is nn.Linear and x.dtype == torch.float32:
+            return BF.NormLinearResidualFn.apply(x, np_[0], np_[1], self.decoder_proj_context.weight, self.decoder_proj_context.bias,
+                                                 encoder_emb, np_[2])
         return _linear_residual(self.decoder_proj_context, _norm_bf16(self.encoder_norm, x), encoder_emb)
 
     # ------------------------------------------------------------------ heads

@@ -274,6 +274,57 @@ def _residual_ok(block):
     return isinstance(block.drop_path, nn.Identity) or not block.training
 
 
+def _norm_params(norm):
+    """(weight, bias, eps) of a LayerNorm the kernels can run, else None."""
+    if isinstance(norm, LayerNorm) or (type(norm) is nn.LayerNorm and norm.elementwise_affine):
+        return norm.weight, norm.bias, norm.eps
+    return None
+
+
+def _plain_attention(a):
+    return (type(a) is Attention and _plain_linear(a.qkv) and _plain_linear(a.proj) and not a.allow_zero_attn
+            and (a.proj_drop.p == 0. or not a.training) and (a.attn_drop.p == 0. or not a.training))
+
+
+def _plain_cross_attention(a):
+    return (type(a) is CrossAttention and _plain_linear(a.q) and _plain_linear(a.kv) and _plain_linear(a.proj)
+            and not a.allow_zero_attn and (a.proj_drop.p == 0. or not a.training) and (a.attn_drop.p == 0. or not a.training))
+
+
+def _plain_gated_mlp(m):
+    return (type(m) is GatedMlp and _plain_linear(m.fc1) and _plain_linear(m.fc2) and _plain_linear(m.fc3) and type(m.act) is nn.SiLU)
+
+
+def _self_attn_sublayer(norm, attn, x, mask):
+    """x + attn(norm(x)) as ONE autograd node when every piece is a plain module; None otherwise."""
+    np_ = _norm_params(norm)
+    if np_ is None or not _plain_attention(attn) or x.shape[-1] // attn.num_heads != 64 or x.dtype != torch.float32:
+        return None
+    B, N, _ = x.shape
+    return BF.SelfAttnSubLayerFn.apply(x, _prep_mask(mask, B, N, N), np_[0], np_[1], attn.qkv.weight, attn.qkv.bias,
+                                       attn.proj.weight, attn.proj.bias, np_[2], attn.num_heads, attn.scale)
+
+
+def _cross_attn_sublayer(qnorm, cnorm, attn, x, context, mask):
+    qp, cp = _norm_params(qnorm), _norm_params(cnorm)
+    if qp is None or cp is None or not _plain_cross_attention(attn) or x.shape[-1] // attn.num_heads != 64:
+        return None
+    if x.dtype != torch.float32 or context.dtype != torch.float32:
+        return None
+    B, N, _ = x.shape
+    return BF.CrossAttnSubLayerFn.apply(x, context, _prep_mask(mask, B, N, context.shape[1]), qp[0], qp[1], cp[0], cp[1],
+                                        attn.q.weight, attn.q.bias, attn.kv.weight, attn.kv.bias, attn.proj.weight, attn.proj.bias,
+                                        qp[2], cp[2], attn.num_heads, attn.scale)
+
+
+def _mlp_sublayer(norm, mlp, x):
+    np_ = _norm_params(norm)
+    if np_ is None or not _plain_gated_mlp(mlp) or x.dtype != torch.float32:
+        return None
+    return BF.GatedMlpSubLayerFn.apply(x, np_[0], np_[1], mlp.fc1.weight, mlp.fc3.weight, mlp.fc2.weight, mlp.fc1.bias,
+                                       mlp.fc3.bias, mlp.fc2.bias, np_[2])
+
+
 class Block(nn.Module):
     """Pre-norm encoder block x += attn(norm1 x); x += mlp(norm2 x) (reference fm_utils.py:310-334).
     The residual adds are fused into the proj / fc2 GEMM epilogues, the norms emit the bf16 GEMM operand directly."""
@@ -296,8 +347,10 @@ class Block(nn.Module):
 
     def forward(self, x, mask=None):
         if _residual_ok(self):
-            x = self.attn.forward_residual(_norm_bf16(self.norm1, x), x, mask)
-            x = self.mlp.forward_residual(_norm_bf16(self.norm2, x), x)
+            y = _self_attn_sublayer(self.norm1, self.attn, x, mask)
+            x = y if y is not None else self.attn.forward_residual(_norm_bf16(self.norm1, x), x, mask)
+            y = _mlp_sublayer(self.norm2, self.mlp, x)
+            x = y if y is not None else self.mlp.forward_residual(_norm_bf16(self.norm2, x), x)
             return x
         x = x + self.drop_path(self.attn(_norm_bf16(self.norm1, x), mask))
         x = x + self.drop_path(self.mlp(_norm_bf16(self.norm2, x)))
@@ -330,9 +383,13 @@ class DecoderBlock(nn.Module):
 
     def forward(self, x, context, sa_mask=None, xa_mask=None):
         if _residual_ok(self):
-            x = self.self_attn.forward_residual(_norm_bf16(self.norm1, x), x, sa_mask)
-            x = self.cross_attn.forward_residual(_norm_bf16(self.query_norm, x), _norm_bf16(self.context_norm, context), x, xa_mask)
-            x = self.mlp.forward_residual(_norm_bf16(self.norm2, x), x)
+            y = _self_attn_sublayer(self.norm1, self.self_attn, x, sa_mask)
+            x = y if y is not None else self.self_attn.forward_residual(_norm_bf16(self.norm1, x), x, sa_mask)
+            y = _cross_attn_sublayer(self.query_norm, self.context_norm, self.cross_attn, x, context, xa_mask)
+            x = y if y is not None else self.cross_attn.forward_residual(_norm_bf16(self.query_norm, x),
+                                                                        _norm_bf16(self.context_norm, context), x, xa_mask)
+            y = _mlp_sublayer(self.norm2, self.mlp, x)
+            x = y if y is not None else self.mlp.forward_residual(_norm_bf16(self.norm2, x), x)
             return x
         x = x + self.drop_path(self.self_attn(_norm_bf16(self.norm1, x), sa_mask))
         x = x + self.drop_path(self.cross_attn(_norm_bf16(self.query_norm, x), _norm_bf16(self.context_norm, context), xa_mask))

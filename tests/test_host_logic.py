@@ -1,0 +1,116 @@
+"""Host-side logic that needs no GPU: model registry / state_dict contract / parameter sharing of the overlay, the synthetic
+wire-format batches, segment construction, the loud no-fallback behaviour, and the N>1 launch contract of bench.py
+(world_size 2 under torchrun on CPU)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import fourm_oracle as O
+from tests import helpers as H
+
+ROOT = H.ROOT
+
+
+@pytest.fixture(scope="module")
+def tiny_cpu():
+    from b200fm.compat import build_mod7_embeddings, create_model
+    enc, dec, info = build_mod7_embeddings()
+    return create_model("fm_tiny_6e_6d_swiglu_nobias", encoder_embeddings=enc, decoder_embeddings=dec, modality_info=info)
+
+
+def test_registry_has_the_13_reference_names():
+    import fourm.models.fm as fm
+    from b200fm import compat
+    names = ['fm_tiny_6e_6d_gelu', 'fm_small_8e_8d_gelu', 'fm_base_12e_12d_gelu', 'fm_large_24e_24d_gelu', 'fm_xlarge_24e_24d_gelu',
+             'fm_tiny_6e_6d_swiglu_nobias', 'fm_small_8e_8d_swiglu_nobias', 'fm_base_12e_12d_swiglu_nobias',
+             'fm_large_24e_24d_swiglu_nobias', 'fm_xlarge_24e_24d_swiglu_nobias', 'fm_base_12e_12d_swiglu_qknorm_nobias',
+             'fm_large_24e_24d_swiglu_qknorm_nobias', 'fm_xlarge_24e_24d_swiglu_qknorm_nobias']      # reference fm.py:33-50
+    assert sorted(fm.__all__) == sorted(names)
+    for n in names:
+        assert callable(getattr(fm, n)) and n in compat._local_entrypoints
+
+
+def test_state_dict_matches_reference_golden_shapes(tiny_cpu):
+    gold = H.load_golden("fourm_tiny_golden.pt")
+    sd = tiny_cpu.state_dict()
+    assert list(sd.keys()) == list(gold["shapes"].keys())
+    assert all(tuple(v.shape) == gold["shapes"][k] and v.dtype == torch.float32 for k, v in sd.items())
+    assert [k for k, _ in tiny_cpu.named_parameters(remove_duplicate=False)] == gold["param_names"]
+    # sincos buffers are bit-identical to the reference's tables (same construction)
+    assert torch.equal(sd["encoder_embeddings.tok_rgb@224.pos_emb"], O.sincos_2d(14, 14, 384))
+    assert torch.equal(sd["encoder_embeddings.caption.pos_emb"], O.sincos_1d(512, 384))
+
+
+def test_parameter_sharing_and_weight_decay_groups(tiny_cpu):
+    from b200fm.optim import param_groups_like_reference
+    m = tiny_cpu
+    for mod in ("caption", "tok_rgb@224"):
+        assert m.decoder_embeddings[mod].mod_emb is m.encoder_embeddings[mod].mod_emb
+        assert m.decoder_embeddings[mod].to_logits.weight is m.decoder_embeddings[mod].token_emb.weight
+    groups = param_groups_like_reference(m, 0.05)
+    decay, no_decay = groups
+    ids_no = {id(p) for p in no_decay["params"]}
+    assert id(m.encoder[0].norm1.weight) in ids_no and id(m.decoder_proj_context.bias) in ids_no
+    assert id(m.encoder[0].attn.qkv.weight) not in ids_no and decay["weight_decay"] == 0.05
+    n = sum(p.numel() for g in groups for p in g["params"])
+    assert n == sum(p.numel() for p in m.parameters())
+
+
+def test_forward_refuses_cpu_tensors(tiny_cpu):
+    from b200fm import lib
+    batch = O.synthetic_mod7_batch(1)
+    with pytest.raises(lib.B200FMError):
+        tiny_cpu(batch, num_encoder_tokens=128, num_decoder_tokens=128)
+
+
+def test_invalid_loss_type_raises_like_reference(tiny_cpu):
+    with pytest.raises(ValueError, match="Invalid loss type"):
+        tiny_cpu(O.synthetic_mod7_batch(1), 128, 128, loss_type="nope")
+
+
+def test_synthetic_batches_have_exact_budgets():
+    from b200fm.synthetic import budgets_for, mod7_batch
+    for n_tok in (128, 256):
+        a, b, c, d = budgets_for(n_tok)
+        batch = mod7_batch(3, a, b, c, d, seed=7)
+        n_in = sum((~v["input_mask"]).sum(1) for v in batch.values())
+        n_tgt = 0
+        for name, v in batch.items():
+            if name == "rgb@224":
+                continue
+            tm = v["target_mask"]
+            if v["tensor"].dim() == 2 and v["tensor"].dtype == torch.int32:      # sequences lose one row to the shift
+                tm = tm[:, 1:] | tm[:, :-1]
+            n_tgt = n_tgt + (~tm).sum(1)
+        assert n_in.tolist() == [n_tok] * 3 and n_tgt.tolist() == [n_tok] * 3
+        assert batch["caption"]["tensor"].shape == (3, 514) and batch["tok_rgb@224"]["tensor"].dtype == torch.int64
+
+
+def test_segment_struct_layout_matches_header():
+    import ctypes
+    import re
+    from b200fm import lib
+    text = open(os.path.join(ROOT, "include", "b200fm.h")).read()
+    body = text[text.index("typedef struct b200fm_segment {"):text.index("} b200fm_segment;")]
+    fields = re.findall(r"\b(\w+);\s*(?:/\*|$)", body, flags=re.M)
+    assert fields == [f[0] for f in lib.Segment._fields_]
+    assert ctypes.sizeof(lib.Segment) == 10 * 8 + 8 + 6 * 4
+    assert int(re.search(r"#define B200FM_MAX_SEGMENTS (\d+)", text).group(1)) == lib.MAX_SEGMENTS
+
+
+def test_bench_reference_arm_contract_under_torchrun_world2():
+    """`bench.py --impl reference` launched like the driver does for N=2 (gloo-free: rank 0 runs the CPU oracle, rank 1 exits 0)."""
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29731", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "tokens_per_sec" and j["value"] > 0 and j["n_gpus"] == 2
+    assert j["cpu_baseline"]["kind"] == "port" and j["e2e"]["h2d_bytes_per_step"] == 0
