@@ -200,9 +200,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     const bool row_ok = qrow < args.Nq;
                     const uint8_t* mrow = args.mask ? args.mask + b * args.mask_b_stride + (row_ok ? qrow : 0) * args.mask_q_stride : nullptr;
                     const float m = m_[qt], inv = inv_[qt], Dr = D_[qt];
+                    uint32_t mb[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) mb[c] = attn_mask_bits32(mrow, kt * 128 + c * 32, args.Nk);
                     mbar_wait(sdp_full, stepc & 1);
                     tc_fence_after();
-#pragma unroll 1
+#pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const int col0 = kt * 128 + c * 32;
                         uint32_t pk[16], dk_[16];
@@ -211,7 +214,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                             tmem_ld_x32(t_lane + kColS + c * 32, ss);
                             tmem_ld_x32(t_lane + kColDP + c * 32, dd);
                             tmem_ld_wait();
-                            const uint32_t mbits = attn_mask_bits32(mrow, col0, args.Nk);
+                            const uint32_t mbits = mb[c];
 #pragma unroll
                             for (int j = 0; j < 32; j += 2) {
                                 float p[2], ds[2];
@@ -220,7 +223,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                                     const bool masked = (mbits >> (j + e)) & 1u;
                                     float t = __uint_as_float(ss[j + e]) * args.scale_log2;
                                     if (masked) t = kMaskedScore;
-                                    float pe = exp2f(t - m) * inv;
+                                    float pe = fast_exp2(t - m) * inv;
                                     if (!row_ok || col0 + j + e >= args.Nk) pe = 0.f;
                                     p[e] = pe;
                                     ds[e] = masked ? 0.f : pe * (__uint_as_float(dd[j + e]) - Dr) * args.scale;

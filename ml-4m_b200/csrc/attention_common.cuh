@@ -11,6 +11,13 @@ namespace b200fm {
 // scale*log2e multiplication, so no overflow to -inf can occur.
 constexpr float kMaskedScore = -3.0e38f;
 
+// 2^x on the SFU (ex2.approx.ftz): exact 0 for x <= -150, 1 for x == 0 -- all the softmax needs.
+B200FM_DEVINL float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 B200FM_DEVINL uint32_t nonzero_bytes_to_bits(uint32_t w) {
     const uint32_t m = __vcmpne4(w, 0u) & 0x01010101u;
     return (m & 1u) | ((m >> 7) & 2u) | ((m >> 14) & 4u) | ((m >> 21) & 8u);

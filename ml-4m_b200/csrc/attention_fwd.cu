@@ -140,41 +140,46 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             const bool row_ok = qrow < args.Nq;
             const uint8_t* mrow = args.mask ? args.mask + b * args.mask_b_stride + (row_ok ? qrow : 0) * args.mask_q_stride : nullptr;
 
+            // mask bits of the whole row are fetched before the scores are ready (hides the global-load latency)
+            uint32_t mb[NKT * 4];
+#pragma unroll
+            for (int c = 0; c < NKT * 4; ++c) mb[c] = attn_mask_bits32(mrow, c * 32, args.Nk);
             mbar_wait(s_full, par);
             tc_fence_after();
             // pass 1: row maximum of t = s * scale * log2e (masked -> -3e38, padding keys -> -inf)
             float m = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < NKT * 4; ++c) {
-                if (c * 32 >= args.Nk) break;
-                uint32_t rr[32];
-                tmem_ld_x32(t_lane + c * 32, rr);
-                tmem_ld_wait();
-                uint32_t mbits = attn_mask_bits32(mrow, c * 32, args.Nk);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float t = __uint_as_float(rr[j]) * args.scale_log2;
-                    if ((mbits >> j) & 1u) t = kMaskedScore;
-                    if (c * 32 + j >= args.Nk) t = -INFINITY;
-                    m = fmaxf(m, t);
+            for (int c = 0; c < NKT * 4; ++c) {
+                if (c * 32 < args.Nk) {
+                    uint32_t rr[32];
+                    tmem_ld_x32(t_lane + c * 32, rr);
+                    tmem_ld_wait();
+                    const uint32_t mbits = mb[c];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float t = __uint_as_float(rr[j]) * args.scale_log2;
+                        if ((mbits >> j) & 1u) t = kMaskedScore;
+                        if (c * 32 + j >= args.Nk) t = -INFINITY;
+                        m = fmaxf(m, t);
+                    }
                 }
             }
             // pass 2: p = exp2(t - m), row sum, bf16 P into swizzled smem
             float sum = 0.f;
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < NKT * 4; ++c) {
                 uint32_t pk[16];
                 if (c * 32 < args.Nk) {
                     uint32_t rr[32];
                     tmem_ld_x32(t_lane + c * 32, rr);
                     tmem_ld_wait();
-                    uint32_t mbits = attn_mask_bits32(mrow, c * 32, args.Nk);
+                    const uint32_t mbits = mb[c];
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
                         float t0 = __uint_as_float(rr[j]) * args.scale_log2, t1 = __uint_as_float(rr[j + 1]) * args.scale_log2;
                         if ((mbits >> j) & 1u) t0 = kMaskedScore;
                         if ((mbits >> (j + 1)) & 1u) t1 = kMaskedScore;
-                        float p0 = exp2f(t0 - m), p1 = exp2f(t1 - m);
+                        float p0 = fast_exp2(t0 - m), p1 = fast_exp2(t1 - m);
                         if (c * 32 + j >= args.Nk) p0 = 0.f;
                         if (c * 32 + j + 1 >= args.Nk) p1 = 0.f;
                         const uint32_t w = pack_bf16x2(p0, p1);

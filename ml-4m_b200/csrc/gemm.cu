@@ -10,7 +10,8 @@
 //     LAYOUT_NN : A [M,K] row-major (K-major), B [K,N] row-major (N-major / "MN-major") dgrad    dx = dy W
 //     LAYOUT_TN : A [K,M] row-major (M-major), B [K,N] row-major (N-major)             wgrad    dW = dy^T x
 //
-// CTA = 6 warps: warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMA producer + TMEM allocator, warp 5 MMA issuer.
+// CTA = 10 warps: warps 0-7 epilogue (TMEM lane quarter = warp & 3, column half = warp >> 2; two warps per quarter keep the
+// epilogue off the critical path), warp 8 TMA producer + TMEM allocator, warp 9 MMA issuer.
 // Tile 128 x BN x 64, BN in {128, 256}; smem ring of (16 KB + BN*128 B) stages; accumulators 2 x BN TMEM columns.
 #include "../../include/b200fm.h"
 #include "common.cuh"
@@ -20,7 +21,8 @@ namespace b200fm {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;     // warps 0-7 epilogue (lane quarter = warp & 3, column half = warp >> 2), 8 = TMA, 9 = MMA
+constexpr int kEpiWarps = 8;
 
 enum GemmLayout { LAYOUT_NT = 0, LAYOUT_NN = 1, LAYOUT_TN = 2 };
 
@@ -51,7 +53,7 @@ struct GemmSmem {
 };
 
 B200FM_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-B200FM_DEVINL float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+B200FM_DEVINL float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 template <int BN, int LAYOUT, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -79,12 +81,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int num_tiles = num_mn * args.k_splits;               // work items: (k slice, n block, m block), m fastest
     const int num_kb_total = (args.K + kBK - 1) / kBK;
 
-    if (warp == 4) {
+    if (warp == kEpiWarps) {
         if (lane == 0) {
             tma_prefetch_desc(&tmap_a);
             tma_prefetch_desc(&tmap_b);
             for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-            for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+            for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps); }
             fence_mbar_init();
         }
         __syncwarp();
@@ -95,7 +97,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == kEpiWarps) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
@@ -139,7 +141,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == kEpiWarps + 1) {
         // ------------------------------ MMA issuer (single thread) ------------------------------
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
@@ -170,25 +172,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
         }
     } else {
-        // ------------------------------ epilogue warps 0..3 ------------------------------
+        // ------------------------------ epilogue warps 0..7 ------------------------------
+        const int quarter = warp & 3, half = warp >> 2;
         int as = 0; uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int mn = tile % num_mn;
             const int m_blk = mn % args.num_m_blocks;
             const int n_blk = mn / args.num_m_blocks;
-            const int row = m_blk * kBM + warp * 32 + lane;
+            const int row = m_blk * kBM + quarter * 32 + lane;
             const bool row_ok = row < args.M;
-            mbar_wait(&tfull_bar[as], aphase);
-            tc_fence_after();
-            const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(warp * 32) << 16);
+            const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
 
             if constexpr (EPI == B200FM_EPI_SWIGLU) {
+                mbar_wait(&tfull_bar[as], aphase);
+                tc_fence_after();
                 constexpr int HB = BN / 2;
                 const int n0 = n_blk * HB;
                 __nv_bfloat16* ab = reinterpret_cast<__nv_bfloat16*>(args.out0) + static_cast<long long>(row) * args.ld0;
                 __nv_bfloat16* gg = reinterpret_cast<__nv_bfloat16*>(args.out1) + static_cast<long long>(row) * args.ld1;
 #pragma unroll 1
-                for (int c = 0; c < HB / 16; ++c) {
+                for (int c = half * (HB / 32); c < (half + 1) * (HB / 32); ++c) {
                     uint32_t ra[16], rb[16];
                     tmem_ld_x16(t_acc + c * 16, ra);
                     tmem_ld_x16(t_acc + HB + c * 16, rb);
@@ -231,12 +234,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             } else {
                 const int n0 = n_blk * BN;
                 const float alpha = args.alpha * (args.alpha_dev ? __ldg(args.alpha_dev) : 1.0f);
+                constexpr int kChunks = BN / 64;                 // 32-column chunks per epilogue warp
+                const int c0 = half * kChunks;
+                [[maybe_unused]] float4 rnext[8];
+                [[maybe_unused]] bool rvec = false;
+                if constexpr (EPI == B200FM_EPI_RESID) {
+                    // the residual tile does not depend on the accumulator: fetch the first chunk before waiting for the MMAs,
+                    // and every following chunk one iteration ahead
+                    rvec = (args.ld0 & 3) == 0 && (args.ldr & 3) == 0;
+                    const int n = n0 + c0 * 32;
+                    if (rvec && row_ok && n + 32 <= args.N) {
+                        const float4* rs4 = reinterpret_cast<const float4*>(args.resid + static_cast<long long>(row) * args.ldr + n);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) rnext[q] = __ldg(rs4 + q);
+                    }
+                }
+                mbar_wait(&tfull_bar[as], aphase);
+                tc_fence_after();
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = c0; c < c0 + kChunks; ++c) {
                     uint32_t r[32];
                     tmem_ld_x32(t_acc + c * 32, r);
-                    tmem_ld_wait();
                     const int n = n0 + c * 32;
+                    [[maybe_unused]] float4 rcur[8];
+                    if constexpr (EPI == B200FM_EPI_RESID) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) rcur[q] = rnext[q];
+                        const int nn = n + 32;
+                        if (c + 1 < c0 + kChunks && rvec && row_ok && nn + 32 <= args.N) {
+                            const float4* rs4 = reinterpret_cast<const float4*>(args.resid + static_cast<long long>(row) * args.ldr + nn);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) rnext[q] = __ldg(rs4 + q);
+                        }
+                    }
+                    tmem_ld_wait();
                     if (!row_ok || n >= args.N) continue;
                     float v[32];
 #pragma unroll
@@ -296,16 +327,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                             for (int j = 0; j < 32 && n + j < args.N; ++j) o0[j] = v[j];
                         }
                     } else {   // EPI_RESID: out = resid + bf16_round(acc + bias)   (fp32 residual stream)
-                        const float* rs = args.resid + static_cast<long long>(row) * args.ldr + n;
                         float* o0 = reinterpret_cast<float*>(args.out0) + static_cast<long long>(row) * args.ld0 + n;
-                        if (full && (args.ld0 & 3) == 0 && (args.ldr & 3) == 0) {
+                        if (full && rvec) {
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
-                                const float4 x = reinterpret_cast<const float4*>(rs)[q];
+                                const float4 x = rcur[q];
                                 reinterpret_cast<float4*>(o0)[q] = make_float4(x.x + bf16_round(v[4 * q]), x.y + bf16_round(v[4 * q + 1]),
                                                                               x.z + bf16_round(v[4 * q + 2]), x.w + bf16_round(v[4 * q + 3]));
                             }
                         } else {
+                            const float* rs = args.resid + static_cast<long long>(row) * args.ldr + n;
                             for (int j = 0; j < 32 && n + j < args.N; ++j) o0[j] = rs[j] + bf16_round(v[j]);
                         }
                     }
@@ -320,7 +351,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kEpiWarps) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }

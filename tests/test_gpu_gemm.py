@@ -94,3 +94,15 @@ def test_gemm_strided_views():
     b = _mk((384, 256), 15)
     out = ops.gemm(a, b, epilogue=ops.EPI_F32)
     torch.testing.assert_close(out, a.float() @ b.float().t(), rtol=2e-4, atol=5e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(768, 768, 16384), (2304, 768, 16384), (4096, 768, 8192), (200, 328, 4096)])
+def test_gemm_wgrad_split_k(M, N, K):
+    """Weight-gradient shapes (few output tiles, long K) take the split-K path (fp32 atomics into a pre-zeroed output)."""
+    from b200fm import ops
+    a, b = _mk((K, M), 21, 0.5), _mk((K, N), 22, 0.5)
+    out = ops.gemm(a, b, layout=2, epilogue=ops.EPI_F32)
+    ref = a.float().t() @ b.float()
+    torch.testing.assert_close(out, ref, rtol=2e-3, atol=2e-2 * (K ** 0.5) / 8)
+    out2 = ops.gemm(a, b, layout=2, epilogue=ops.EPI_F32, alpha=0.5)
+    torch.testing.assert_close(out2, ref * 0.5, rtol=2e-3, atol=2e-2 * (K ** 0.5) / 8)
