@@ -13,6 +13,8 @@
 // CTA = 10 warps: warps 0-7 epilogue (TMEM lane quarter = warp & 3, column half = warp >> 2; two warps per quarter keep the
 // epilogue off the critical path), warp 8 TMA producer + TMEM allocator, warp 9 MMA issuer.
 // Tile 128 x BN x 64, BN in {128, 256}; smem ring of (16 KB + BN*128 B) stages; accumulators 2 x BN TMEM columns.
+#include <cstdlib>
+
 #include "../../include/b200fm.h"
 #include "common.cuh"
 #include "tmap.cuh"
@@ -44,10 +46,13 @@ struct GemmArgs {
     int kb_per_split;
 };
 
-template <int BN>
+// CTA2: a CTA pair (cluster of 2, one TPC) computes a 256 x BN tile with tcgen05.mma.cta_group::2 -- each CTA stages its own
+// 128 rows of A and only HALF of the B tile (BN/2 rows), so the per-SM smem fill per MMA-cycle drops by a third.
+template <int BN, bool CTA2>
 struct GemmSmem {
-    static constexpr int kStageBytes = kBM * 128 + BN * 128;
-    static constexpr int kStages = (BN == 256) ? 4 : 6;
+    static constexpr int kBBytes = CTA2 ? BN * 64 : BN * 128;
+    static constexpr int kStageBytes = kBM * 128 + kBBytes;
+    static constexpr int kStages = CTA2 ? (BN == 256 ? 6 : 8) : ((BN == 256) ? 4 : 6);
     static constexpr int kBarBytes = 256;
     static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;   // +1024 alignment slack
 };
@@ -55,17 +60,22 @@ struct GemmSmem {
 B200FM_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 B200FM_DEVINL float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
-template <int BN, int LAYOUT, int EPI>
+template <int BN, int LAYOUT, int EPI, bool CTA2>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmArgs args) {
-    using SM = GemmSmem<BN>;
+    using SM = GemmSmem<BN, CTA2>;
     constexpr int kStages = SM::kStages;
     constexpr bool A_MN = (LAYOUT == LAYOUT_TN);
     constexpr bool B_MN = (LAYOUT != LAYOUT_NT);
     constexpr int kABytes = kBM * 128;
-    constexpr int kBBytes = BN * 128;
-    constexpr uint32_t kIdesc = make_idesc_bf16(kBM, BN, A_MN, B_MN);
+    constexpr int kBBytes = SM::kBBytes;
+    constexpr int kBNLocal = CTA2 ? BN / 2 : BN;              // B rows (N) staged by this CTA
+    constexpr uint32_t kIdesc = make_idesc_bf16(CTA2 ? 2 * kBM : kBM, BN, A_MN, B_MN);
     constexpr int kTmemCols = 2 * BN;
+    const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;      // 0 = leader (issues the MMAs), 1 = peer
+    const int cta_stride = CTA2 ? 2 : 1;
+    const int my_first = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int my_step = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -77,8 +87,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_mn = args.num_m_blocks * args.num_n_blocks;
-    const int num_tiles = num_mn * args.k_splits;               // work items: (k slice, n block, m block), m fastest
+    const int num_m_units = (args.num_m_blocks + cta_stride - 1) / cta_stride;      // CTA2: pairs of 128-row blocks
+    const int num_mn = num_m_units * args.num_n_blocks;
+    const int num_tiles = num_mn * args.k_splits;               // work items: (k slice, n block, m unit), m fastest
     const int num_kb_total = (args.K + kBK - 1) / kBK;
 
     if (warp == kEpiWarps) {
@@ -86,14 +97,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             tma_prefetch_desc(&tmap_a);
             tma_prefetch_desc(&tmap_b);
             for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-            for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps); }
+            for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps * cta_stride); }
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, kTmemCols);
+        if constexpr (CTA2) tmem_alloc_2sm(tmem_slot, kTmemCols); else tmem_alloc(tmem_slot, kTmemCols);
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CTA2) cluster_sync_all(); else __syncthreads();      // peer barriers must be initialised before any remote signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -101,10 +112,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = my_first; tile < num_tiles; tile += my_step) {
                 const int mn = tile % num_mn, ks = tile / num_mn;
-                const int m_blk = mn % args.num_m_blocks;
-                const int n_blk = mn / args.num_m_blocks;
+                const int m_blk = (mn % num_m_units) * cta_stride + static_cast<int>(rank);
+                const int n_blk = mn / num_m_units;
                 const int m0 = m_blk * kBM;
                 const int n0 = (EPI == B200FM_EPI_SWIGLU) ? n_blk * (BN / 2) : n_blk * BN;
                 const int kb_begin = ks * args.kb_per_split;
@@ -113,8 +124,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * SM::kStageBytes;
                     uint8_t* sb = sa + kABytes;
-                    mbar_arrive_expect_tx(&full_bar[stage], kABytes + kBBytes);
                     const int k0 = kb * kBK;
+                    if constexpr (CTA2) {
+                        // both CTAs' bytes are counted on the LEADER's full barrier (the leader issues the MMA for the pair)
+                        const uint32_t fb = mapa_u32(&full_bar[stage], 0);
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (kABytes + kBBytes));
+                        if constexpr (!A_MN) {
+                            tma_load_2d_2sm(sa, &tmap_a, fb, k0, m0);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < kBM / 64; ++c) tma_load_2d_2sm(sa + c * 8192, &tmap_a, fb, m0 + 64 * c, k0);
+                        }
+                        if constexpr (!B_MN) {          // this CTA's half of the B tile: kBNLocal rows
+                            const int nrow = (EPI == B200FM_EPI_SWIGLU) ? (rank == 0 ? n0 : args.n_half + n0) : n0 + static_cast<int>(rank) * kBNLocal;
+                            tma_load_2d_2sm(sb, &tmap_b, fb, k0, nrow, kEvictLast);
+                            if constexpr (kBNLocal == 256) tma_load_2d_2sm(sb + 128 * 128, &tmap_b, fb, k0, nrow + 128, kEvictLast);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < kBNLocal / 64; ++c)
+                                tma_load_2d_2sm(sb + c * 8192, &tmap_b, fb, n0 + static_cast<int>(rank) * kBNLocal + 64 * c, k0);
+                        }
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
+                    mbar_arrive_expect_tx(&full_bar[stage], kABytes + kBBytes);
                     if constexpr (!A_MN) {
                         tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);                 // box {64 k, 128 rows}
                     } else {
@@ -143,10 +176,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
     } else if (warp == kEpiWarps + 1) {
         // ------------------------------ MMA issuer (single thread) ------------------------------
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = my_first; tile < num_tiles; tile += my_step) {
                 const int ks = tile / num_mn;
                 const int kb_begin = ks * args.kb_per_split;
                 const int num_kb = min(kb_begin + args.kb_per_split, num_kb_total) - kb_begin;
@@ -162,12 +195,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     for (int k = 0; k < kBK / 16; ++k) {
                         const uint64_t da = A_MN ? make_smem_desc(sa + k * 2048, 64 * 128, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
                         const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 64 * 128, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-                        umma_bf16(d_tmem, da, db, kIdesc, (kb | k) != 0 ? 1u : 0u);
+                        if constexpr (CTA2) umma_bf16_2sm(d_tmem, da, db, kIdesc, (kb | k) != 0 ? 1u : 0u);
+                        else umma_bf16(d_tmem, da, db, kIdesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);          // smem slot reusable once these MMAs retire
+                    // smem slot reusable once these MMAs retire (CTA2: in both CTAs of the pair)
+                    if constexpr (CTA2) umma_commit_2sm(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[as]);                  // accumulator complete
+                // accumulator complete (CTA2: each CTA's epilogue reads its own 128 rows from its own TMEM)
+                if constexpr (CTA2) umma_commit_2sm(&tfull_bar[as], 3); else umma_commit(&tfull_bar[as]);
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
         }
@@ -175,10 +211,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         // ------------------------------ epilogue warps 0..7 ------------------------------
         const int quarter = warp & 3, half = warp >> 2;
         int as = 0; uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const uint32_t tempty_leader0 = CTA2 ? mapa_u32(&tempty_bar[0], 0) : 0u;
+        const uint32_t tempty_leader1 = CTA2 ? mapa_u32(&tempty_bar[1], 0) : 0u;
+        for (int tile = my_first; tile < num_tiles; tile += my_step) {
             const int mn = tile % num_mn;
-            const int m_blk = mn % args.num_m_blocks;
-            const int n_blk = mn / args.num_m_blocks;
+            const int m_blk = (mn % num_m_units) * cta_stride + static_cast<int>(rank);
+            const int n_blk = mn / num_m_units;
             const int row = m_blk * kBM + quarter * 32 + lane;
             const bool row_ok = row < args.M;
             const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -344,16 +382,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (lane == 0) {
+                if constexpr (CTA2) mbar_arrive_cluster(as == 0 ? tempty_leader0 : tempty_leader1);   // the leader's MMA thread waits for both CTAs
+                else mbar_arrive(&tempty_bar[as]);
+            }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CTA2) cluster_sync_all(); else __syncthreads();       // the peer may still read this CTA's smem / signal its barriers
     if (warp == kEpiWarps) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if constexpr (CTA2) tmem_dealloc_2sm(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -371,20 +412,43 @@ static int sm_count() {
     return g_sm_count;
 }
 
-template <int BN, int LAYOUT, int EPI>
+template <int BN, int LAYOUT, int EPI, bool CTA2>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t stream) {
-    auto kern = gemm_kernel<BN, LAYOUT, EPI>;
-    constexpr int smem = GemmSmem<BN>::kTotal;
+    auto kern = gemm_kernel<BN, LAYOUT, EPI, CTA2>;
+    constexpr int smem = GemmSmem<BN, CTA2>::kTotal;
     static bool configured = false;
     if (!configured) {
         B200FM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    const int tiles = a.num_m_blocks * a.num_n_blocks * a.k_splits;
-    const int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, a);
+    const int units = (CTA2 ? (a.num_m_blocks + 1) / 2 : a.num_m_blocks) * a.num_n_blocks * a.k_splits;
+    if constexpr (CTA2) {
+        const int clusters = units < sm_count() / 2 ? units : sm_count() / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        B200FM_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, a));
+    } else {
+        const int grid = units < sm_count() ? units : sm_count();
+        kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, a);
+    }
     B200FM_CUDA(cudaGetLastError());
     return 0;
+}
+
+static bool use_cta_pairs() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200FM_GEMM_CTA_PAIRS");
+        v = (e == nullptr || e[0] != '0') ? 1 : 0;
+    }
+    return v == 1;
 }
 
 }  // namespace b200fm
@@ -453,8 +517,12 @@ extern "C" int b200fm_gemm_bf16(int layout, int epilogue, int M, int N, int K, c
     }
     if (rc) return rc;
 
-#define B200FM_GEMM_CASE(BN_, L_, E_) \
-    if (BN == BN_ && layout == L_ && epilogue == E_) return launch_gemm<BN_, L_, E_>(ta, tb, a, stream);
+    // CTA pairs whenever there are at least two 128-row blocks (a lone block would leave the peer CTA idle)
+    // (BN == 256 only: the B tensor map's 128-row box is exactly one CTA's half of the tile)
+    const bool pairs = use_cta_pairs() && a.num_m_blocks >= 2 && BN == 256;
+#define B200FM_GEMM_CASE(BN_, L_, E_)                                                                  \
+    if (BN == BN_ && layout == L_ && epilogue == E_)                                                    \
+        return pairs ? launch_gemm<BN_, L_, E_, true>(ta, tb, a, stream) : launch_gemm<BN_, L_, E_, false>(ta, tb, a, stream);
     B200FM_GEMM_CASE(256, LAYOUT_NT, B200FM_EPI_BF16)
     B200FM_GEMM_CASE(128, LAYOUT_NT, B200FM_EPI_BF16)
     B200FM_GEMM_CASE(256, LAYOUT_NT, B200FM_EPI_F32)
