@@ -263,9 +263,18 @@ def run_b200_arm(args):
     ops.PROFILE = []
     step(dev_batches[0]); step(dev_batches[1])
     torch.cuda.synchronize()
-    gemm_ms = sum(s.elapsed_time(e) for s, e, _ in ops.PROFILE)
-    gemm_flops = sum(f for _, _, f in ops.PROFILE)
+    gemm_ms = sum(s.elapsed_time(e) for s, e, _, _ in ops.PROFILE)
+    gemm_flops = sum(f for _, _, f, _ in ops.PROFILE)
     n_gemm = len(ops.PROFILE)
+    if rank == 0 and os.environ.get("B200FM_DUMP_GEMM"):
+        agg = {}
+        for s_, e_, f_, key in ops.PROFILE:
+            a_ = agg.setdefault(key, [0, 0.0, 0.0])
+            a_[0] += 1; a_[1] += s_.elapsed_time(e_); a_[2] += f_
+        rows = [dict(layout=k[0], epilogue=k[1], M=k[2], N=k[3], K=k[4], launches_per_step=v[0] // 2, ms_per_launch=v[1] / v[0],
+                     tflops=v[2] / (v[1] * 1e-3) / 1e12) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])]
+        with open(os.environ["B200FM_DUMP_GEMM"], "w") as f:
+            json.dump(rows, f, indent=1)
     ops.PROFILE = None
     step_ms_prof = None
 

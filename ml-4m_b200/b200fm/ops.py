@@ -75,7 +75,7 @@ def gemm(a, b, layout=LAYOUT_NT, epilogue=EPI_BF16, out=None, out1=None, bias=No
              _ptr(bias), _ptr(resid), ldr, float(alpha), _ptr(alpha_dev), _stream())
     if PROFILE is not None:
         ev1.record()
-        PROFILE.append((ev0, ev1, 2.0 * M * K * (2 * N if epilogue == EPI_SWIGLU else N)))
+        PROFILE.append((ev0, ev1, 2.0 * M * K * (2 * N if epilogue == EPI_SWIGLU else N), (layout, epilogue, M, N, K)))
     return (out, out1) if epilogue in (EPI_SWIGLU, EPI_GELU, EPI_TANH) else out
 
 
