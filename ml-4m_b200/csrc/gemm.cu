@@ -52,13 +52,52 @@ template <int BN, bool CTA2>
 struct GemmSmem {
     static constexpr int kBBytes = CTA2 ? BN * 64 : BN * 128;
     static constexpr int kStageBytes = kBM * 128 + kBBytes;
-    static constexpr int kStages = CTA2 ? (BN == 256 ? 6 : 8) : ((BN == 256) ? 4 : 6);
+    static constexpr int kStages = CTA2 ? (BN == 256 ? 5 : 6) : ((BN == 256) ? 3 : 5);
     static constexpr int kBarBytes = 256;
-    static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;   // +1024 alignment slack
+    static constexpr int kEpiStageBytes = 32 * 36 * 4;                        // per epilogue warp: 32 rows x (32 + 4 pad) fp32
+    static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 8 * kEpiStageBytes + 1024;   // +1024 alignment slack
 };
 
 B200FM_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 B200FM_DEVINL float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// ---- warp-private smem staging: the accumulator arrives with thread = row (TMEM lane); going through a small smem tile turns
+// the global accesses into row-contiguous segments (full 32 B sectors, 64-128 B per row) instead of 32 strided 16 B pieces.
+//
+// bf16: 32 rows x 16 packed words, XOR-swizzled 16 B quads (conflict-free for both the row-wise write and the 8-row read)
+B200FM_DEVINL void stage_store_bf16(uint32_t* stg, int lane, const uint32_t (&p)[16], __nv_bfloat16* out, long long ld, int row_base, int n,
+                                    int M, int N, bool vec_ok) {
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(stg + lane * 16 + 4 * (q ^ sw)) = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int rl = i * 8 + (lane >> 2), quad = lane & 3;
+        const uint4 w = *reinterpret_cast<const uint4*>(stg + rl * 16 + 4 * (quad ^ ((rl >> 1) & 3)));
+        const int grow = row_base + rl, gcol = n + quad * 8;
+        if (grow < M && gcol < N) {
+            __nv_bfloat16* dst = out + static_cast<long long>(grow) * ld + gcol;
+            if (vec_ok && gcol + 8 <= N) {
+                *reinterpret_cast<uint4*>(dst) = w;
+            } else {
+                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+                for (int e = 0; e < 8 && gcol + e < N; ++e)
+                    reinterpret_cast<uint16_t*>(dst)[e] = (e & 1) ? (ww[e >> 1] >> 16) : (ww[e >> 1] & 0xffff);
+            }
+        }
+    }
+    __syncwarp();
+}
+// fp32: 32 rows x 36 floats (4 pad): row-wise float4 writes and 4-row x 32-column float4 reads are both conflict-free
+B200FM_DEVINL void stage_write_f32(float* stg, int lane, const uint32_t (&r)[32]) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(stg + lane * 36 + 4 * q) =
+            make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+    __syncwarp();
+}
 
 template <int BN, int LAYOUT, int EPI, bool CTA2>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -217,169 +256,130 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const int mn = tile % num_mn;
             const int m_blk = (mn % num_m_units) * cta_stride + static_cast<int>(rank);
             const int n_blk = mn / num_m_units;
-            const int row = m_blk * kBM + quarter * 32 + lane;
+            const int row_base = m_blk * kBM + quarter * 32;            // first of this warp's 32 rows
+            const int row = row_base + lane;
             const bool row_ok = row < args.M;
             const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+            float* stg_f = reinterpret_cast<float*>(smem + kStages * SM::kStageBytes + SM::kBarBytes) + warp * (SM::kEpiStageBytes / 4);
+            uint32_t* stg_u = reinterpret_cast<uint32_t*>(stg_f);
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
 
             if constexpr (EPI == B200FM_EPI_SWIGLU) {
-                mbar_wait(&tfull_bar[as], aphase);
-                tc_fence_after();
                 constexpr int HB = BN / 2;
                 const int n0 = n_blk * HB;
-                __nv_bfloat16* ab = reinterpret_cast<__nv_bfloat16*>(args.out0) + static_cast<long long>(row) * args.ld0;
-                __nv_bfloat16* gg = reinterpret_cast<__nv_bfloat16*>(args.out1) + static_cast<long long>(row) * args.ld1;
+                __nv_bfloat16* ab = reinterpret_cast<__nv_bfloat16*>(args.out0);
+                __nv_bfloat16* gg = reinterpret_cast<__nv_bfloat16*>(args.out1);
+                const bool vec_ok = (args.ld0 & 7) == 0 && (args.ld1 & 7) == 0 && (args.n_half & 7) == 0;
 #pragma unroll 1
-                for (int c = half * (HB / 32); c < (half + 1) * (HB / 32); ++c) {
-                    uint32_t ra[16], rb[16];
-                    tmem_ld_x16(t_acc + c * 16, ra);
-                    tmem_ld_x16(t_acc + HB + c * 16, rb);
+                for (int c = half * (HB / 64); c < (half + 1) * (HB / 64); ++c) {        // 32 gate columns per iteration
+                    uint32_t ra[32], rb[32];
+                    tmem_ld_x32(t_acc + c * 32, ra);
+                    tmem_ld_x32(t_acc + HB + c * 32, rb);
                     tmem_ld_wait();
-                    const int n = n0 + c * 16;
-                    if (row_ok && n < args.N) {
-                        uint32_t pa[8], pb[8], pg[8];
+                    const int n = n0 + c * 32;
+                    uint32_t pa[16], pb[16], pg[16];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float a0 = __uint_as_float(ra[2 * j]), a1 = __uint_as_float(ra[2 * j + 1]);
-                            float b0 = __uint_as_float(rb[2 * j]), b1 = __uint_as_float(rb[2 * j + 1]);
-                            if (args.bias) { a0 += args.bias[n + 2 * j]; a1 += args.bias[n + 2 * j + 1];
-                                             b0 += args.bias[args.n_half + n + 2 * j]; b1 += args.bias[args.n_half + n + 2 * j + 1]; }
-                            pa[j] = pack_bf16x2(a0, a1);
-                            pb[j] = pack_bf16x2(b0, b1);
-                            // reference numerics (fm_utils.py:143 under autocast): silu and the product are each rounded to bf16
-                            const float2 ar = unpack_bf16x2(pa[j]), br = unpack_bf16x2(pb[j]);
-                            pg[j] = pack_bf16x2(bf16_round(silu_f(ar.x)) * br.x, bf16_round(silu_f(ar.y)) * br.y);
+                    for (int j = 0; j < 16; ++j) {
+                        float a0 = __uint_as_float(ra[2 * j]), a1 = __uint_as_float(ra[2 * j + 1]);
+                        float b0 = __uint_as_float(rb[2 * j]), b1 = __uint_as_float(rb[2 * j + 1]);
+                        if (args.bias && n + 2 * j + 1 < args.N) {
+                            a0 += args.bias[n + 2 * j]; a1 += args.bias[n + 2 * j + 1];
+                            b0 += args.bias[args.n_half + n + 2 * j]; b1 += args.bias[args.n_half + n + 2 * j + 1];
                         }
-                        if (n + 16 <= args.N) {
-                            uint4* pa4 = reinterpret_cast<uint4*>(ab + n);
-                            uint4* pb4 = reinterpret_cast<uint4*>(ab + args.n_half + n);
-                            uint4* pg4 = reinterpret_cast<uint4*>(gg + n);
-                            pa4[0] = make_uint4(pa[0], pa[1], pa[2], pa[3]); pa4[1] = make_uint4(pa[4], pa[5], pa[6], pa[7]);
-                            pb4[0] = make_uint4(pb[0], pb[1], pb[2], pb[3]); pb4[1] = make_uint4(pb[4], pb[5], pb[6], pb[7]);
-                            pg4[0] = make_uint4(pg[0], pg[1], pg[2], pg[3]); pg4[1] = make_uint4(pg[4], pg[5], pg[6], pg[7]);
-                        } else {
-                            for (int j = 0; j < 16 && n + j < args.N; ++j) {
-                                const uint32_t wa = pa[j >> 1], wb = pb[j >> 1], wg = pg[j >> 1];
-                                const uint16_t ha = (j & 1) ? (wa >> 16) : (wa & 0xffff);
-                                const uint16_t hb = (j & 1) ? (wb >> 16) : (wb & 0xffff);
-                                const uint16_t hg = (j & 1) ? (wg >> 16) : (wg & 0xffff);
-                                reinterpret_cast<uint16_t*>(ab)[n + j] = ha;
-                                reinterpret_cast<uint16_t*>(ab)[args.n_half + n + j] = hb;
-                                reinterpret_cast<uint16_t*>(gg)[n + j] = hg;
-                            }
-                        }
+                        pa[j] = pack_bf16x2(a0, a1);
+                        pb[j] = pack_bf16x2(b0, b1);
+                        // reference numerics (fm_utils.py:143 under autocast): silu and the product are each rounded to bf16
+                        const float2 ar = unpack_bf16x2(pa[j]), br = unpack_bf16x2(pb[j]);
+                        pg[j] = pack_bf16x2(bf16_round(silu_f(ar.x)) * br.x, bf16_round(silu_f(ar.y)) * br.y);
                     }
+                    stage_store_bf16(stg_u, lane, pa, ab, args.ld0, row_base, n, args.M, args.N, vec_ok);
+                    stage_store_bf16(stg_u, lane, pb, ab + args.n_half, args.ld0, row_base, n, args.M, args.N, vec_ok);
+                    stage_store_bf16(stg_u, lane, pg, gg, args.ld1, row_base, n, args.M, args.N, vec_ok);
                 }
             } else {
                 const int n0 = n_blk * BN;
                 const float alpha = args.alpha * (args.alpha_dev ? __ldg(args.alpha_dev) : 1.0f);
                 constexpr int kChunks = BN / 64;                 // 32-column chunks per epilogue warp
                 const int c0 = half * kChunks;
-                [[maybe_unused]] float4 rnext[8];
-                [[maybe_unused]] bool rvec = false;
-                if constexpr (EPI == B200FM_EPI_RESID) {
-                    // the residual tile does not depend on the accumulator: fetch the first chunk before waiting for the MMAs,
-                    // and every following chunk one iteration ahead
-                    rvec = (args.ld0 & 3) == 0 && (args.ldr & 3) == 0;
-                    const int n = n0 + c0 * 32;
-                    if (rvec && row_ok && n + 32 <= args.N) {
-                        const float4* rs4 = reinterpret_cast<const float4*>(args.resid + static_cast<long long>(row) * args.ldr + n);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) rnext[q] = __ldg(rs4 + q);
-                    }
-                }
-                mbar_wait(&tfull_bar[as], aphase);
-                tc_fence_after();
 #pragma unroll 1
                 for (int c = c0; c < c0 + kChunks; ++c) {
                     uint32_t r[32];
                     tmem_ld_x32(t_acc + c * 32, r);
-                    const int n = n0 + c * 32;
-                    [[maybe_unused]] float4 rcur[8];
-                    if constexpr (EPI == B200FM_EPI_RESID) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) rcur[q] = rnext[q];
-                        const int nn = n + 32;
-                        if (c + 1 < c0 + kChunks && rvec && row_ok && nn + 32 <= args.N) {
-                            const float4* rs4 = reinterpret_cast<const float4*>(args.resid + static_cast<long long>(row) * args.ldr + nn);
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) rnext[q] = __ldg(rs4 + q);
-                        }
-                    }
                     tmem_ld_wait();
-                    if (!row_ok || n >= args.N) continue;
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    const bool full = (n + 32 <= args.N);
-                    if (args.bias) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (full || n + j < args.N) v[j] += args.bias[n + j];
-                    }
-                    if constexpr (EPI == B200FM_EPI_BF16 || EPI == B200FM_EPI_F32) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] *= alpha;
-                    }
+                    const int n = n0 + c * 32;
+                    if (n >= args.N) continue;                   // warp-uniform
                     if constexpr (EPI == B200FM_EPI_BF16 || EPI == B200FM_EPI_GELU) {
-                        __nv_bfloat16* o0 = reinterpret_cast<__nv_bfloat16*>(args.out0) + static_cast<long long>(row) * args.ld0 + n;
                         uint32_t p[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) p[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-                        if (full) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(o0)[q] = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
-                        } else {
-                            for (int j = 0; j < 32 && n + j < args.N; ++j)
-                                reinterpret_cast<uint16_t*>(o0)[j] = (j & 1) ? (p[j >> 1] >> 16) : (p[j >> 1] & 0xffff);
+                        for (int j = 0; j < 16; ++j) {
+                            float v0 = __uint_as_float(r[2 * j]), v1 = __uint_as_float(r[2 * j + 1]);
+                            if (args.bias) {
+                                if (n + 2 * j < args.N) v0 += args.bias[n + 2 * j];
+                                if (n + 2 * j + 1 < args.N) v1 += args.bias[n + 2 * j + 1];
+                            }
+                            if constexpr (EPI == B200FM_EPI_BF16) { v0 *= alpha; v1 *= alpha; }
+                            p[j] = pack_bf16x2(v0, v1);
                         }
+                        const bool vec0 = (args.ld0 & 7) == 0;
+                        stage_store_bf16(stg_u, lane, p, reinterpret_cast<__nv_bfloat16*>(args.out0), args.ld0, row_base, n, args.M, args.N, vec0);
                         if constexpr (EPI == B200FM_EPI_GELU) {
-                            __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(args.out1) + static_cast<long long>(row) * args.ld1 + n;
                             uint32_t g[16];
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
                                 const float2 pr = unpack_bf16x2(p[j]);       // activation sees the bf16-rounded pre-activation
                                 g[j] = args.act == 0 ? pack_bf16x2(gelu_erf(pr.x), gelu_erf(pr.y)) : pack_bf16x2(tanhf(pr.x), tanhf(pr.y));
                             }
-                            if (full) {
+                            stage_store_bf16(stg_u, lane, g, reinterpret_cast<__nv_bfloat16*>(args.out1), args.ld1, row_base, n, args.M, args.N, (args.ld1 & 7) == 0);
+                        }
+                    } else {
+                        // fp32 outputs: transpose through smem, then each lane owns 4 consecutive columns of 8 rows
+                        stage_write_f32(stg_f, lane, r);
+                        const int c4 = (lane & 7) * 4;
+                        const int gcol = n + c4;
+                        const bool vec = (args.ld0 & 3) == 0 && (EPI != B200FM_EPI_RESID || (args.ldr & 3) == 0) && gcol + 4 <= args.N;
+                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (args.bias && gcol < args.N) {
+                            b4.x = args.bias[gcol];
+                            if (gcol + 1 < args.N) b4.y = args.bias[gcol + 1];
+                            if (gcol + 2 < args.N) b4.z = args.bias[gcol + 2];
+                            if (gcol + 3 < args.N) b4.w = args.bias[gcol + 3];
+                        }
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(o1)[q] = make_uint4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
-                            } else {
-                                for (int j = 0; j < 32 && n + j < args.N; ++j)
-                                    reinterpret_cast<uint16_t*>(o1)[j] = (j & 1) ? (g[j >> 1] >> 16) : (g[j >> 1] & 0xffff);
+                        for (int i = 0; i < 8; ++i) {
+                            const int rl = i * 4 + (lane >> 3);
+                            const int grow = row_base + rl;
+                            float4 a = *reinterpret_cast<const float4*>(stg_f + rl * 36 + c4);
+                            a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+                            if (grow >= args.M || gcol >= args.N) continue;
+                            float* o0 = reinterpret_cast<float*>(args.out0) + static_cast<long long>(grow) * args.ld0 + gcol;
+                            if constexpr (EPI == B200FM_EPI_F32) {
+                                a.x *= alpha; a.y *= alpha; a.z *= alpha; a.w *= alpha;
+                                if (vec) {
+                                    if (args.k_splits > 1) atomicAdd(reinterpret_cast<float4*>(o0), a);
+                                    else *reinterpret_cast<float4*>(o0) = a;
+                                } else {
+                                    const float av[4] = {a.x, a.y, a.z, a.w};
+                                    for (int e = 0; e < 4 && gcol + e < args.N; ++e) {
+                                        if (args.k_splits > 1) atomicAdd(o0 + e, av[e]); else o0[e] = av[e];
+                                    }
+                                }
+                            } else {   // EPI_RESID: out = resid + bf16_round(acc + bias)   (fp32 residual stream)
+                                const float* rs = args.resid + static_cast<long long>(grow) * args.ldr + gcol;
+                                if (vec) {
+                                    const float4 x = __ldg(reinterpret_cast<const float4*>(rs));
+                                    *reinterpret_cast<float4*>(o0) = make_float4(x.x + bf16_round(a.x), x.y + bf16_round(a.y), x.z + bf16_round(a.z), x.w + bf16_round(a.w));
+                                } else {
+                                    const float av[4] = {a.x, a.y, a.z, a.w};
+                                    for (int e = 0; e < 4 && gcol + e < args.N; ++e) o0[e] = rs[e] + bf16_round(av[e]);
+                                }
                             }
                         }
-                    } else if constexpr (EPI == B200FM_EPI_F32) {
-                        float* o0 = reinterpret_cast<float*>(args.out0) + static_cast<long long>(row) * args.ld0 + n;
-                        if (args.k_splits > 1) {
-                            if (full && (args.ld0 & 3) == 0) {
-#pragma unroll
-                                for (int q = 0; q < 8; ++q)
-                                    atomicAdd(reinterpret_cast<float4*>(o0) + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-                            } else {
-                                for (int j = 0; j < 32 && n + j < args.N; ++j) atomicAdd(o0 + j, v[j]);
-                            }
-                        } else if (full && (args.ld0 & 3) == 0) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q)
-                                reinterpret_cast<float4*>(o0)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                        } else {
-                            for (int j = 0; j < 32 && n + j < args.N; ++j) o0[j] = v[j];
-                        }
-                    } else {   // EPI_RESID: out = resid + bf16_round(acc + bias)   (fp32 residual stream)
-                        float* o0 = reinterpret_cast<float*>(args.out0) + static_cast<long long>(row) * args.ld0 + n;
-                        if (full && rvec) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const float4 x = rcur[q];
-                                reinterpret_cast<float4*>(o0)[q] = make_float4(x.x + bf16_round(v[4 * q]), x.y + bf16_round(v[4 * q + 1]),
-                                                                              x.z + bf16_round(v[4 * q + 2]), x.w + bf16_round(v[4 * q + 3]));
-                            }
-                        } else {
-                            const float* rs = args.resid + static_cast<long long>(row) * args.ldr + n;
-                            for (int j = 0; j < 32 && n + j < args.N; ++j) o0[j] = rs[j] + bf16_round(v[j]);
-                        }
+                        __syncwarp();
                     }
                 }
             }
+            (void)row; (void)row_ok;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
