@@ -54,6 +54,11 @@ int b200fm_gemm_bf16(int layout, int epilogue, int M, int N, int K, const void* 
  * x fp32 [rows, D] -> y (bf16 if y_is_bf16 else fp32) [rows, D]; mean/rstd fp32 [rows] saved for backward (may be NULL). */
 int b200fm_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_is_bf16, float* mean,
                          float* rstd, int rows, int D, float eps, void* stream);
+/* Residual add fused into the norm: x_out fp32 = x + add (bf16 branch output of the previous sub-layer), y = LayerNorm(x_out).
+ * This is how `x = x + proj(...)` / `x = x + fc2(...)` (fm_utils.py:332-334, 363-365) are realised: the GEMM writes its bf16
+ * output, the NEXT norm adds it to the fp32 stream while it reads the stream anyway.                                        */
+int b200fm_add_layernorm_fwd(const float* x, const void* add_bf16, float* x_out, const float* gamma, const float* beta, void* y,
+                             int y_is_bf16, float* mean, float* rstd, int rows, int D, float eps, void* stream);
 /* dy (bf16 if dy_is_bf16 else fp32) is the gradient w.r.t. the LN output; dx_out fp32 = (dres ? dres : 0) + LN backward;
  * dx_bf16 (optional) = bf16 copy of dx_out; dgamma/dbeta fp32 [D] are ACCUMULATED into (atomics), may be NULL.   */
 int b200fm_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* gamma, const float* mean,

@@ -402,31 +402,57 @@ def _hand_over(dx, dxb, shape):
     return out
 
 
-class SelfAttnSubLayerFn(torch.autograd.Function):
-    """x + proj(attention(qkv(LN(x)))) -- fm_utils.py:332 / 363 with Attention.forward (:160-180)."""
+def _prep_stream(x, ypend, D):
+    x2 = x.reshape(-1, D)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    y2 = None
+    if ypend is not None:
+        y2 = ypend.reshape(-1, D)
+        if not y2.is_contiguous():
+            y2 = y2.contiguous()
+    return x2, y2
 
-    @staticmethod
-    def forward(ctx, x, mask, nw, nb, qkv_w, qkv_b, proj_w, proj_b, eps, heads, scale):
-        B, N, D = x.shape
-        x2 = x.reshape(B * N, D)
-        if not x2.is_contiguous():
-            x2 = x2.contiguous()
-        h, mean, rstd = ops.layernorm_fwd(x2, nw, nb, eps, out_bf16=True)
-        qkv = ops.gemm(h, weight_bf16(qkv_w), epilogue=ops.EPI_BF16, bias=qkv_b, n_out=3 * D)
-        o, stats = ops.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, heads, N, N, mask, scale)
-        out = ops.gemm(o, weight_bf16(proj_w), epilogue=ops.EPI_RESID, bias=proj_b, resid=x2, n_out=D)
-        ctx.save_for_backward(x2, mean, rstd, h, qkv, o, stats, mask, nw, qkv_w, proj_w)
-        ctx.cfg = (B, N, D, heads, scale, qkv_b is not None, proj_b is not None, nb is not None and nb.requires_grad)
-        return out.view(B, N, D)
 
-    @staticmethod
-    def backward(ctx, dout):
-        x2, mean, rstd, h, qkv, o, stats, mask, nw, qkv_w, proj_w = ctx.saved_tensors
-        B, N, D, heads, scale, has_qb, has_pb, nb_grad = ctx.cfg
-        d2 = dout.reshape(B * N, D)
+def _stream_grads(g_s, g_y, rows, D):
+    """(fp32 residual-stream gradient | None, bf16 branch-output gradient) as contiguous 2-D tensors."""
+    d2 = None
+    if g_s is not None:
+        d2 = g_s.reshape(rows, D)
         if not d2.is_contiguous():
             d2 = d2.contiguous()
-        db = _grad_bf16(d2, dout)
+    db = g_y.reshape(rows, D)
+    if db.dtype != torch.bfloat16:
+        db = ops.cast_bf16(db.float().contiguous())
+    elif not db.is_contiguous():
+        db = db.contiguous()
+    return d2, db
+
+
+# Sub-layer convention ("pending add"): every node takes the fp32 stream x and the previous sub-layer's bf16 branch output
+# `ypend` (not yet added), does  s = x + ypend  inside its LayerNorm kernel, and returns (s, y) with y its own bf16 branch
+# output.  The GEMMs therefore always use the plain bf16 epilogue; the fp32 stream is touched only by the norm kernels.
+# Backward receives (grad wrt s: fp32, grad wrt y: bf16) and returns (grad wrt x: fp32, grad wrt ypend: its bf16 copy).
+class SelfAttnSubLayerFn(torch.autograd.Function):
+    """(x, ypend) -> (s = x + ypend, y = proj(attention(qkv(LN(s)))))   fm_utils.py:332 / 363 with Attention.forward (:160-180)."""
+
+    @staticmethod
+    def forward(ctx, x, ypend, mask, nw, nb, qkv_w, qkv_b, proj_w, proj_b, eps, heads, scale):
+        B, N, D = x.shape
+        x2, y2 = _prep_stream(x, ypend, D)
+        s2, h, mean, rstd = ops.add_layernorm_fwd(x2, y2, nw, nb, eps)
+        qkv = ops.gemm(h, weight_bf16(qkv_w), epilogue=ops.EPI_BF16, bias=qkv_b, n_out=3 * D)
+        o, stats = ops.attention_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, heads, N, N, mask, scale)
+        y = ops.gemm(o, weight_bf16(proj_w), epilogue=ops.EPI_BF16, bias=proj_b, n_out=D)
+        ctx.save_for_backward(s2, mean, rstd, h, qkv, o, stats, mask, nw, qkv_w, proj_w)
+        ctx.cfg = (B, N, D, heads, scale, qkv_b is not None, proj_b is not None, nb is not None and nb.requires_grad, ypend is not None)
+        return s2.view(B, N, D), y.view(B, N, D)
+
+    @staticmethod
+    def backward(ctx, g_s, g_y):
+        s2, mean, rstd, h, qkv, o, stats, mask, nw, qkv_w, proj_w = ctx.saved_tensors
+        B, N, D, heads, scale, has_qb, has_pb, nb_grad, has_pend = ctx.cfg
+        d2, db = _stream_grads(g_s, g_y, B * N, D)
         do = ops.gemm(db, weight_bf16(proj_w)[:D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
         dproj_w = ops.gemm(db, o, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if proj_w.requires_grad else None
         dproj_b = ops.colsum_bf16(db) if has_pb else None
@@ -436,45 +462,41 @@ class SelfAttnSubLayerFn(torch.autograd.Function):
         dh = ops.gemm(dqkv, weight_bf16(qkv_w)[:3 * D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
         dqkv_w = ops.gemm(dqkv, h, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if qkv_w.requires_grad else None
         dqkv_b = ops.colsum_bf16(dqkv) if has_qb else None
-        dgamma = torch.zeros(D, device=x2.device, dtype=torch.float32) if nw.requires_grad else None
-        dbeta = torch.zeros(D, device=x2.device, dtype=torch.float32) if nb_grad else None
-        dx, dxb = ops.layernorm_bwd(dh, x2, nw, mean, rstd, dres=d2, want_bf16=True, dgamma=dgamma, dbeta=dbeta)
-        return _hand_over(dx, dxb, (B, N, D)), None, dgamma, dbeta, dqkv_w, dqkv_b, dproj_w, dproj_b, None, None, None
+        dgamma = torch.zeros(D, device=s2.device, dtype=torch.float32) if nw.requires_grad else None
+        dbeta = torch.zeros(D, device=s2.device, dtype=torch.float32) if nb_grad else None
+        dx, dxb = ops.layernorm_bwd(dh, s2, nw, mean, rstd, dres=d2, want_bf16=has_pend, dgamma=dgamma, dbeta=dbeta)
+        return (dx.view(B, N, D), dxb.view(B, N, D) if has_pend else None, None, dgamma, dbeta, dqkv_w, dqkv_b, dproj_w, dproj_b,
+                None, None, None)
 
 
 class CrossAttnSubLayerFn(torch.autograd.Function):
-    """x + proj(attention(q(LNq(x)), kv(LNc(context)))) -- fm_utils.py:364 with CrossAttention.forward (:197-219)."""
+    """(x, ypend, context) -> (s, y = proj(attention(q(LNq(s)), kv(LNc(context)))))   fm_utils.py:364, CrossAttention.forward (:197-219)."""
 
     @staticmethod
-    def forward(ctx, x, context, mask, qnw, qnb, cnw, cnb, q_w, q_b, kv_w, kv_b, proj_w, proj_b, eps_q, eps_c, heads, scale):
+    def forward(ctx, x, ypend, context, mask, qnw, qnb, cnw, cnb, q_w, q_b, kv_w, kv_b, proj_w, proj_b, eps_q, eps_c, heads, scale):
         B, N, D = x.shape
         M = context.shape[1]
-        x2 = x.reshape(B * N, D)
+        x2, y2 = _prep_stream(x, ypend, D)
         c2 = context.reshape(B * M, D)
-        if not x2.is_contiguous():
-            x2 = x2.contiguous()
         if not c2.is_contiguous():
             c2 = c2.contiguous()
-        hq, qmean, qrstd = ops.layernorm_fwd(x2, qnw, qnb, eps_q, out_bf16=True)
+        s2, hq, qmean, qrstd = ops.add_layernorm_fwd(x2, y2, qnw, qnb, eps_q)
         hc, cmean, crstd = ops.layernorm_fwd(c2, cnw, cnb, eps_c, out_bf16=True)
         q = ops.gemm(hq, weight_bf16(q_w), epilogue=ops.EPI_BF16, bias=q_b, n_out=D)
         kv = ops.gemm(hc, weight_bf16(kv_w), epilogue=ops.EPI_BF16, bias=kv_b, n_out=2 * D)
         o, stats = ops.attention_fwd(q, kv[:, :D], kv[:, D:], B, heads, N, M, mask, scale)
-        out = ops.gemm(o, weight_bf16(proj_w), epilogue=ops.EPI_RESID, bias=proj_b, resid=x2, n_out=D)
-        ctx.save_for_backward(x2, c2, qmean, qrstd, cmean, crstd, hq, hc, q, kv, o, stats, mask, qnw, cnw, q_w, kv_w, proj_w)
+        y = ops.gemm(o, weight_bf16(proj_w), epilogue=ops.EPI_BF16, bias=proj_b, n_out=D)
+        ctx.save_for_backward(s2, c2, qmean, qrstd, cmean, crstd, hq, hc, q, kv, o, stats, mask, qnw, cnw, q_w, kv_w, proj_w)
         ctx.cfg = (B, N, M, D, heads, scale, q_b is not None, kv_b is not None, proj_b is not None,
-                   qnb is not None and qnb.requires_grad, cnb is not None and cnb.requires_grad)
-        return out.view(B, N, D)
+                   qnb is not None and qnb.requires_grad, cnb is not None and cnb.requires_grad, ypend is not None)
+        return s2.view(B, N, D), y.view(B, N, D)
 
     @staticmethod
-    def backward(ctx, dout):
-        (x2, c2, qmean, qrstd, cmean, crstd, hq, hc, q, kv, o, stats, mask, qnw, cnw, q_w, kv_w, proj_w) = ctx.saved_tensors
-        B, N, M, D, heads, scale, has_qb, has_kvb, has_pb, qnb_grad, cnb_grad = ctx.cfg
-        dev = x2.device
-        d2 = dout.reshape(B * N, D)
-        if not d2.is_contiguous():
-            d2 = d2.contiguous()
-        db = _grad_bf16(d2, dout)
+    def backward(ctx, g_s, g_y):
+        (s2, c2, qmean, qrstd, cmean, crstd, hq, hc, q, kv, o, stats, mask, qnw, cnw, q_w, kv_w, proj_w) = ctx.saved_tensors
+        B, N, M, D, heads, scale, has_qb, has_kvb, has_pb, qnb_grad, cnb_grad, has_pend = ctx.cfg
+        dev = s2.device
+        d2, db = _stream_grads(g_s, g_y, B * N, D)
         do = ops.gemm(db, weight_bf16(proj_w)[:D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
         dproj_w = ops.gemm(db, o, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if proj_w.requires_grad else None
         dproj_b = ops.colsum_bf16(db) if has_pb else None
@@ -488,50 +510,44 @@ class CrossAttnSubLayerFn(torch.autograd.Function):
         dkv_b = ops.colsum_bf16(dkv) if has_kvb else None
         dqg = torch.zeros(D, device=dev, dtype=torch.float32) if qnw.requires_grad else None
         dqb = torch.zeros(D, device=dev, dtype=torch.float32) if qnb_grad else None
-        dx, dxb = ops.layernorm_bwd(dhq, x2, qnw, qmean, qrstd, dres=d2, want_bf16=True, dgamma=dqg, dbeta=dqb)
+        dx, dxb = ops.layernorm_bwd(dhq, s2, qnw, qmean, qrstd, dres=d2, want_bf16=has_pend, dgamma=dqg, dbeta=dqb)
         dctx = dcg = dcb = None
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[2]:
             dhc = ops.gemm(dkv, weight_bf16(kv_w)[:2 * D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
             dcg = torch.zeros(D, device=dev, dtype=torch.float32) if cnw.requires_grad else None
             dcb = torch.zeros(D, device=dev, dtype=torch.float32) if cnb_grad else None
             dctx, _ = ops.layernorm_bwd(dhc, c2, cnw, cmean, crstd, dgamma=dcg, dbeta=dcb)
             dctx = dctx.view(B, M, D)
-        return (_hand_over(dx, dxb, (B, N, D)), dctx, None, dqg, dqb, dcg, dcb, dq_w, dq_b, dkv_w, dkv_b, dproj_w, dproj_b,
-                None, None, None, None)
+        return (dx.view(B, N, D), dxb.view(B, N, D) if has_pend else None, dctx, None, dqg, dqb, dcg, dcb, dq_w, dq_b, dkv_w, dkv_b,
+                dproj_w, dproj_b, None, None, None, None)
 
 
 class GatedMlpSubLayerFn(torch.autograd.Function):
-    """x + fc2(silu(fc1 LN(x)) * fc3 LN(x)) -- fm_utils.py:333 / 365 with GatedMlp.forward (:142-144)."""
+    """(x, ypend) -> (s, y = fc2(silu(fc1 LN(s)) * fc3 LN(s)))   fm_utils.py:333 / 365 with GatedMlp.forward (:142-144)."""
 
     @staticmethod
-    def forward(ctx, x, nw, nb, w1, w3, w2, b1, b3, b2, eps):
+    def forward(ctx, x, ypend, nw, nb, w1, w3, w2, b1, b3, b2, eps):
         shape = x.shape
         D = shape[-1]
-        x2 = x.reshape(-1, D)
-        if not x2.is_contiguous():
-            x2 = x2.contiguous()
+        x2, y2 = _prep_stream(x, ypend, D)
         H, Hp = w1.shape[0], _pad_rows(w1.shape[0])
-        h, mean, rstd = ops.layernorm_fwd(x2, nw, nb, eps, out_bf16=True)
+        s2, h, mean, rstd = ops.add_layernorm_fwd(x2, y2, nw, nb, eps)
         bias13 = None
         if b1 is not None:
             bias13 = torch.zeros(2 * Hp, device=x2.device, dtype=torch.float32)
             bias13[:H] = b1
             bias13[Hp:Hp + H] = b3
         ab, g = ops.gemm(h, weight_bf16(w1, w3), epilogue=ops.EPI_SWIGLU, bias=bias13)           # [R, 2Hp], [R, Hp]
-        w2b = weight_bf16(w2)
-        out = ops.gemm(g[:, :H] if Hp != H else g, w2b, epilogue=ops.EPI_RESID, bias=b2, resid=x2, n_out=D)
-        ctx.save_for_backward(x2, mean, rstd, h, ab, g, nw, w1, w3, w2)
-        ctx.cfg = (shape, D, H, Hp, b1 is not None, b2 is not None, nb is not None and nb.requires_grad)
-        return out.view(shape)
+        y = ops.gemm(g[:, :H] if Hp != H else g, weight_bf16(w2), epilogue=ops.EPI_BF16, bias=b2, n_out=D)
+        ctx.save_for_backward(s2, mean, rstd, h, ab, g, nw, w1, w3, w2)
+        ctx.cfg = (shape, D, H, Hp, b1 is not None, b2 is not None, nb is not None and nb.requires_grad, ypend is not None)
+        return s2.view(shape), y.view(shape)
 
     @staticmethod
-    def backward(ctx, dout):
-        x2, mean, rstd, h, ab, g, nw, w1, w3, w2 = ctx.saved_tensors
-        shape, D, H, Hp, has_b13, has_b2, nb_grad = ctx.cfg
-        d2 = dout.reshape(-1, D)
-        if not d2.is_contiguous():
-            d2 = d2.contiguous()
-        db = _grad_bf16(d2, dout)
+    def backward(ctx, g_s, g_y):
+        s2, mean, rstd, h, ab, g, nw, w1, w3, w2 = ctx.saved_tensors
+        shape, D, H, Hp, has_b13, has_b2, nb_grad, has_pend = ctx.cfg
+        d2, db = _stream_grads(g_s, g_y, s2.shape[0], D)
         gH = g[:, :H] if Hp != H else g
         if Hp != H:
             dg = torch.zeros_like(g)
@@ -549,43 +565,67 @@ class GatedMlpSubLayerFn(torch.autograd.Function):
         if has_b13:
             dbias = ops.colsum_bf16(dab)
             db1, db3 = dbias[:H], dbias[Hp:Hp + H]
-        dgamma = torch.zeros(D, device=x2.device, dtype=torch.float32) if nw.requires_grad else None
-        dbeta = torch.zeros(D, device=x2.device, dtype=torch.float32) if nb_grad else None
-        dx, dxb = ops.layernorm_bwd(dh, x2, nw, mean, rstd, dres=d2, want_bf16=True, dgamma=dgamma, dbeta=dbeta)
-        return _hand_over(dx, dxb, shape), dgamma, dbeta, dw1, dw3, dw2, db1, db3, db2, None
+        dgamma = torch.zeros(D, device=s2.device, dtype=torch.float32) if nw.requires_grad else None
+        dbeta = torch.zeros(D, device=s2.device, dtype=torch.float32) if nb_grad else None
+        dx, dxb = ops.layernorm_bwd(dh, s2, nw, mean, rstd, dres=d2, want_bf16=has_pend, dgamma=dgamma, dbeta=dbeta)
+        return dx.view(shape), dxb.view(shape) if has_pend else None, dgamma, dbeta, dw1, dw3, dw2, db1, db3, db2, None
 
 
 class NormLinearResidualFn(torch.autograd.Function):
-    """resid + bf16(LN(x) W^T + b):  decoder_proj_context(encoder_norm(x)) + encoder_emb  (fm.py:678-679)."""
+    """resid + bf16(LN(x + ypend) W^T + b):  decoder_proj_context(encoder_norm(x)) + encoder_emb  (fm.py:678-679)."""
 
     @staticmethod
-    def forward(ctx, x, nw, nb, w, b, resid, eps):
+    def forward(ctx, x, ypend, nw, nb, w, b, resid, eps):
         D = x.shape[-1]
-        x2 = x.reshape(-1, D)
-        if not x2.is_contiguous():
-            x2 = x2.contiguous()
+        x2, y2 = _prep_stream(x, ypend, D)
         r2 = resid.reshape(-1, w.shape[0])
         if not r2.is_contiguous():
             r2 = r2.contiguous()
-        h, mean, rstd = ops.layernorm_fwd(x2, nw, nb, eps, out_bf16=True)
+        s2, h, mean, rstd = ops.add_layernorm_fwd(x2, y2, nw, nb, eps)
         out = ops.gemm(h, weight_bf16(w), epilogue=ops.EPI_RESID, bias=b, resid=r2, n_out=w.shape[0])
-        ctx.save_for_backward(x2, mean, rstd, h, nw, w)
-        ctx.cfg = (x.shape, resid.shape, b is not None, nb is not None and nb.requires_grad)
+        ctx.save_for_backward(s2, mean, rstd, h, nw, w)
+        ctx.cfg = (x.shape, resid.shape, b is not None, nb is not None and nb.requires_grad, ypend is not None)
         return out.view(resid.shape)
 
     @staticmethod
     def backward(ctx, dout):
-        x2, mean, rstd, h, nw, w = ctx.saved_tensors
-        xshape, rshape, has_b, nb_grad = ctx.cfg
-        D = x2.shape[1]
+        s2, mean, rstd, h, nw, w = ctx.saved_tensors
+        xshape, rshape, has_b, nb_grad, has_pend = ctx.cfg
+        D = s2.shape[1]
         d2 = dout.reshape(-1, w.shape[0])
         if not d2.is_contiguous():
             d2 = d2.contiguous()
-        db = _grad_bf16(d2, dout)
+        db = ops.cast_bf16(d2) if d2.dtype == torch.float32 else d2
         dh = ops.gemm(db, weight_bf16(w)[:w.shape[0]], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
         dw = ops.gemm(db, h, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if w.requires_grad else None
         dbias = ops.colsum_bf16(db) if has_b else None
-        dgamma = torch.zeros(D, device=x2.device, dtype=torch.float32) if nw.requires_grad else None
-        dbeta = torch.zeros(D, device=x2.device, dtype=torch.float32) if nb_grad else None
-        dx, dxb = ops.layernorm_bwd(dh, x2, nw, mean, rstd, want_bf16=True, dgamma=dgamma, dbeta=dbeta)
-        return _hand_over(dx, dxb, xshape), dgamma, dbeta, dw, dbias, dout.view(rshape), None
+        dgamma = torch.zeros(D, device=s2.device, dtype=torch.float32) if nw.requires_grad else None
+        dbeta = torch.zeros(D, device=s2.device, dtype=torch.float32) if nb_grad else None
+        dx, dxb = ops.layernorm_bwd(dh, s2, nw, mean, rstd, want_bf16=has_pend, dgamma=dgamma, dbeta=dbeta)
+        return dx.view(xshape), dxb.view(xshape) if has_pend else None, dgamma, dbeta, dw, dbias, dout.view(rshape), None
+
+
+class AddLayerNormFn(torch.autograd.Function):
+    """LN(x + ypend) as bf16: the stack's final norm (fm.py:494 / 517) consuming the last pending branch."""
+
+    @staticmethod
+    def forward(ctx, x, ypend, nw, nb, eps):
+        D = x.shape[-1]
+        x2, y2 = _prep_stream(x, ypend, D)
+        s2, h, mean, rstd = ops.add_layernorm_fwd(x2, y2, nw, nb, eps)
+        ctx.save_for_backward(s2, mean, rstd, nw)
+        ctx.cfg = (x.shape, nb is not None and nb.requires_grad, ypend is not None)
+        return h.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dh):
+        s2, mean, rstd, nw = ctx.saved_tensors
+        shape, nb_grad, has_pend = ctx.cfg
+        D = s2.shape[1]
+        dh2 = dh.reshape(-1, D)
+        if not dh2.is_contiguous():
+            dh2 = dh2.contiguous()
+        dgamma = torch.zeros(D, device=s2.device, dtype=torch.float32) if nw.requires_grad else None
+        dbeta = torch.zeros(D, device=s2.device, dtype=torch.float32) if nb_grad else None
+        dx, dxb = ops.layernorm_bwd(dh2, s2, nw, mean, rstd, want_bf16=has_pend, dgamma=dgamma, dbeta=dbeta)
+        return dx.view(shape), dxb.view(shape) if has_pend else None, dgamma, dbeta, None

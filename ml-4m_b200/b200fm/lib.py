@@ -28,6 +28,8 @@ SIGNATURES = {
     "b200fm_gemm_bf16": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll,
                          c_void_p, c_void_p, c_ll, c_float, c_void_p, c_void_p],
     "b200fm_layernorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p],
+    "b200fm_add_layernorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                                 c_float, c_void_p],
     "b200fm_layernorm_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_int, c_int, c_void_p],
     "b200fm_attention_fwd": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_void_p,

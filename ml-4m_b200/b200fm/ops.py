@@ -93,6 +93,27 @@ def layernorm_fwd(x, gamma, beta, eps, out_bf16=True, save_stats=True):
     return y, mean, rstd
 
 
+def add_layernorm_fwd(x, add, gamma, beta, eps, out_bf16=True):
+    """s = x + add (fp32 stream + bf16 pending branch; add may be None -> s is x), y = LN(s).  -> (s, y, mean, rstd)."""
+    _need_cuda(x, add, gamma, beta)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    D = x.shape[-1]
+    rows = x.numel() // D
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    if add is None:
+        s = x
+        lib.call("b200fm_layernorm_fwd", _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), int(out_bf16), _ptr(mean), _ptr(rstd), rows, D,
+                 float(eps), _stream())
+    else:
+        assert add.dtype == torch.bfloat16 and add.is_contiguous() and add.numel() == x.numel()
+        s = torch.empty_like(x)
+        lib.call("b200fm_add_layernorm_fwd", _ptr(x), _ptr(add), _ptr(s), _ptr(gamma), _ptr(beta), _ptr(y), int(out_bf16), _ptr(mean),
+                 _ptr(rstd), rows, D, float(eps), _stream())
+    return s, y, mean, rstd
+
+
 def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, want_bf16=False, dgamma=None, dbeta=None):
     """Returns (dx fp32, dx_bf16 | None).  dgamma / dbeta (fp32 [D]) are accumulated into when given."""
     _need_cuda(dy, x, gamma, mean, rstd, dres, dgamma, dbeta)

@@ -12,7 +12,8 @@ constexpr int kLnWarps = 8;
 // VEC = D / 128 float4 per lane
 template <int VEC, bool OUT_BF16>
 __global__ void __launch_bounds__(kLnWarps * 32)
-layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+layernorm_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ add, float* __restrict__ x_out,
+                     const float* __restrict__ gamma, const float* __restrict__ beta,
                      void* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, float eps) {
     constexpr int D = VEC * 128;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -27,7 +28,16 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
         float4 v[VEC];
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) { v[i] = xr[i * 32 + lane]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+        for (int i = 0; i < VEC; ++i) {
+            v[i] = xr[i * 32 + lane];
+            if (add != nullptr) {      // pending residual branch: x := x + y (fp32 stream += bf16 branch output), written back
+                const uint2 u = reinterpret_cast<const uint2*>(add + (size_t)row * D)[i * 32 + lane];
+                const float2 a = unpack_bf16x2(u.x), c = unpack_bf16x2(u.y);
+                v[i].x += a.x; v[i].y += a.y; v[i].z += c.x; v[i].w += c.y;
+                reinterpret_cast<float4*>(x_out + (size_t)row * D)[i * 32 + lane] = v[i];
+            }
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
         const float mean = warp_sum(s) * (1.0f / D);
         float q = 0.f;
 #pragma unroll
@@ -141,15 +151,22 @@ static int ln_grid(int rows) {
 
 extern "C" int b200fm_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_is_bf16, float* mean,
                                     float* rstd, int rows, int D, float eps, void* stream_) {
+    return b200fm_add_layernorm_fwd(x, nullptr, nullptr, gamma, beta, y, y_is_bf16, mean, rstd, rows, D, eps, stream_);
+}
+
+extern "C" int b200fm_add_layernorm_fwd(const float* x, const void* add_bf16, float* x_out, const float* gamma, const float* beta, void* y,
+                                        int y_is_bf16, float* mean, float* rstd, int rows, int D, float eps, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (rows == 0) return 0;
     B200FM_CHECK(x && gamma && y, "layernorm_fwd: null pointer");
+    B200FM_CHECK((add_bf16 == nullptr) == (x_out == nullptr), "add_layernorm_fwd: add and x_out go together");
+    const __nv_bfloat16* add = reinterpret_cast<const __nv_bfloat16*>(add_bf16);
     B200FM_CHECK(D % 128 == 0 && D >= 128 && D <= 2048, "layernorm_fwd: D=%d unsupported (need multiple of 128 in [128, 2048])", D);
     const int grid = ln_grid(rows);
 #define LN_FWD(V)                                                                                                        \
     case V:                                                                                                              \
-        if (y_is_bf16) layernorm_fwd_kernel<V, true><<<grid, kLnWarps * 32, 0, stream>>>(x, gamma, beta, y, mean, rstd, rows, eps); \
-        else layernorm_fwd_kernel<V, false><<<grid, kLnWarps * 32, 0, stream>>>(x, gamma, beta, y, mean, rstd, rows, eps);          \
+        if (y_is_bf16) layernorm_fwd_kernel<V, true><<<grid, kLnWarps * 32, 0, stream>>>(x, add, x_out, gamma, beta, y, mean, rstd, rows, eps); \
+        else layernorm_fwd_kernel<V, false><<<grid, kLnWarps * 32, 0, stream>>>(x, add, x_out, gamma, beta, y, mean, rstd, rows, eps);          \
         break;
     switch (D / 128) {
         LN_FWD(1) LN_FWD(2) LN_FWD(3) LN_FWD(4) LN_FWD(5) LN_FWD(6) LN_FWD(8) LN_FWD(10) LN_FWD(12) LN_FWD(16)

@@ -28,7 +28,7 @@ from b200fm import functional as BF
 from b200fm import lib, ops
 from b200fm.compat import MODALITY_INFO, PyTorchModelHubMixin, register_model
 
-from .fm_utils import Block, DecoderBlock, LayerNorm, _linear_residual, _norm_bf16, _norm_params
+from .fm_utils import Block, DecoderBlock, LayerNorm, _linear_residual, _norm_bf16, _norm_params, _settle
 
 # the 13 registered model names of the reference (fm.py:33-50); `register_model` appends them to __all__
 _PRESET_NAMES = (
@@ -287,12 +287,14 @@ class FourM(nn.Module):
     def _encoder_to_context(self, x, encoder_mask, encoder_emb):
         """encoder blocks -> encoder_norm -> decoder_proj_context(x) + encoder_emb (reference fm.py:678-679); the norm
         emits the bf16 GEMM operand and the `+ encoder_emb` rides in the GEMM epilogue."""
+        ypend = None
         for blk in self.encoder:
-            x = blk(x, mask=encoder_mask)
+            x, ypend = blk.forward_pending(x, ypend, mask=encoder_mask)
         np_ = _norm_params(self.encoder_norm)
         if np_ is not None and type(self.decoder_proj_context) is nn.Linear and x.dtype == torch.float32:
-            return BF.NormLinearResidualFn.apply(x, np_[0], np_[1], self.decoder_proj_context.weight, self.decoder_proj_context.bias,
-                                                 encoder_emb, np_[2])
+            return BF.NormLinearResidualFn.apply(x, ypend, np_[0], np_[1], self.decoder_proj_context.weight,
+                                                 self.decoder_proj_context.bias, encoder_emb, np_[2])
+        x = _settle(x, ypend)
         return _linear_residual(self.decoder_proj_context, _norm_bf16(self.encoder_norm, x), encoder_emb)
 
     # ------------------------------------------------------------------ heads
@@ -376,10 +378,14 @@ class FourM(nn.Module):
         dec_attn_mask = ops.decoder_attention_mask(dplan.dam, dplan.mod_raw, self.decoder_causal_mask, self.decoder_sep_mask)
 
         context = self._encoder_to_context(x0, encoder_mask, enc_emb)
-        y = y0
+        y, ypend = y0, None
         for blk in self.decoder:
-            y = blk(y, context, sa_mask=dec_attn_mask, xa_mask=encoder_mask)
-        y = _norm_bf16(self.decoder_norm, y)                      # bf16: the head GEMMs' operand
+            y, ypend = blk.forward_pending(y, ypend, context, sa_mask=dec_attn_mask, xa_mask=encoder_mask)
+        np_ = _norm_params(self.decoder_norm)
+        if np_ is not None and y.dtype == torch.float32:
+            y = BF.AddLayerNormFn.apply(y, ypend, np_[0], np_[1], np_[2])      # bf16: the head GEMMs' operand
+        else:
+            y = _norm_bf16(self.decoder_norm, _settle(y, ypend))
 
         if return_logits:
             return {mod: self.decoder_embeddings[mod].forward_logits(y) for mod in dec_mods}

@@ -295,34 +295,40 @@ def _plain_gated_mlp(m):
     return (type(m) is GatedMlp and _plain_linear(m.fc1) and _plain_linear(m.fc2) and _plain_linear(m.fc3) and type(m.act) is nn.SiLU)
 
 
-def _self_attn_sublayer(norm, attn, x, mask):
-    """x + attn(norm(x)) as ONE autograd node when every piece is a plain module; None otherwise."""
+def _self_attn_sublayer(norm, attn, x, ypend, mask):
+    """(x, pending bf16 branch) -> (s = x + pending, new pending branch) as ONE autograd node when every piece is a plain
+    module; None otherwise."""
     np_ = _norm_params(norm)
     if np_ is None or not _plain_attention(attn) or x.shape[-1] // attn.num_heads != 64 or x.dtype != torch.float32:
         return None
     B, N, _ = x.shape
-    return BF.SelfAttnSubLayerFn.apply(x, _prep_mask(mask, B, N, N), np_[0], np_[1], attn.qkv.weight, attn.qkv.bias,
+    return BF.SelfAttnSubLayerFn.apply(x, ypend, _prep_mask(mask, B, N, N), np_[0], np_[1], attn.qkv.weight, attn.qkv.bias,
                                        attn.proj.weight, attn.proj.bias, np_[2], attn.num_heads, attn.scale)
 
 
-def _cross_attn_sublayer(qnorm, cnorm, attn, x, context, mask):
+def _cross_attn_sublayer(qnorm, cnorm, attn, x, ypend, context, mask):
     qp, cp = _norm_params(qnorm), _norm_params(cnorm)
     if qp is None or cp is None or not _plain_cross_attention(attn) or x.shape[-1] // attn.num_heads != 64:
         return None
     if x.dtype != torch.float32 or context.dtype != torch.float32:
         return None
     B, N, _ = x.shape
-    return BF.CrossAttnSubLayerFn.apply(x, context, _prep_mask(mask, B, N, context.shape[1]), qp[0], qp[1], cp[0], cp[1],
+    return BF.CrossAttnSubLayerFn.apply(x, ypend, context, _prep_mask(mask, B, N, context.shape[1]), qp[0], qp[1], cp[0], cp[1],
                                         attn.q.weight, attn.q.bias, attn.kv.weight, attn.kv.bias, attn.proj.weight, attn.proj.bias,
                                         qp[2], cp[2], attn.num_heads, attn.scale)
 
 
-def _mlp_sublayer(norm, mlp, x):
+def _mlp_sublayer(norm, mlp, x, ypend):
     np_ = _norm_params(norm)
     if np_ is None or not _plain_gated_mlp(mlp) or x.dtype != torch.float32:
         return None
-    return BF.GatedMlpSubLayerFn.apply(x, np_[0], np_[1], mlp.fc1.weight, mlp.fc3.weight, mlp.fc2.weight, mlp.fc1.bias,
+    return BF.GatedMlpSubLayerFn.apply(x, ypend, np_[0], np_[1], mlp.fc1.weight, mlp.fc3.weight, mlp.fc2.weight, mlp.fc1.bias,
                                        mlp.fc3.bias, mlp.fc2.bias, np_[2])
+
+
+def _settle(x, ypend):
+    """Materialise the stream: x + pending branch (only where a caller needs the plain tensor)."""
+    return x if ypend is None else x + ypend.float()
 
 
 class Block(nn.Module):
@@ -345,13 +351,28 @@ class Block(nn.Module):
         else:
             self.mlp = GatedMlp(in_features=dim, hidden_features=mlp_hidden_dim, act_layer=act_layer, bias=mlp_bias)
 
+    def forward_pending(self, x, ypend, mask=None):
+        """(stream, pending bf16 branch output) -> (stream, pending): the residual adds are deferred into the next norm
+        kernel.  FourM's stacks chain blocks through this; `forward` is the reference-shaped wrapper."""
+        if not _residual_ok(self):
+            return self.forward(_settle(x, ypend), mask), None
+        r = _self_attn_sublayer(self.norm1, self.attn, x, ypend, mask)
+        if r is None:
+            x = _settle(x, ypend)
+            x, ypend = self.attn.forward_residual(_norm_bf16(self.norm1, x), x, mask), None
+        else:
+            x, ypend = r
+        r = _mlp_sublayer(self.norm2, self.mlp, x, ypend)
+        if r is None:
+            x = _settle(x, ypend)
+            x, ypend = self.mlp.forward_residual(_norm_bf16(self.norm2, x), x), None
+        else:
+            x, ypend = r
+        return x, ypend
+
     def forward(self, x, mask=None):
         if _residual_ok(self):
-            y = _self_attn_sublayer(self.norm1, self.attn, x, mask)
-            x = y if y is not None else self.attn.forward_residual(_norm_bf16(self.norm1, x), x, mask)
-            y = _mlp_sublayer(self.norm2, self.mlp, x)
-            x = y if y is not None else self.mlp.forward_residual(_norm_bf16(self.norm2, x), x)
-            return x
+            return _settle(*self.forward_pending(x, None, mask))
         x = x + self.drop_path(self.attn(_norm_bf16(self.norm1, x), mask))
         x = x + self.drop_path(self.mlp(_norm_bf16(self.norm2, x)))
         return x
@@ -381,16 +402,33 @@ class DecoderBlock(nn.Module):
         else:
             self.mlp = GatedMlp(in_features=dim, hidden_features=mlp_hidden_dim, act_layer=act_layer, bias=mlp_bias)
 
+    def forward_pending(self, x, ypend, context, sa_mask=None, xa_mask=None):
+        """See Block.forward_pending."""
+        if not _residual_ok(self):
+            return self.forward(_settle(x, ypend), context, sa_mask, xa_mask), None
+        r = _self_attn_sublayer(self.norm1, self.self_attn, x, ypend, sa_mask)
+        if r is None:
+            x = _settle(x, ypend)
+            x, ypend = self.self_attn.forward_residual(_norm_bf16(self.norm1, x), x, sa_mask), None
+        else:
+            x, ypend = r
+        r = _cross_attn_sublayer(self.query_norm, self.context_norm, self.cross_attn, x, ypend, context, xa_mask)
+        if r is None:
+            x = _settle(x, ypend)
+            x, ypend = self.cross_attn.forward_residual(_norm_bf16(self.query_norm, x), _norm_bf16(self.context_norm, context), x, xa_mask), None
+        else:
+            x, ypend = r
+        r = _mlp_sublayer(self.norm2, self.mlp, x, ypend)
+        if r is None:
+            x = _settle(x, ypend)
+            x, ypend = self.mlp.forward_residual(_norm_bf16(self.norm2, x), x), None
+        else:
+            x, ypend = r
+        return x, ypend
+
     def forward(self, x, context, sa_mask=None, xa_mask=None):
         if _residual_ok(self):
-            y = _self_attn_sublayer(self.norm1, self.self_attn, x, sa_mask)
-            x = y if y is not None else self.self_attn.forward_residual(_norm_bf16(self.norm1, x), x, sa_mask)
-            y = _cross_attn_sublayer(self.query_norm, self.context_norm, self.cross_attn, x, context, xa_mask)
-            x = y if y is not None else self.cross_attn.forward_residual(_norm_bf16(self.query_norm, x),
-                                                                        _norm_bf16(self.context_norm, context), x, xa_mask)
-            y = _mlp_sublayer(self.norm2, self.mlp, x)
-            x = y if y is not None else self.mlp.forward_residual(_norm_bf16(self.norm2, x), x)
-            return x
+            return _settle(*self.forward_pending(x, None, context, sa_mask, xa_mask))
         x = x + self.drop_path(self.self_attn(_norm_bf16(self.norm1, x), sa_mask))
         x = x + self.drop_path(self.cross_attn(_norm_bf16(self.query_norm, x), _norm_bf16(self.context_norm, context), xa_mask))
         x = x + self.drop_path(self.mlp(_norm_bf16(self.norm2, x)))
