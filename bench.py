@@ -226,6 +226,7 @@ def run_b200_arm(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         last = None
+        t_cpu0 = time.perf_counter()
         for i in range(n_steps):
             if e2e:
                 hb = host_batches[i % 2]
@@ -235,6 +236,7 @@ def run_b200_arm(args):
             else:
                 loss, mod_loss, gnorm = step(dev_batches[i % 2])
         e1.record()
+        timed.cpu_ms = (time.perf_counter() - t_cpu0) * 1e3 / n_steps       # host time to ISSUE a step (no sync inside)
         sync()
         ms = e0.elapsed_time(e1)
         if world > 1:
@@ -256,6 +258,7 @@ def run_b200_arm(args):
     if rank == 0:
         sampler.start()
     ms, launches, loss_val = timed(args.steps, e2e=False)
+    cpu_issue_ms = timed.cpu_ms
     ms_e2e, _, loss_e2e = timed(args.steps, e2e=True)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -298,7 +301,7 @@ def run_b200_arm(args):
                                 decoder_tokens=n_tok, parallelism=f"dp{world}", params_m=round(n_params / 1e6, 1),
                                 l2_policy="per-step working set (activations+grads > 2 GB) exceeds the 126 MB L2; two alternating input batches"),
                     e2e=dict(value=tps_e2e, unit="tokens/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
-                    gpu_launches=launches, loss=loss_val,
+                    gpu_launches=launches, loss=loss_val, host_issue_ms_per_step=cpu_issue_ms,
                     model_tflops_per_gpu=model_tflops / world,
                     frac_of_bf16_peak=model_tflops / world / peaks["bf16"],
                     roofline=dict(bound="tensor", kernel="gemm_kernel<BN,LAYOUT,EPI> (all tcgen05 GEMM launches of a step)", achieved=achieved,

@@ -10,7 +10,12 @@ EPI_BF16, EPI_F32, EPI_RESID, EPI_SWIGLU, EPI_GELU, EPI_TANH = 0, 1, 2, 3, 4, 5
 PROFILE = None     # bench.py sets this to a list: (start_event, end_event, flops) per GEMM launch
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -308,12 +308,28 @@ class FourM(nn.Module):
                 mod_logits[mod] = self.decoder_embeddings[mod].forward_logits(y[decoder_mod_mask == self._mod_id(mod)])
         return mod_logits
 
-    def _head_losses(self, y_bf16, target_ids, decoder_mods, decoder_mod_mask):
+    def _head_index_sets(self, decoder_mods, decoder_mod_mask):
+        """Row-index lists per modality + their counts.  Launched right after the decoder selection, long before the head needs
+        them: the counts travel to pinned host memory asynchronously while the block stack runs, so reading them later does not
+        drain the GPU queue (the reference syncs ~15 times per step here, fm.py:591-596 + run_training_4m.py:726-727)."""
+        dev = decoder_mod_mask.device
+        key = (tuple(decoder_mods), str(dev))
+        cache = self.__dict__.setdefault("_head_ids_cache", {})
+        if key not in cache:
+            cache[key] = torch.tensor([self._mod_id(m) for m in decoder_mods], device=dev, dtype=torch.int32)
+        rows, counts = ops.head_rows(decoder_mod_mask.reshape(-1), cache[key])
+        host = torch.empty(len(decoder_mods), dtype=torch.int32, pin_memory=True)
+        host.copy_(counts, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return rows, host, ev
+
+    def _head_losses(self, y_bf16, target_ids, decoder_mods, decoder_mod_mask, index_sets=None):
         """Per-modality mean cross-entropy (reference fm.py:589-600) with device-side index sets and one host read."""
         dev = y_bf16.device
-        ids = torch.tensor([self._mod_id(m) for m in decoder_mods], device=dev, dtype=torch.int32)
-        rows, counts = ops.head_rows(decoder_mod_mask.reshape(-1), ids)
-        counts_host = counts.tolist()                      # the single device->host read of the head
+        rows, host, ev = index_sets if index_sets is not None else self._head_index_sets(decoder_mods, decoder_mod_mask)
+        ev.synchronize()                                   # the single device->host hand-over of the head (already complete)
+        counts_host = host.tolist()
         y2 = y_bf16.reshape(-1, y_bf16.shape[-1])
         parts = BF.HeadGatherFn.apply(y2, rows, tuple(counts_host))
         tflat = target_ids.reshape(-1)
@@ -376,6 +392,7 @@ class FourM(nn.Module):
 
         y0, _, dplan = self._embed_side(mod_dict, True, num_decoder_tokens, dec_order)
         dec_attn_mask = ops.decoder_attention_mask(dplan.dam, dplan.mod_raw, self.decoder_causal_mask, self.decoder_sep_mask)
+        index_sets = None if return_logits else self._head_index_sets(dec_mods, dplan.mod_mask)
 
         context = self._encoder_to_context(x0, encoder_mask, enc_emb)
         y, ypend = y0, None
@@ -389,7 +406,7 @@ class FourM(nn.Module):
 
         if return_logits:
             return {mod: self.decoder_embeddings[mod].forward_logits(y) for mod in dec_mods}
-        mod_loss, mod_count = self._head_losses(y, dplan.target_ids, dec_mods, dplan.mod_mask)
+        mod_loss, mod_count = self._head_losses(y, dplan.target_ids, dec_mods, dplan.mod_mask, index_sets)
         if loss_type == 'token':
             loss = sum(mod_loss[m] * mod_count[m] for m in mod_loss) / sum(mod_count.values())
         else:
