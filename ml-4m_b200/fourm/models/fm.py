@@ -318,7 +318,12 @@ class FourM(nn.Module):
         if key not in cache:
             cache[key] = torch.tensor([self._mod_id(m) for m in decoder_mods], device=dev, dtype=torch.int32)
         rows, counts = ops.head_rows(decoder_mod_mask.reshape(-1), cache[key])
-        host = torch.empty(len(decoder_mods), dtype=torch.int32, pin_memory=True)
+        pin = self.__dict__.setdefault("_head_pinned", {})
+        slot = pin.get("i", 0) ^ 1                               # two pinned buffers, alternated (cudaHostAlloc is slow)
+        pin["i"] = slot
+        host = pin.get(slot)
+        if host is None or host.numel() != len(decoder_mods):
+            host = pin[slot] = torch.empty(len(decoder_mods), dtype=torch.int32, pin_memory=True)
         host.copy_(counts, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
