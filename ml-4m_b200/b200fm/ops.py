@@ -41,6 +41,8 @@ def gemm(a, b, layout=LAYOUT_NT, epilogue=EPI_BF16, out=None, out1=None, bias=No
     Returns out (and out1 for SWIGLU / GELU / TANH).  (Hot wrapper: argument validation lives in the C entry point.)"""
     if not a.is_cuda:
         raise lib.B200FMError("b200fm ops need CUDA tensors (there is no CPU fallback)")
+    if a.dtype is not torch.bfloat16 or b.dtype is not torch.bfloat16 or a.stride(1) != 1 or b.stride(1) != 1:
+        raise ValueError("gemm: operands must be bf16 2-D tensors with unit inner stride")
     ash, bsh = a.shape, b.shape
     if layout == LAYOUT_NT:
         M, K = ash
