@@ -50,6 +50,21 @@ def weight_bf16(*params):
     return buf
 
 
+def weight_bf16_padk(param, k_pad):
+    """bf16 copy of a [N, K] weight with its K (column) dimension zero-padded to k_pad: operands whose K is not a multiple of 8
+    (SwiGLU widths 2730 / 5461 of 4M-L / XL) need 16-byte rows for TMA.  Cached per parameter version."""
+    key = (id(param), "padk", k_pad)
+    ver = (param._version, param.data_ptr())
+    hit = _shadow.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    with torch.no_grad():
+        buf = hit[1] if hit is not None else torch.zeros(param.shape[0], k_pad, device=param.device, dtype=torch.bfloat16)
+        buf[:, :param.shape[1]].copy_(param.detach())
+    _shadow[key] = (ver, buf)
+    return buf
+
+
 def shadow_views(param):
     """bf16 mirrors of `param` currently cached (the fused AdamW kernel writes the first one itself)."""
     return _shadow_views.get(id(param), [])
@@ -538,7 +553,8 @@ class GatedMlpSubLayerFn(torch.autograd.Function):
             bias13[:H] = b1
             bias13[Hp:Hp + H] = b3
         ab, g = ops.gemm(h, weight_bf16(w1, w3), epilogue=ops.EPI_SWIGLU, bias=bias13)           # [R, 2Hp], [R, Hp]
-        y = ops.gemm(g[:, :H] if Hp != H else g, weight_bf16(w2), epilogue=ops.EPI_BF16, bias=b2, n_out=D)
+        w2b = weight_bf16(w2) if Hp == H else weight_bf16_padk(w2, Hp)      # padded gate columns are exactly zero
+        y = ops.gemm(g, w2b, epilogue=ops.EPI_BF16, bias=b2, n_out=D)
         ctx.save_for_backward(s2, mean, rstd, h, ab, g, nw, w1, w3, w2)
         ctx.cfg = (shape, D, H, Hp, b1 is not None, b2 is not None, nb is not None and nb.requires_grad, ypend is not None)
         return s2.view(shape), y.view(shape)
@@ -548,13 +564,13 @@ class GatedMlpSubLayerFn(torch.autograd.Function):
         s2, mean, rstd, h, ab, g, nw, w1, w3, w2 = ctx.saved_tensors
         shape, D, H, Hp, has_b13, has_b2, nb_grad, has_pend = ctx.cfg
         d2, db = _stream_grads(g_s, g_y, s2.shape[0], D)
-        gH = g[:, :H] if Hp != H else g
-        if Hp != H:
-            dg = torch.zeros_like(g)
-            ops.gemm(db, weight_bf16(w2)[:D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16, out=dg[:, :H])
-        else:
-            dg = ops.gemm(db, weight_bf16(w2)[:D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
-        dw2 = ops.gemm(db, gH, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if w2.requires_grad else None
+        w2b = weight_bf16(w2)[:D] if Hp == H else weight_bf16_padk(w2, Hp)
+        dg = ops.gemm(db, w2b, layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)              # [R, Hp]; padded columns are zero
+        dw2 = None
+        if w2.requires_grad:
+            dw2 = ops.gemm(db, g, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32)            # [D, Hp]
+            if Hp != H:
+                dw2 = dw2[:, :H]
         db2 = ops.colsum_bf16(db) if has_b2 else None
         dab = ops.swiglu_bwd(ab, dg)
         dh = ops.gemm(dab, weight_bf16(w1, w3), layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)

@@ -130,3 +130,55 @@ def test_loss_invariant_to_decoder_shuffle_when_no_truncation(tiny):
             loss, _ = model({m: dict(d) for m, d in batch.items()}, 128, 128)
         vals.append(float(loss))
     assert max(vals) - min(vals) <= 2e-3
+
+
+def test_odd_swiglu_width_matches_oracle():
+    """SwiGLU hidden widths that are not multiples of 8 (4M-L: 2730, 4M-XL: 5461; here dim 256 -> 682) run on zero-padded
+    weight shadows; forward loss and gradients must match the oracle on the same weights."""
+    from functools import partial
+    import torch.nn as nn
+    from b200fm.compat import build_mod7_embeddings
+    from fourm.models.fm import FourM
+    from fourm.models.fm_utils import LayerNorm
+    torch.manual_seed(0)
+    enc, dec, info = build_mod7_embeddings()
+    model = FourM(enc, dec, info, dim=256, encoder_depth=2, decoder_depth=2, num_heads=4, qkv_bias=False, proj_bias=False, mlp_bias=False,
+                  norm_layer=partial(LayerNorm, eps=1e-6, bias=False), act_layer=nn.SiLU, gated_mlp=True).cuda()
+    assert model.encoder[0].mlp.fc1.weight.shape[0] == 682
+    batch = O.synthetic_mod7_batch(2, seed=11)
+    random.seed(1)
+    loss, _ = model(_to_cuda(batch), 128, 128)
+    loss.backward()
+    torch.cuda.synchronize()
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    keys = ["encoder.1.mlp.fc2.weight", "decoder.0.mlp.fc1.weight", "decoder.1.mlp.fc3.weight"]
+    for k in keys:
+        sd[k] = sd[k].clone().requires_grad_(True)
+    random.seed(1)
+    order = random.sample([m for m in batch if m in model.decoder_embeddings], len(model.decoder_embeddings))
+    ref, _ = O.fourm_forward(sd, O.model_cfg(256, 4, 2, 2), O.mod7_specs(), batch, 128, 128, order)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 5e-3
+    params = dict(model.named_parameters())
+    for k in keys:
+        g, r = params[k].grad.float().cpu(), sd[k].grad
+        assert g.shape == r.shape
+        assert abs(float(g.norm()) - float(r.norm())) <= 3e-2 * float(r.norm()), k
+
+
+def test_large_config_shapes_cfg3():
+    """BASELINE configs[2] shape: 4M-L (dim 1024, 16 heads, SwiGLU 2730) with 256 + 256 tokens: one fwd+bwd step runs and is finite."""
+    from b200fm.compat import build_mod7_embeddings, create_model
+    from b200fm.synthetic import budgets_for, mod7_batch
+    torch.manual_seed(0)
+    enc, dec, info = build_mod7_embeddings()
+    model = create_model("fm_large_24e_24d_swiglu_nobias", encoder_embeddings=enc, decoder_embeddings=dec, modality_info=info).cuda()
+    a, b, c, d = budgets_for(256)
+    batch = _to_cuda(mod7_batch(4, a, b, c, d, seed=3))
+    random.seed(0)
+    loss, mod_loss = model(batch, 256, 256)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss) and 8.0 < float(loss) < 12.0
+    g = model.encoder[3].mlp.fc2.weight.grad
+    assert g is not None and g.shape == (1024, 2730) and torch.isfinite(g).all() and float(g.abs().sum()) > 0
