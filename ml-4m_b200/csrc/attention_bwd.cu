@@ -9,7 +9,8 @@
 //     dV += P^T dO,  dK += dS^T Q              (M = keys: the bf16 P / dS smem tiles are consumed as MN-major A operands)
 //     dQ += dS K                               (same dS tile consumed as a K-major A operand)
 // dV, dK live in TMEM across the query loop, dQ (one 64-column accumulator per query tile) across the key loop.
-// CTA = 6 warps: 0-3 softmax-backward math + epilogues (thread = row), 4 = TMA producer / TMEM allocator, 5 = MMA issuer.
+// CTA = 10 warps: 0-7 softmax-backward math + epilogues (thread = row; the two warps of a lane quarter split the key columns),
+// 8 = TMA producer / TMEM allocator (loads run one buffer ahead of the MMAs), 9 = MMA issuer.
 #include <cfloat>
 
 #include "../../include/b200fm.h"
@@ -19,18 +20,22 @@
 
 namespace b200fm {
 
+// smem: Q/dO buffers (double-buffered across work items when NQT == 1), K/V double-buffered across key tiles / items,
+// P and dS tiles.  NQT=1: 2*32 + 2*32 + 64 = 192 KB;  NQT=2: 64 + 2*32 + 64 = 192 KB.
 template <int NQT>
 struct AttnBwdSmem {
-    static constexpr int kQ = 0;                       // NQT x 16 KB
-    static constexpr int kDO = NQT * 16384;            // NQT x 16 KB
-    static constexpr int kK = 2 * NQT * 16384;
-    static constexpr int kV = kK + 16384;
-    static constexpr int kP = kV + 16384;              // 32 KB  [128 q][128 keys] bf16, two 64-key swizzle atoms
-    static constexpr int kDS = kP + 32768;             // 32 KB
+    static constexpr int kQBufs = NQT == 1 ? 2 : 1;
+    static constexpr int kQBufBytes = NQT * 2 * 16384;                  // Q tiles then dO tiles of one item
+    static constexpr int kQ = 0;
+    static constexpr int kKV = kQBufs * kQBufBytes;                     // 2 x (K 16 KB + V 16 KB)
+    static constexpr int kP = kKV + 2 * 32768;                          // 32 KB  [128 q][128 keys] bf16, two 64-key swizzle atoms
+    static constexpr int kDS = kP + 32768;                              // 32 KB
     static constexpr int kBar = kDS + 32768;
     static constexpr int kTotal = kBar + 256 + 1024;
 };
 constexpr int kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
+constexpr int kBwdThreads = 320;       // warps 0-7: softmax-backward math + epilogues (lane quarter = warp & 3, column half = warp >> 2)
+constexpr int kBwdMathWarps = 8;       // warp 8: TMA producer + TMEM allocator, warp 9: MMA issuer
 
 struct AttnBwdArgs {
     const uint8_t* mask;
@@ -45,7 +50,7 @@ struct AttnBwdArgs {
     float scale, scale_log2;
 };
 
-B200FM_DEVINL void store_row64_bf16(__nv_bfloat16* dst, const uint32_t (&a)[32], const uint32_t (&b)[32]) {
+B200FM_DEVINL void store_row32_bf16(__nv_bfloat16* dst, const uint32_t (&a)[32]) {
     uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -53,39 +58,36 @@ B200FM_DEVINL void store_row64_bf16(__nv_bfloat16* dst, const uint32_t (&a)[32],
                            pack_bf16x2(__uint_as_float(a[8 * q + 2]), __uint_as_float(a[8 * q + 3])),
                            pack_bf16x2(__uint_as_float(a[8 * q + 4]), __uint_as_float(a[8 * q + 5])),
                            pack_bf16x2(__uint_as_float(a[8 * q + 6]), __uint_as_float(a[8 * q + 7])));
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-        d4[4 + q] = make_uint4(pack_bf16x2(__uint_as_float(b[8 * q]), __uint_as_float(b[8 * q + 1])),
-                               pack_bf16x2(__uint_as_float(b[8 * q + 2]), __uint_as_float(b[8 * q + 3])),
-                               pack_bf16x2(__uint_as_float(b[8 * q + 4]), __uint_as_float(b[8 * q + 5])),
-                               pack_bf16x2(__uint_as_float(b[8 * q + 6]), __uint_as_float(b[8 * q + 7])));
 }
 
 template <int NQT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                      const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                      const AttnBwdArgs args) {
     using SM = AttnBwdSmem<NQT>;
+    constexpr int QB = SM::kQBufs;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::kBar);
-    uint64_t* full_q = bars + 0;    uint64_t* free_q = bars + 1;
-    uint64_t* full_kv = bars + 2;   uint64_t* free_kv = bars + 3;
-    uint64_t* sdp_full = bars + 4;  uint64_t* pds_full = bars + 5;
-    uint64_t* dkv_full = bars + 6;  uint64_t* dkv_free = bars + 7;
-    uint64_t* dq_full = bars + 8;   uint64_t* dq_free = bars + 9;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* full_q = bars + 0;    // [2]
+    uint64_t* free_q = bars + 2;    // [2]
+    uint64_t* full_kv = bars + 4;   // [2]
+    uint64_t* free_kv = bars + 6;   // [2]
+    uint64_t* sdp_full = bars + 8;  uint64_t* pds_full = bars + 9;
+    uint64_t* dkv_full = bars + 10; uint64_t* dkv_free = bars + 11;
+    uint64_t* dq_full = bars + 12;  uint64_t* dq_free = bars + 13;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkt = args.nkt;
 
-    if (warp == 4) {
+    if (warp == kBwdMathWarps) {
         if (lane == 0) {
             tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
-            mbar_init(full_q, 1); mbar_init(free_q, 1); mbar_init(full_kv, 1); mbar_init(free_kv, 1);
-            mbar_init(sdp_full, 1); mbar_init(pds_full, 128); mbar_init(dkv_full, 1); mbar_init(dkv_free, 4);
-            mbar_init(dq_full, 1); mbar_init(dq_free, 4);
+            for (int i = 0; i < 2; ++i) { mbar_init(&full_q[i], 1); mbar_init(&free_q[i], 1); mbar_init(&full_kv[i], 1); mbar_init(&free_kv[i], 1); }
+            mbar_init(sdp_full, 1); mbar_init(pds_full, kBwdMathWarps * 32); mbar_init(dkv_full, 1); mbar_init(dkv_free, kBwdMathWarps);
+            mbar_init(dq_full, 1); mbar_init(dq_free, kBwdMathWarps);
             fence_mbar_init();
         }
         __syncwarp();
@@ -96,42 +98,50 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == kBwdMathWarps) {
+        // ------------------------------ TMA producer: runs ahead of the MMAs by one buffer ------------------------------
         if (lane == 0) {
             uint32_t it = 0, kvc = 0;
             for (int item = blockIdx.x; item < args.num_items; item += gridDim.x, ++it) {
                 const int h = item % args.H, b = item / args.H;
-                mbar_wait(free_q, (it & 1) ^ 1);
-                mbar_arrive_expect_tx(full_q, NQT * 2 * 16384);
+                const uint32_t qb = it % QB, qn = it / QB;                  // buffer and its use count
+                mbar_wait(&free_q[qb], (qn & 1) ^ 1);
+                mbar_arrive_expect_tx(&full_q[qb], NQT * 2 * 16384);
+                uint8_t* sq = smem + SM::kQ + qb * SM::kQBufBytes;
 #pragma unroll
                 for (int qt = 0; qt < NQT; ++qt) {
-                    tma_load_3d(smem + SM::kQ + qt * 16384, &tmap_q, full_q, h * 64, qt * 128, b);
-                    tma_load_3d(smem + SM::kDO + qt * 16384, &tmap_do, full_q, h * 64, qt * 128, b);
+                    tma_load_3d(sq + qt * 16384, &tmap_q, &full_q[qb], h * 64, qt * 128, b);
+                    tma_load_3d(sq + (NQT + qt) * 16384, &tmap_do, &full_q[qb], h * 64, qt * 128, b);
                 }
                 for (int kt = 0; kt < nkt; ++kt, ++kvc) {
-                    mbar_wait(free_kv, (kvc & 1) ^ 1);
-                    mbar_arrive_expect_tx(full_kv, 2 * 16384);
-                    tma_load_3d(smem + SM::kK, &tmap_k, full_kv, h * 64, kt * 128, b);
-                    tma_load_3d(smem + SM::kV, &tmap_v, full_kv, h * 64, kt * 128, b);
+                    const uint32_t kb = kvc & 1, kn = kvc >> 1;
+                    mbar_wait(&free_kv[kb], (kn & 1) ^ 1);
+                    mbar_arrive_expect_tx(&full_kv[kb], 2 * 16384);
+                    tma_load_3d(smem + SM::kKV + kb * 32768, &tmap_k, &full_kv[kb], h * 64, kt * 128, b);
+                    tma_load_3d(smem + SM::kKV + kb * 32768 + 16384, &tmap_v, &full_kv[kb], h * 64, kt * 128, b);
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == kBwdMathWarps + 1) {
+        // ------------------------------ MMA issuer ------------------------------
         if (lane == 0) {
             constexpr uint32_t kIdS = make_idesc_bf16(128, 128, false, false);    // S, dP : K-major x K-major
             constexpr uint32_t kIdT = make_idesc_bf16(128, 64, true, true);       // dV, dK: MN-major A (P^T / dS^T), MN-major B
             constexpr uint32_t kIdQ = make_idesc_bf16(128, 64, false, true);      // dQ    : K-major A (dS), MN-major B (K)
-            const uint32_t sK = smem_u32(smem + SM::kK), sV = smem_u32(smem + SM::kV), sP = smem_u32(smem + SM::kP),
-                           sDS = smem_u32(smem + SM::kDS);
+            const uint32_t sP = smem_u32(smem + SM::kP), sDS = smem_u32(smem + SM::kDS);
             uint32_t it = 0, kvc = 0, stepc = 0;
             for (int item = blockIdx.x; item < args.num_items; item += gridDim.x, ++it) {
-                mbar_wait(full_q, it & 1);
+                const uint32_t qb = it % QB, qn = it / QB;
+                const uint32_t sQbase = smem_u32(smem + SM::kQ + qb * SM::kQBufBytes);
+                mbar_wait(&full_q[qb], qn & 1);
                 for (int kt = 0; kt < nkt; ++kt, ++kvc) {
-                    mbar_wait(full_kv, kvc & 1);
+                    const uint32_t kb = kvc & 1, kn = kvc >> 1;
+                    const uint32_t sK = smem_u32(smem + SM::kKV + kb * 32768), sV = sK + 16384;
+                    mbar_wait(&full_kv[kb], kn & 1);
                     tc_fence_after();
 #pragma unroll 1
                     for (int qt = 0; qt < NQT; ++qt, ++stepc) {
-                        const uint32_t sQ = smem_u32(smem + SM::kQ + qt * 16384), sDO = smem_u32(smem + SM::kDO + qt * 16384);
+                        const uint32_t sQ = sQbase + qt * 16384, sDO = sQbase + (NQT + qt) * 16384;
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             umma_bf16(tmem_base + kColS, make_smem_desc(sQ + k * 32, 16, 1024), make_smem_desc(sK + k * 32, 16, 1024), kIdS, k != 0);
@@ -154,15 +164,17 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                                       make_smem_desc(sK + kk * 2048, 16384, 1024), kIdQ, (kt | kk) != 0);
                     }
                     umma_commit(dkv_full);
-                    umma_commit(free_kv);
+                    umma_commit(&free_kv[kb]);
                 }
                 umma_commit(dq_full);
-                umma_commit(free_q);
+                umma_commit(&free_q[qb]);
             }
         }
     } else {
-        const int r = warp * 32 + lane;
-        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+        // ------------------------------ math + epilogue warps 0..7 ------------------------------
+        const int quarter = warp & 3, half = warp >> 2;
+        const int r = quarter * 32 + lane;                                  // query (or key) row inside the tile == TMEM lane
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         uint8_t* sP = smem + SM::kP;
         uint8_t* sDS = smem + SM::kDS;
         uint32_t it = 0, kvc = 0, stepc = 0;
@@ -200,13 +212,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     const bool row_ok = qrow < args.Nq;
                     const uint8_t* mrow = args.mask ? args.mask + b * args.mask_b_stride + (row_ok ? qrow : 0) * args.mask_q_stride : nullptr;
                     const float m = m_[qt], inv = inv_[qt], Dr = D_[qt];
-                    uint32_t mb[4];
+                    uint32_t mb[2];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) mb[c] = attn_mask_bits32(mrow, kt * 128 + c * 32, args.Nk);
+                    for (int cc = 0; cc < 2; ++cc) mb[cc] = attn_mask_bits32(mrow, kt * 128 + (half * 2 + cc) * 32, args.Nk);
                     mbar_wait(sdp_full, stepc & 1);
                     tc_fence_after();
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int c = half * 2 + cc;                          // this warp's 32-key chunk of the 128-key tile
                         const int col0 = kt * 128 + c * 32;
                         uint32_t pk[16], dk_[16];
                         if (col0 < args.Nk) {
@@ -214,7 +227,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                             tmem_ld_x32(t_lane + kColS + c * 32, ss);
                             tmem_ld_x32(t_lane + kColDP + c * 32, dd);
                             tmem_ld_wait();
-                            const uint32_t mbits = mb[c];
+                            const uint32_t mbits = mb[cc];
 #pragma unroll
                             for (int j = 0; j < 32; j += 2) {
                                 float p[2], ds[2];
@@ -247,35 +260,36 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     tc_fence_before();
                     mbar_arrive(pds_full);
                 }
-                // dV, dK of this key tile are complete
+                // dV, dK of this key tile are complete: half 0 writes dV, half 1 writes dK (64 columns = 128 B per row each)
                 mbar_wait(dkv_full, kvc & 1);
                 tc_fence_after();
                 {
                     uint32_t a0[32], a1[32];
                     const int key = kt * 128 + r;
-                    tmem_ld_x32(t_lane + kColDV, a0);
-                    tmem_ld_x32(t_lane + kColDV + 32, a1);
-                    tmem_ld_wait();
-                    if (key < args.Nk) store_row64_bf16(args.dv + (static_cast<long long>(b) * args.Nk + key) * args.lddv + h * 64, a0, a1);
-                    tmem_ld_x32(t_lane + kColDK, a0);
-                    tmem_ld_x32(t_lane + kColDK + 32, a1);
+                    const uint32_t col = half == 0 ? kColDV : kColDK;
+                    tmem_ld_x32(t_lane + col, a0);
+                    tmem_ld_x32(t_lane + col + 32, a1);
                     tmem_ld_wait();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(dkv_free);
-                    if (key < args.Nk) store_row64_bf16(args.dk + (static_cast<long long>(b) * args.Nk + key) * args.lddk + h * 64, a0, a1);
+                    if (key < args.Nk) {
+                        __nv_bfloat16* dst = (half == 0 ? args.dv + (static_cast<long long>(b) * args.Nk + key) * args.lddv
+                                                        : args.dk + (static_cast<long long>(b) * args.Nk + key) * args.lddk) + h * 64;
+                        store_row32_bf16(dst, a0);
+                        store_row32_bf16(dst + 32, a1);
+                    }
                 }
             }
             mbar_wait(dq_full, it & 1);
             tc_fence_after();
 #pragma unroll
             for (int qt = 0; qt < NQT; ++qt) {
-                uint32_t a0[32], a1[32];
-                tmem_ld_x32(t_lane + kColDQ + qt * 64, a0);
-                tmem_ld_x32(t_lane + kColDQ + qt * 64 + 32, a1);
+                uint32_t a0[32];
+                tmem_ld_x32(t_lane + kColDQ + qt * 64 + half * 32, a0);       // each half writes 32 of the 64 dQ columns
                 tmem_ld_wait();
                 const int qrow = qt * 128 + r;
-                if (qrow < args.Nq) store_row64_bf16(args.dq + (static_cast<long long>(b) * args.Nq + qrow) * args.lddq + h * 64, a0, a1);
+                if (qrow < args.Nq) store_row32_bf16(args.dq + (static_cast<long long>(b) * args.Nq + qrow) * args.lddq + h * 64 + half * 32, a0);
             }
             tc_fence_before();
             __syncwarp();
@@ -285,7 +299,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kBwdMathWarps) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
@@ -305,7 +319,7 @@ static int launch_attn_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = a.num_items < sms ? a.num_items : sms;
-    kern<<<grid, 192, smem, stream>>>(tq, tdo, tk, tv, a);
+    kern<<<grid, kBwdThreads, smem, stream>>>(tq, tdo, tk, tv, a);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
