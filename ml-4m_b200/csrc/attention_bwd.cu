@@ -31,7 +31,8 @@ struct AttnBwdSmem {
     static constexpr int kP = kKV + 2 * 32768;                          // 32 KB  [128 q][128 keys] bf16, two 64-key swizzle atoms
     static constexpr int kDS = kP + 32768;                              // 32 KB
     static constexpr int kBar = kDS + 32768;
-    static constexpr int kTotal = kBar + 256 + 1024;
+    static constexpr int kStage = kBar + 256;                           // 8 warps x 2 KB store staging
+    static constexpr int kTotal = kStage + 8 * 2048 + 1024;
 };
 constexpr int kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
 constexpr int kBwdThreads = 320;       // warps 0-7: softmax-backward math + epilogues (lane quarter = warp & 3, column half = warp >> 2)
@@ -43,6 +44,7 @@ struct AttnBwdArgs {
     const __nv_bfloat16* out;  long long ldo;
     const __nv_bfloat16* dout; long long lddo;
     const float* stats;
+    const float* dsum;         // [B, H, Nq] fp32: D = rowsum(dO o O), produced by attn_bwd_prep_kernel
     __nv_bfloat16* dq; long long lddq;
     __nv_bfloat16* dk; long long lddk;
     __nv_bfloat16* dv; long long lddv;
@@ -50,14 +52,37 @@ struct AttnBwdArgs {
     float scale, scale_log2;
 };
 
-B200FM_DEVINL void store_row32_bf16(__nv_bfloat16* dst, const uint32_t (&a)[32]) {
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
+B200FM_DEVINL void pack32(const uint32_t (&a)[32], uint32_t (&p)[16]) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-        d4[q] = make_uint4(pack_bf16x2(__uint_as_float(a[8 * q]), __uint_as_float(a[8 * q + 1])),
-                           pack_bf16x2(__uint_as_float(a[8 * q + 2]), __uint_as_float(a[8 * q + 3])),
-                           pack_bf16x2(__uint_as_float(a[8 * q + 4]), __uint_as_float(a[8 * q + 5])),
-                           pack_bf16x2(__uint_as_float(a[8 * q + 6]), __uint_as_float(a[8 * q + 7])));
+    for (int j = 0; j < 16; ++j) p[j] = pack_bf16x2(__uint_as_float(a[2 * j]), __uint_as_float(a[2 * j + 1]));
+}
+
+// D[b, h, q] = sum_d dO[b, q, h, d] * O[b, q, h, d]: 8 lanes per (row, head), 16 B per lane, fully coalesced.
+__global__ void __launch_bounds__(256)
+attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ out, long long ldo, const __nv_bfloat16* __restrict__ dout, long long lddo,
+                     float* __restrict__ dsum, int B, int H, int Nq) {
+    const long long total = static_cast<long long>(B) * Nq * H;
+    const int sub = threadIdx.x & 7;
+    for (long long g = (blockIdx.x * 256ll + threadIdx.x) >> 3; g < total; g += (gridDim.x * 256ll) >> 3) {
+        const int h = static_cast<int>(g % H);
+        const long long row = g / H;                       // b * Nq + q
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(out + row * ldo + h * 64) + sub);
+        const uint4 d = __ldg(reinterpret_cast<const uint4*>(dout + row * lddo + h * 64) + sub);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
+        float acc = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 x = unpack_bf16x2(aw[e]), y = unpack_bf16x2(dw[e]);
+            acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if (sub == 0) {
+            const long long b = row / Nq, q = row % Nq;
+            dsum[(b * H + h) * Nq + q] = acc;
+        }
+    }
 }
 
 template <int NQT>
@@ -177,6 +202,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         uint8_t* sP = smem + SM::kP;
         uint8_t* sDS = smem + SM::kDS;
+        uint32_t* stg = reinterpret_cast<uint32_t*>(smem + SM::kStage) + warp * 512;
         uint32_t it = 0, kvc = 0, stepc = 0;
         for (int item = blockIdx.x; item < args.num_items; item += gridDim.x, ++it) {
             const int h = item % args.H, b = item / args.H;
@@ -187,22 +213,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 const int qrow = qt * 128 + r;
                 m_[qt] = 0.f; inv_[qt] = 0.f; D_[qt] = 0.f;
                 if (qrow < args.Nq) {
-                    const float2 st = reinterpret_cast<const float2*>(args.stats)[(static_cast<long long>(b) * args.H + h) * args.Nq + qrow];
+                    const long long si = (static_cast<long long>(b) * args.H + h) * args.Nq + qrow;
+                    const float2 st = reinterpret_cast<const float2*>(args.stats)[si];
                     m_[qt] = st.x; inv_[qt] = st.y;
-                    const uint4* po = reinterpret_cast<const uint4*>(args.out + (static_cast<long long>(b) * args.Nq + qrow) * args.ldo + h * 64);
-                    const uint4* pd = reinterpret_cast<const uint4*>(args.dout + (static_cast<long long>(b) * args.Nq + qrow) * args.lddo + h * 64);
-                    float acc = 0.f;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint4 a = __ldg(po + q), d = __ldg(pd + q);
-                        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 x = unpack_bf16x2(aw[e]), y = unpack_bf16x2(dw[e]);
-                            acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
-                        }
-                    }
-                    D_[qt] = acc;
+                    D_[qt] = __ldg(args.dsum + si);
                 }
             }
             for (int kt = 0; kt < nkt; ++kt, ++kvc) {
@@ -273,12 +287,15 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(dkv_free);
-                    if (key < args.Nk) {
-                        __nv_bfloat16* dst = (half == 0 ? args.dv + (static_cast<long long>(b) * args.Nk + key) * args.lddv
-                                                        : args.dk + (static_cast<long long>(b) * args.Nk + key) * args.lddk) + h * 64;
-                        store_row32_bf16(dst, a0);
-                        store_row32_bf16(dst + 32, a1);
-                    }
+                    (void)key;
+                    __nv_bfloat16* base = (half == 0 ? args.dv + static_cast<long long>(b) * args.Nk * args.lddv
+                                                     : args.dk + static_cast<long long>(b) * args.Nk * args.lddk) + h * 64;
+                    const long long ld = half == 0 ? args.lddv : args.lddk;
+                    uint32_t pk[16];
+                    pack32(a0, pk);
+                    attn_stage_store32(stg, lane, pk, base, ld, kt * 128 + quarter * 32, args.Nk);
+                    pack32(a1, pk);
+                    attn_stage_store32(stg, lane, pk, base + 32, ld, kt * 128 + quarter * 32, args.Nk);
                 }
             }
             mbar_wait(dq_full, it & 1);
@@ -288,8 +305,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                 uint32_t a0[32];
                 tmem_ld_x32(t_lane + kColDQ + qt * 64 + half * 32, a0);       // each half writes 32 of the 64 dQ columns
                 tmem_ld_wait();
-                const int qrow = qt * 128 + r;
-                if (qrow < args.Nq) store_row32_bf16(args.dq + (static_cast<long long>(b) * args.Nq + qrow) * args.lddq + h * 64 + half * 32, a0);
+                uint32_t pk[16];
+                pack32(a0, pk);
+                attn_stage_store32(stg, lane, pk, args.dq + static_cast<long long>(b) * args.Nq * args.lddq + h * 64 + half * 32, args.lddq,
+                                   qt * 128 + quarter * 32, args.Nq);
             }
             tc_fence_before();
             __syncwarp();
@@ -355,5 +374,16 @@ extern "C" int b200fm_attention_bwd(const void* q, long long ldq, const void* k,
     a.dv = reinterpret_cast<__nv_bfloat16*>(dv); a.lddv = lddv;
     a.B = B; a.H = H; a.Nq = Nq; a.Nk = Nk; a.nkt = (Nk + 127) / 128; a.num_items = B * H;
     a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
-    return Nq <= 128 ? launch_attn_bwd<1>(tq, tdo, tk, tv, a, stream) : launch_attn_bwd<2>(tq, tdo, tk, tv, a, stream);
+    float* dsum = nullptr;
+    B200FM_CUDA(cudaMallocAsync(&dsum, sizeof(float) * (size_t)B * H * Nq, stream));
+    a.dsum = dsum;
+    {
+        const long long groups = (long long)B * Nq * H;
+        long long blocks = (groups * 8 + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        attn_bwd_prep_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.out, ldo, a.dout, lddo, dsum, B, H, Nq);
+    }
+    rc = Nq <= 128 ? launch_attn_bwd<1>(tq, tdo, tk, tv, a, stream) : launch_attn_bwd<2>(tq, tdo, tk, tv, a, stream);
+    cudaFreeAsync(dsum, stream);
+    return rc;
 }

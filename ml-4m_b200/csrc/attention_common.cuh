@@ -40,4 +40,22 @@ B200FM_DEVINL uint32_t attn_mask_bits32(const uint8_t* mrow, int col0, int Nk) {
     return bits;
 }
 
+// Warp-private smem staging for bf16 row tiles (same scheme as the GEMM epilogue): the thread = row register layout coming out
+// of TMEM is turned into row-contiguous 64 B global segments.  stg: 32 rows x 16 packed words (2 KB), XOR-swizzled 16 B quads.
+B200FM_DEVINL void attn_stage_store32(uint32_t* stg, int lane, const uint32_t (&p)[16], __nv_bfloat16* base, long long ld, int row0,
+                                      int n_rows) {
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(stg + lane * 16 + 4 * (q ^ sw)) = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int rl = i * 8 + (lane >> 2), quad = lane & 3;
+        const uint4 w = *reinterpret_cast<const uint4*>(stg + rl * 16 + 4 * (quad ^ ((rl >> 1) & 3)));
+        if (row0 + rl < n_rows) *reinterpret_cast<uint4*>(base + static_cast<long long>(row0 + rl) * ld + quad * 8) = w;
+    }
+    __syncwarp();
+}
+
 }  // namespace b200fm

@@ -26,7 +26,8 @@ struct AttnFwdSmem {
     static constexpr int kV = kK + NKT * 16384;
     static constexpr int kP = kV + NKT * 16384;
     static constexpr int kBar = kP + NKT * 32768;        // P: [128 q][NKT*128 keys] bf16 = NKT x two 64-key swizzle atoms
-    static constexpr int kTotal = kBar + 128 + 1024;
+    static constexpr int kStage = kBar + 128;            // 4 warps x 2 KB store staging
+    static constexpr int kTotal = kStage + 4 * 2048 + 1024;
     static constexpr int kTmemCols = NKT == 1 ? 256 : 512;
     static constexpr int kOCol = NKT * 128;
 };
@@ -214,20 +215,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(o_empty);
-            if (row_ok) {
-                uint4* dst = reinterpret_cast<uint4*>(args.out + (static_cast<long long>(b) * args.Nq + qrow) * args.ldo + h * 64);
+            {
+                uint32_t* stg = reinterpret_cast<uint32_t*>(smem + SM::kStage) + warp * 512;
+                __nv_bfloat16* base = args.out + static_cast<long long>(b) * args.Nq * args.ldo + h * 64;
+                uint32_t pk[16];
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    dst[q] = make_uint4(pack_bf16x2(__uint_as_float(o0[8 * q]) * inv, __uint_as_float(o0[8 * q + 1]) * inv),
-                                        pack_bf16x2(__uint_as_float(o0[8 * q + 2]) * inv, __uint_as_float(o0[8 * q + 3]) * inv),
-                                        pack_bf16x2(__uint_as_float(o0[8 * q + 4]) * inv, __uint_as_float(o0[8 * q + 5]) * inv),
-                                        pack_bf16x2(__uint_as_float(o0[8 * q + 6]) * inv, __uint_as_float(o0[8 * q + 7]) * inv));
+                for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(o0[2 * j]) * inv, __uint_as_float(o0[2 * j + 1]) * inv);
+                attn_stage_store32(stg, lane, pk, base, args.ldo, qt * 128 + warp * 32, args.Nq);
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    dst[4 + q] = make_uint4(pack_bf16x2(__uint_as_float(o1[8 * q]) * inv, __uint_as_float(o1[8 * q + 1]) * inv),
-                                            pack_bf16x2(__uint_as_float(o1[8 * q + 2]) * inv, __uint_as_float(o1[8 * q + 3]) * inv),
-                                            pack_bf16x2(__uint_as_float(o1[8 * q + 4]) * inv, __uint_as_float(o1[8 * q + 5]) * inv),
-                                            pack_bf16x2(__uint_as_float(o1[8 * q + 6]) * inv, __uint_as_float(o1[8 * q + 7]) * inv));
+                for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(o1[2 * j]) * inv, __uint_as_float(o1[2 * j + 1]) * inv);
+                attn_stage_store32(stg, lane, pk, base + 32, args.ldo, qt * 128 + warp * 32, args.Nq);
             }
         }
     }
