@@ -70,15 +70,16 @@ int b200fm_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const f
  * (so q/k/v may alias one packed qkv buffer).  mask: uint8/bool, 1 = masked (reference convention), addressed as
  * mask[b*mask_b_stride + i*mask_q_stride + j]; NULL = no mask.  Masked scores are filled with -FLT_MAX-like
  * finite value (fully masked rows -> uniform attention, like masked_fill(-finfo.max)).
- * out bf16 [B*Nq, ldo]; lse fp32 [B, H, Nq] (saved for backward; natural log).  head_dim is fixed at 64.        */
+ * out bf16 [B*Nq, ldo]; lse ("stats") fp32 [B, H, Nq, 2] = (row max of s*scale*log2e, 1/rowsum), saved for backward.
+ * head_dim is fixed at 64.  attention_bwd needs dsum_ws: fp32 [B, H, Nq] scratch (receives rowsum(dO o O)).                  */
 int b200fm_attention_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                          const uint8_t* mask, long long mask_b_stride, long long mask_q_stride, void* out, long long ldo,
                          float* lse, int B, int H, int Nq, int Nk, float scale, void* stream);
 int b200fm_attention_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                          const uint8_t* mask, long long mask_b_stride, long long mask_q_stride, const void* out,
-                         long long ldo, const void* dout, long long lddo, const float* lse, void* dq, long long lddq,
-                         void* dk, long long lddk, void* dv, long long lddv, int B, int H, int Nq, int Nk, float scale,
-                         void* stream);
+                         long long ldo, const void* dout, long long lddo, const float* lse, float* dsum_ws, void* dq,
+                         long long lddq, void* dk, long long lddk, void* dv, long long lddv, int B, int H, int Nq, int Nk,
+                         float scale, void* stream);
 
 /* ---- element-wise / row-wise kernels around the GEMMs -------------------------------------------------------
  * swiglu_bwd: fm_utils.py:143 backward. ab bf16 [R,2H] = [a|b] saved by EPI_SWIGLU, dg bf16 [R,H] -> dab bf16 [R,2H].   */

@@ -35,7 +35,8 @@ SIGNATURES = {
     "b200fm_attention_fwd": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_void_p,
                              c_int, c_int, c_int, c_int, c_float, c_void_p],
     "b200fm_attention_bwd": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_void_p, c_ll,
-                             c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_float, c_void_p],
+                             c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_float,
+                             c_void_p],
     "b200fm_swiglu_bwd": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p],
     "b200fm_act_bwd": [c_int, c_void_p, c_void_p, c_void_p, c_ll, c_void_p],
     "b200fm_cross_entropy": [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_int, c_void_p],

@@ -179,9 +179,10 @@ def attention_bwd(q, k, v, out, dout, stats, B, H, Nq, Nk, mask=None, scale=None
     dk = torch.empty(B * Nk, H * 64, device=dev, dtype=torch.bfloat16) if dk is None else dk
     dv = torch.empty(B * Nk, H * 64, device=dev, dtype=torch.bfloat16) if dv is None else dv
     mk, mp, mbs, mqs = _mask_args(mask, B, Nq, Nk)
+    dsum = torch.empty(B, H, Nq, device=dev, dtype=torch.float32)
     lib.call("b200fm_attention_bwd", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), mp, mbs, mqs, _ptr(out),
-             out.stride(0), _ptr(dout), dout.stride(0), _ptr(stats), _ptr(dq), dq.stride(0), _ptr(dk), dk.stride(0), _ptr(dv),
-             dv.stride(0), B, H, Nq, Nk, float(scale), _stream())
+             out.stride(0), _ptr(dout), dout.stride(0), _ptr(stats), _ptr(dsum), _ptr(dq), dq.stride(0), _ptr(dk), dk.stride(0),
+             _ptr(dv), dv.stride(0), B, H, Nq, Nk, float(scale), _stream())
     return dq, dk, dv
 
 

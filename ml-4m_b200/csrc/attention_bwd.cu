@@ -349,9 +349,9 @@ using namespace b200fm;
 
 extern "C" int b200fm_attention_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                                     const uint8_t* mask, long long mask_b_stride, long long mask_q_stride, const void* out,
-                                    long long ldo, const void* dout, long long lddo, const float* stats, void* dq, long long lddq,
-                                    void* dk, long long lddk, void* dv, long long lddv, int B, int H, int Nq, int Nk, float scale,
-                                    void* stream_) {
+                                    long long ldo, const void* dout, long long lddo, const float* stats, float* dsum_ws, void* dq,
+                                    long long lddq, void* dk, long long lddk, void* dv, long long lddv, int B, int H, int Nq, int Nk,
+                                    float scale, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (B == 0 || H == 0 || Nq == 0) return 0;
     B200FM_CHECK(q && k && v && out && dout && stats && dq && dk && dv, "attention_bwd: null pointer");
@@ -374,8 +374,8 @@ extern "C" int b200fm_attention_bwd(const void* q, long long ldq, const void* k,
     a.dv = reinterpret_cast<__nv_bfloat16*>(dv); a.lddv = lddv;
     a.B = B; a.H = H; a.Nq = Nq; a.Nk = Nk; a.nkt = (Nk + 127) / 128; a.num_items = B * H;
     a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
-    float* dsum = nullptr;
-    B200FM_CUDA(cudaMallocAsync(&dsum, sizeof(float) * (size_t)B * H * Nq, stream));
+    B200FM_CHECK(dsum_ws != nullptr, "attention_bwd: dsum_ws (fp32 [B, H, Nq] workspace) is required");
+    float* dsum = dsum_ws;
     a.dsum = dsum;
     {
         const long long groups = (long long)B * Nq * H;
@@ -383,7 +383,5 @@ extern "C" int b200fm_attention_bwd(const void* q, long long ldq, const void* k,
         if (blocks > 148 * 16) blocks = 148 * 16;
         attn_bwd_prep_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.out, ldo, a.dout, lddo, dsum, B, H, Nq);
     }
-    rc = Nq <= 128 ? launch_attn_bwd<1>(tq, tdo, tk, tv, a, stream) : launch_attn_bwd<2>(tq, tdo, tk, tv, a, stream);
-    cudaFreeAsync(dsum, stream);
-    return rc;
+    return Nq <= 128 ? launch_attn_bwd<1>(tq, tdo, tk, tv, a, stream) : launch_attn_bwd<2>(tq, tdo, tk, tv, a, stream);
 }
