@@ -5,6 +5,8 @@ LayerNorm statistics are fp32 and its output is consumed as bf16; every Linear /
 operands with fp32 accumulation and produces bf16; weight gradients are produced in fp32 directly (the reference rounds
 them to bf16 first).  Master weights stay fp32 `nn.Parameter`s; their bf16 shadows are cached per parameter version.
 """
+import weakref
+
 import torch
 
 from . import ops
@@ -26,7 +28,7 @@ def weight_bf16(*params):
     key = tuple(id(p) for p in params)
     ver = tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)
     hit = _shadow.get(key)
-    if hit is not None and hit[0] == ver:
+    if hit is not None and hit[0] == ver and all(r() is p for r, p in zip(hit[2], params)):     # id() may be recycled: check identity
         return hit[1]
     with torch.no_grad():
         rows = [p.shape[0] for p in params]
@@ -42,11 +44,13 @@ def weight_bf16(*params):
                 src = src.float().contiguous()
             view = buf[off:off + r]
             ops.cast_bf16(src, view)
-            views = _shadow_views.setdefault(id(p), [])
-            if not any(v.data_ptr() == view.data_ptr() for v in views):
-                views.append(view)
+            ent = _shadow_views.get(id(p))
+            if ent is None or ent[0]() is not p:
+                ent = _shadow_views[id(p)] = (weakref.ref(p), [])
+            if not any(v.data_ptr() == view.data_ptr() for v in ent[1]):
+                ent[1].append(view)
             off += pr
-    _shadow[key] = (ver, buf)
+    _shadow[key] = (ver, buf, tuple(weakref.ref(p) for p in params))
     return buf
 
 
@@ -56,18 +60,19 @@ def weight_bf16_padk(param, k_pad):
     key = (id(param), "padk", k_pad)
     ver = (param._version, param.data_ptr())
     hit = _shadow.get(key)
-    if hit is not None and hit[0] == ver:
+    if hit is not None and hit[0] == ver and hit[2]() is param:
         return hit[1]
     with torch.no_grad():
         buf = hit[1] if hit is not None else torch.zeros(param.shape[0], k_pad, device=param.device, dtype=torch.bfloat16)
         buf[:, :param.shape[1]].copy_(param.detach())
-    _shadow[key] = (ver, buf)
+    _shadow[key] = (ver, buf, weakref.ref(param))
     return buf
 
 
 def shadow_views(param):
     """bf16 mirrors of `param` currently cached (the fused AdamW kernel writes the first one itself)."""
-    return _shadow_views.get(id(param), [])
+    ent = _shadow_views.get(id(param))
+    return ent[1] if ent is not None and ent[0]() is param else []
 
 
 def clear_weight_cache():

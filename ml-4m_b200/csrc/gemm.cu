@@ -128,7 +128,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int lane = threadIdx.x & 31;
     const int num_m_units = (args.num_m_blocks + cta_stride - 1) / cta_stride;      // CTA2: pairs of 128-row blocks
     const int num_mn = num_m_units * args.num_n_blocks;
-    const int num_tiles = num_mn * args.k_splits;               // work items: (k slice, n block, m unit), m fastest
+    const int num_tiles = num_mn * args.k_splits;               // work items: (k slice, m unit, n block), n fastest
     const int num_kb_total = (args.K + kBK - 1) / kBK;
 
     if (warp == kEpiWarps) {
@@ -153,8 +153,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             int stage = 0; uint32_t phase = 0;
             for (int tile = my_first; tile < num_tiles; tile += my_step) {
                 const int mn = tile % num_mn, ks = tile / num_mn;
-                const int m_blk = (mn % num_m_units) * cta_stride + static_cast<int>(rank);
-                const int n_blk = mn / num_m_units;
+                const int m_blk = (mn / args.num_n_blocks) * cta_stride + static_cast<int>(rank);   // n fastest: concurrent CTAs share the A rows,
+                const int n_blk = mn % args.num_n_blocks;                                           // B (weights) stays L2-resident -> A streams from HBM once
                 const int m0 = m_blk * kBM;
                 const int n0 = (EPI == B200FM_EPI_SWIGLU) ? n_blk * (BN / 2) : n_blk * BN;
                 const int kb_begin = ks * args.kb_per_split;
@@ -254,8 +254,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const uint32_t tempty_leader1 = CTA2 ? mapa_u32(&tempty_bar[1], 0) : 0u;
         for (int tile = my_first; tile < num_tiles; tile += my_step) {
             const int mn = tile % num_mn;
-            const int m_blk = (mn % num_m_units) * cta_stride + static_cast<int>(rank);
-            const int n_blk = mn / num_m_units;
+            const int m_blk = (mn / args.num_n_blocks) * cta_stride + static_cast<int>(rank);
+            const int n_blk = mn % args.num_n_blocks;
             const int row_base = m_blk * kBM + quarter * 32;            // first of this warp's 32 rows
             const int row = row_base + lane;
             const bool row_ok = row < args.M;
