@@ -84,11 +84,18 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------------
 # the reference algorithm on the host CPU (oracle port): cpu_baseline leg and `--impl reference`
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_reference_steps(steps, warmup, sample_B, n_tok):
-    """Times fwd+bwd of the oracle restatement of FourM.forward (4M-B mod7, fp32, all host threads)."""
+def cpu_threads():
+    """Threads for the CPU arm: every hardware thread up to 32.  (Measured on the GPU box -- 2 x Xeon 8562Y+, 128 hardware
+    threads: 128 torch threads are ~8x SLOWER than 32 on these small fp32 GEMMs)"""
+    env = os.environ.get("B200FM_CPU_THREADS")
+    return int(env) if env else min(os.cpu_count() or 1, 32)
+
+
+def cpu_reference_steps(steps, warmup, sample_B, n_tok, threads=None):
+    """Times fwd+bwd of the oracle restatement of FourM.forward (4M-B mod7, fp32, host threads per cpu_threads())."""
     import random
     from oracle import fourm_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(threads or cpu_threads())
     specs = O.mod7_specs()
     cfg = O.PRESETS[MODEL]
     g = torch.Generator().manual_seed(0)
@@ -146,7 +153,7 @@ def cpu_reference_steps(steps, warmup, sample_B, n_tok):
         if it >= warmup:
             times.append(dt)
     tok = sample_B * 2 * n_tok
-    return tok / (sum(times) / len(times)), sum(times) / len(times), os.cpu_count() or 1
+    return tok / (sum(times) / len(times)), sum(times) / len(times), torch.get_num_threads()
 
 
 def run_reference_arm(args):
@@ -154,7 +161,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     n_tok = 128
-    B = 4
+    B = 8
     tps, sec, cores = cpu_reference_steps(args.steps, args.warmup, B, n_tok)
     line = dict(metric="tokens_per_sec", value=tps, unit="tokens/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
@@ -162,7 +169,7 @@ def run_reference_arm(args):
                 config=dict(workload="4M-B mod7 train step fwd+bwd (oracle port of FourM.forward on host CPU, fp32)", model=MODEL,
                             global_batch=B, seq_len=2 * n_tok, parallelism="cpu"),
                 cpu_baseline=dict(value=tps, unit="tokens/s", cores=cores, kind="port",
-                                  sample=f"fwd+bwd of B={B} samples x {2 * n_tok} tokens per step, fp32, torch CPU {torch.get_num_threads()} threads"),
+                                  sample=f"fwd+bwd of B={B} samples x {2 * n_tok} tokens per step, fp32, torch CPU {cores} threads of {os.cpu_count()}"),
                 e2e=dict(value=tps, unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
 
@@ -291,9 +298,9 @@ def run_b200_arm(args):
         model_tflops = 3 * total * B * world / (ms / args.steps / 1e3) / 1e12
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            v, sec, cores = cpu_reference_steps(2, 1, 4, n_tok)
+            v, sec, cores = cpu_reference_steps(2, 1, 8, n_tok)
             cpu = dict(value=v, unit="tokens/s", cores=cores, kind="port",
-                       sample=f"2 timed fwd+bwd steps of B=4 x {2 * n_tok} tokens, oracle port of FourM.forward, fp32, {torch.get_num_threads()} threads")
+                       sample=f"2 timed fwd+bwd steps (1 warm-up) of B=8 x {2 * n_tok} tokens, oracle port of FourM.forward, fp32, {cores} threads of {os.cpu_count()}")
         line = dict(metric="tokens_per_sec", value=tps, unit="tokens/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                     config=dict(workload="4M-B mod7 full train step (fwd+bwd+DDP all-reduce+AdamW), BASELINE.json configs[1]",
