@@ -85,10 +85,9 @@ class ClockSampler:
 # the reference algorithm on the host CPU (oracle port): cpu_baseline leg and `--impl reference`
 # ----------------------------------------------------------------------------------------------------------------------
 def cpu_threads():
-    """Threads for the CPU arm: every hardware thread up to 32.  (Measured on the GPU box -- 2 x Xeon 8562Y+, 128 hardware
-    threads: 128 torch threads are ~8x SLOWER than 32 on these small fp32 GEMMs)"""
+    """Thread count for the CPU arm when not auto-tuned (B200FM_CPU_THREADS overrides)."""
     env = os.environ.get("B200FM_CPU_THREADS")
-    return int(env) if env else min(os.cpu_count() or 1, 32)
+    return int(env) if env else min(os.cpu_count() or 1, 16)
 
 
 def cpu_reference_steps(steps, warmup, sample_B, n_tok, threads=None):
@@ -140,6 +139,30 @@ def cpu_reference_steps(steps, warmup, sample_B, n_tok, threads=None):
     batch = O.synthetic_mod7_batch(sample_B, a, b, c, d, seed=1234)
     dec_names = [m for m, s in specs.items() if s["kind"] != "img"]
     leaves = [t for t in {id(v): v for v in sd.values()}.values() if t.requires_grad]
+
+    def one(it):
+        random.seed(it)
+        order = random.sample(dec_names, len(dec_names))
+        t0 = time.perf_counter()
+        loss, _ = O.fourm_forward(sd, cfg, specs, batch, n_tok, n_tok, order)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        for t in leaves:
+            t.grad = None
+        return dt
+
+    if threads is None and not os.environ.get("B200FM_CPU_THREADS"):
+        # the reference gets the thread count that serves it best on this host: on the GPU box (128 hardware threads) 16 torch
+        # threads are ~3x faster than 64 and ~25x faster than 128 for these fp32 sizes (measured, profiles/README.md)
+        ncpu = os.cpu_count() or 1
+        best = None
+        one(0)                                           # first-touch / allocator warm-up
+        for cand in sorted({min(ncpu, c) for c in (8, 16, 32, 64)}):
+            torch.set_num_threads(cand)
+            dt = one(0)
+            if best is None or dt < best[0]:
+                best = (dt, cand)
+        torch.set_num_threads(best[1])
     times = []
     for it in range(warmup + steps):
         random.seed(it)
