@@ -102,6 +102,22 @@ int b200fm_patchify(const float* img, void* out, int B, int C, int H, int W, int
 int b200fm_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr, float beta1,
                  float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
+/* Multi-tensor form: ONE launch for all tensors of a param group (same lr / weight decay / step).  table_dev: device array of
+ * per-tensor pointers; chunk_tensor_dev / chunk_offset_dev (device, n_chunks entries) assign b200fm_adamw_chunk_elems()
+ * consecutive elements of one tensor to each CTA.                                                                          */
+typedef struct b200fm_adamw_tensor {
+    float* p;            /* fp32 master weight, updated in place */
+    const float* g;      /* fp32 gradient                        */
+    float* m;            /* exp_avg                               */
+    float* v;            /* exp_avg_sq                            */
+    void* shadow_bf16;   /* optional bf16 mirror of p (refreshed) */
+    long long n;         /* elements                              */
+} b200fm_adamw_tensor;
+int b200fm_adamw_multi(const b200fm_adamw_tensor* table_dev, const int* chunk_tensor_dev, const long long* chunk_offset_dev,
+                       int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                       void* stream);
+int b200fm_adamw_chunk_elems(void);
+
 /* ---- modality-masked token selection + embedding gather / scatter ------------------------------------------------
  * Replaces cat_{encoder,decoder}_tensors + forward_mask_{encoder,decoder} + adapt_decoder_attention_mask
  * (fourm/models/fm.py:245-475) and the embedding module forwards (fourm/models/encoder_embeddings.py:87-121, 184-211,

@@ -1,16 +1,52 @@
-"""Fused AdamW on the b200fm kernel (one launch per parameter tensor: read p,g,m,v / write p,m,v in a single pass).
+"""Fused AdamW on the b200fm kernels.
 
 Same update rule and defaults as torch.optim.AdamW as configured by the reference (fourm/utils/optim_factory.py:239-240:
-betas (0.9, 0.95), weight decay 0.05 with no decay on norm / bias / 1-D tensors via param groups)."""
+betas (0.9, 0.95), weight decay 0.05 with no decay on norm / bias / 1-D tensors via param groups).  One multi-tensor launch
+per param group: read p, g, m, v / write p, m, v (+ the bf16 weight shadow the GEMMs consume) in a single pass."""
+import numpy as np
 import torch
 
 from . import functional as BF
-from . import ops
+from . import lib, ops
 
 
 class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._chunk = None
+        self._tables = {}       # group index -> dict(device table, chunk maps, pinned staging ring)
+
+    def _group_tables(self, gi, tensors):
+        """Device-side pointer table + CTA->chunk maps for one param group.  The chunk maps depend on the tensor sizes only
+        (built once); the pointer table is re-uploaded when a pointer moved (set_to_none gradients are re-allocated every
+        step) through a small ring of pinned staging buffers, each guarded by the event of its last upload."""
+        if self._chunk is None:
+            self._chunk = lib.load().b200fm_adamw_chunk_elems()
+        tab = np.array(tensors, dtype=np.int64)                       # [n_t, 6]: p, g, m, v, shadow, n
+        ent = self._tables.get(gi)
+        sizes = tab[:, 5]
+        if ent is None or ent["sizes"].shape != sizes.shape or not np.array_equal(ent["sizes"], sizes):
+            dev = torch.device("cuda", torch.cuda.current_device())
+            n_chunks = (sizes + self._chunk - 1) // self._chunk
+            ct = np.repeat(np.arange(len(sizes), dtype=np.int32), n_chunks)
+            starts = np.cumsum(n_chunks) - n_chunks
+            co = (np.arange(int(n_chunks.sum()), dtype=np.int64) - np.repeat(starts, n_chunks)) * self._chunk
+            ent = dict(sizes=sizes.copy(), ct=torch.from_numpy(ct).to(dev), co=torch.from_numpy(co).to(dev), n_chunks=int(n_chunks.sum()),
+                       table=torch.empty(tab.shape, dtype=torch.int64, device=dev), last=None, ring=[], slot=0)
+            for _ in range(4):
+                ent["ring"].append([torch.empty(tab.shape, dtype=torch.int64).pin_memory(), None])
+            self._tables[gi] = ent
+        if ent["last"] is None or not np.array_equal(ent["last"], tab):
+            host, ev = ent["ring"][ent["slot"]]
+            if ev is not None:
+                ev.synchronize()                                      # four uploads ago: long done
+            host.numpy()[...] = tab
+            ent["table"].copy_(host, non_blocking=True)
+            ev = ent["ring"][ent["slot"]][1] = ev if ev is not None else torch.cuda.Event()
+            ev.record()
+            ent["slot"] = (ent["slot"] + 1) % 4
+            ent["last"] = tab
+        return ent
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
@@ -18,8 +54,9 @@ class FusedAdamW(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        for group in self.param_groups:
+        for gi, group in enumerate(self.param_groups):
             b1, b2 = group["betas"]
+            tensors, extra_casts, step_no = [], [], None
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -29,14 +66,31 @@ class FusedAdamW(torch.optim.Optimizer):
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["step"] += 1
+                if step_no is None:
+                    step_no = st["step"]
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                if g is not p.grad:
+                    st["_g_keepalive"] = g
+                if st["step"] != step_no or g.dtype != torch.float32 or p.dtype != torch.float32:
+                    # stragglers (different step count / dtype): single-tensor kernel
+                    views = BF.shadow_views(p)
+                    ops.adamw_step(p.data, g.float(), st["exp_avg"], st["exp_avg_sq"], group["lr"], b1, b2, group["eps"],
+                                   group["weight_decay"], st["step"], grad_scale, shadow=views[0] if views else None)
+                    extra_casts += [(p, v) for v in views[1:]]
+                    continue
                 views = BF.shadow_views(p)
-                ops.adamw_step(p.data, g, st["exp_avg"], st["exp_avg_sq"], group["lr"], b1, b2, group["eps"], group["weight_decay"],
-                               st["step"], grad_scale, shadow=views[0] if views else None)
-                for extra in views[1:]:          # a weight mirrored in more than one operand buffer
-                    ops.cast_bf16(p.data, extra)
-                # the kernel writes through raw pointers: p._version is unchanged and the mirrors were refreshed in the same
-                # pass, so the bf16 weight cache stays valid without a re-cast.
+                tensors.append((p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
+                                views[0].data_ptr() if views else 0, p.numel()))
+                extra_casts += [(p, v) for v in views[1:]]
+            if tensors:
+                ent = self._group_tables(gi, tensors)
+                lib.call("b200fm_adamw_multi", ent["table"].data_ptr(), ent["ct"].data_ptr(), ent["co"].data_ptr(), ent["n_chunks"], float(group["lr"]),
+                         float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), int(step_no), float(grad_scale),
+                         ops._stream())
+            for p, view in extra_casts:          # a weight mirrored in more than one operand buffer
+                ops.cast_bf16(p.data, view)
+            # the kernels write through raw pointers: p._version is unchanged and the bf16 mirrors were refreshed in the same
+            # pass, so the weight cache stays valid without a re-cast.
         return loss
 
 

@@ -61,6 +61,7 @@ B200FM_DEVINL void pack32(const uint32_t (&a)[32], uint32_t (&p)[16]) {
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ out, long long ldo, const __nv_bfloat16* __restrict__ dout, long long lddo,
                      float* __restrict__ dsum, int B, int H, int Nq) {
+    pdl_enter();
     const long long total = static_cast<long long>(B) * Nq * H;
     const int sub = threadIdx.x & 7;
     for (long long g = (blockIdx.x * 256ll + threadIdx.x) >> 3; g < total; g += (gridDim.x * 256ll) >> 3) {
@@ -122,6 +123,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();      // TMEM is held: a dependent grid can no longer starve this one of columns
+    pdl_wait();         // everything below touches global memory
 
     if (warp == kBwdMathWarps) {
         // ------------------------------ TMA producer: runs ahead of the MMAs by one buffer ------------------------------
@@ -338,7 +341,7 @@ static int launch_attn_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = a.num_items < sms ? a.num_items : sms;
-    kern<<<grid, kBwdThreads, smem, stream>>>(tq, tdo, tk, tv, a);
+    B200FM_LAUNCH(kern, dim3(grid), dim3(kBwdThreads), smem, stream, 1, tq, tdo, tk, tv, a);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -381,7 +384,7 @@ extern "C" int b200fm_attention_bwd(const void* q, long long ldq, const void* k,
         const long long groups = (long long)B * Nq * H;
         long long blocks = (groups * 8 + 255) / 256;
         if (blocks > 148 * 16) blocks = 148 * 16;
-        attn_bwd_prep_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.out, ldo, a.dout, lddo, dsum, B, H, Nq);
+        B200FM_LAUNCH(attn_bwd_prep_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, 1, a.out, ldo, a.dout, lddo, dsum, B, H, Nq);
     }
     return Nq <= 128 ? launch_attn_bwd<1>(tq, tdo, tk, tv, a, stream) : launch_attn_bwd<2>(tq, tdo, tk, tv, a, stream);
 }

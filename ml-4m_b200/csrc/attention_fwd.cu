@@ -76,6 +76,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();      // TMEM is held: a dependent grid can no longer starve this one of columns
+    pdl_wait();         // everything below touches global memory
     const int nk_steps = (args.Nk + 15) / 16;          // 16-key MMA steps actually needed for P V
 
     if (warp == 4) {
@@ -252,7 +254,7 @@ static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const C
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int cap = sms * (NKT == 1 ? 2 : 1);
     const int grid = a.num_items < cap ? a.num_items : cap;
-    kern<<<grid, 192, smem, stream>>>(tq, tk, tv, a);
+    B200FM_LAUNCH(kern, dim3(grid), dim3(192), smem, stream, 1, tq, tk, tv, a);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }

@@ -13,6 +13,42 @@ namespace b200fm {
 #define B200FM_DEVINL __device__ __forceinline__
 
 // ------------------------------------------------------------------------------------------------------------
+// programmatic dependent launch: every kernel of the library is launched with programmatic stream serialisation, lets
+// the next kernel in the stream start its prologue (pdl_trigger, first instruction) and orders ALL of its own global
+// memory traffic after the previous grid (pdl_wait: every CTA executes it, before its first global access).  A kernel
+// that skipped pdl_wait could finish before its predecessor and break the chain for the kernel after it.
+// ------------------------------------------------------------------------------------------------------------
+B200FM_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+B200FM_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+B200FM_DEVINL void pdl_enter() { pdl_trigger(); pdl_wait(); }
+bool pdl_enabled();      // runtime.cu: env B200FM_PDL (default 1)
+#define B200FM_LAUNCH(...) (void)::b200fm::launch_pdl(__VA_ARGS__)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (cluster_x > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // error reporting for the C ABI (thread-local last-error string; entry points return cudaError_t-like ints)
 // ------------------------------------------------------------------------------------------------------------
 void set_last_error(const char* fmt, ...);

@@ -30,6 +30,7 @@ static int ew_grid(long long work_items, int threads) {
 __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ ab, const __nv_bfloat16* __restrict__ dg,
                                   __nv_bfloat16* __restrict__ dab, long long R, int H, long long ld_ab, long long ld_dg,
                                   long long ld_dab) {
+    pdl_enter();
     const int hv = H / 8;
     const long long total = R * hv;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -56,6 +57,7 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ ab, const __
 template <int ACT>   // 0 = GELU (erf), 1 = tanh
 __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dact,
                                __nv_bfloat16* __restrict__ dpre, long long n8) {
+    pdl_enter();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
         const uint4 pv = reinterpret_cast<const uint4*>(pre)[i], gv = reinterpret_cast<const uint4*>(dact)[i];
         const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
@@ -83,6 +85,7 @@ __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv
 __global__ void __launch_bounds__(256)
 cross_entropy_kernel(const float* __restrict__ logits, long long ld, const int64_t* __restrict__ targets,
                      float* __restrict__ loss_rows, __nv_bfloat16* __restrict__ dlogits, long long ldd, int V) {
+    pdl_enter();
     __shared__ float red[8];
     __shared__ float bc;
     const long long row = blockIdx.x;
@@ -125,6 +128,7 @@ cross_entropy_kernel(const float* __restrict__ logits, long long ld, const int64
 // ---- column sums (bias gradients): out[c] += sum_r x[r, c], x bf16 [R, N] ------------------------------------------
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restrict__ out, long long R, int N, int rows_per_block) {
+    pdl_enter();
     const int c = blockIdx.x * 256 + threadIdx.x;
     const long long r0 = (long long)blockIdx.y * rows_per_block;
     if (c >= N) return;
@@ -136,6 +140,7 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __r
 
 // ---- fp32 -> bf16 cast (weight shadows; also activations) ----------------------------------------------------------
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+    pdl_enter();
     const long long n4 = n / 4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -146,6 +151,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
 
 // ---- patchify (encoder_embeddings.py:301): img fp32 [B,C,H,W] -> bf16 [B*nh*nw, ph*pw*C] in '(ph pw c)' order ------
 __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int C, int Himg, int Wimg, int P) {
+    pdl_enter();
     const int nh = Himg / P, nw = Wimg / P;
     const long long total = (long long)B * nh * nw * P * P * C;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -164,6 +170,7 @@ __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              __nv_bfloat16* __restrict__ shadow, long long n, float lr, float beta1, float beta2, float eps,
                              float wd, float bc1, float bc2_sqrt, float grad_scale) {
+    pdl_enter();
     const float decay = 1.0f - lr * wd, step = lr / bc1, ob1 = 1.0f - beta1, ob2 = 1.0f - beta2;
     const long long n4 = n >> 2;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -190,9 +197,77 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     }
 }
 
+// ---- multi-tensor AdamW: one launch for every parameter tensor of a param group --------------------------------------
+// table: one b200fm_adamw_tensor per tensor; chunk_tensor / chunk_offset map each CTA to (tensor, first element).
+constexpr int kMtChunk = 8192;      // elements per CTA (256 threads x 8 float4)
+__global__ void __launch_bounds__(256)
+adamw_multi_kernel(const b200fm_adamw_tensor* __restrict__ table, const int* __restrict__ chunk_tensor,
+                   const long long* __restrict__ chunk_offset, float lr, float beta1, float beta2, float eps, float wd, float bc1,
+                   float bc2_sqrt, float grad_scale) {
+    pdl_enter();
+    const b200fm_adamw_tensor t = table[chunk_tensor[blockIdx.x]];
+    const long long off = chunk_offset[blockIdx.x];
+    const long long end = off + kMtChunk < t.n ? off + kMtChunk : t.n;
+    float* p = t.p; const float* g = t.g; float* m = t.m; float* v = t.v;
+    __nv_bfloat16* shadow = reinterpret_cast<__nv_bfloat16*>(t.shadow_bf16);
+    const float decay = 1.0f - lr * wd, step = lr / bc1, ob1 = 1.0f - beta1, ob2 = 1.0f - beta2;
+    const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
+                     (shadow == nullptr || (reinterpret_cast<uintptr_t>(shadow) & 7) == 0);
+    if (vec) {
+        const long long e4 = off + ((end - off) & ~3ll);
+        for (long long i = off + threadIdx.x * 4ll; i < e4; i += 1024) {
+            const float4 g4 = *reinterpret_cast<const float4*>(g + i);
+            float4 p4 = *reinterpret_cast<float4*>(p + i), m4 = *reinterpret_cast<float4*>(m + i), v4 = *reinterpret_cast<float4*>(v + i);
+            float* pp = &p4.x; float* mm = &m4.x; float* vv = &v4.x; const float* gg = &g4.x;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float gi = gg[e] * grad_scale;
+                mm[e] = beta1 * mm[e] + ob1 * gi;
+                vv[e] = beta2 * vv[e] + ob2 * gi * gi;
+                pp[e] = pp[e] * decay - step * (mm[e] / (sqrtf(vv[e]) / bc2_sqrt + eps));
+            }
+            *reinterpret_cast<float4*>(p + i) = p4; *reinterpret_cast<float4*>(m + i) = m4; *reinterpret_cast<float4*>(v + i) = v4;
+            if (shadow) *reinterpret_cast<uint2*>(shadow + i) = make_uint2(pack_bf16x2(p4.x, p4.y), pack_bf16x2(p4.z, p4.w));
+        }
+        for (long long i = e4 + threadIdx.x; i < end; i += 256) {
+            const float gi = g[i] * grad_scale;
+            const float mi = beta1 * m[i] + ob1 * gi, vi = beta2 * v[i] + ob2 * gi * gi;
+            const float pi = p[i] * decay - step * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+            p[i] = pi; m[i] = mi; v[i] = vi;
+            if (shadow) shadow[i] = __float2bfloat16_rn(pi);
+        }
+    } else {
+        for (long long i = off + threadIdx.x; i < end; i += 256) {
+            const float gi = g[i] * grad_scale;
+            const float mi = beta1 * m[i] + ob1 * gi, vi = beta2 * v[i] + ob2 * gi * gi;
+            const float pi = p[i] * decay - step * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+            p[i] = pi; m[i] = mi; v[i] = vi;
+            if (shadow) shadow[i] = __float2bfloat16_rn(pi);
+        }
+    }
+}
+
 }  // namespace b200fm
 
 using namespace b200fm;
+
+extern "C" int b200fm_adamw_multi(const b200fm_adamw_tensor* table_dev, const int* chunk_tensor_dev, const long long* chunk_offset_dev,
+                                  int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                                  float grad_scale, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (n_chunks == 0) return 0;
+    B200FM_CHECK(table_dev && chunk_tensor_dev && chunk_offset_dev, "adamw_multi: null pointer");
+    B200FM_CHECK(step >= 1, "adamw_multi: step must be >= 1");
+    const float bc1 = 1.0f - powf(beta1, (float)step);
+    const float bc2s = sqrtf(1.0f - powf(beta2, (float)step));
+    B200FM_LAUNCH(adamw_multi_kernel, dim3(n_chunks), dim3(256), 0, stream, 1, table_dev, chunk_tensor_dev, chunk_offset_dev, lr, beta1, beta2, eps, weight_decay, bc1,
+                                                   bc2s, grad_scale);
+    B200FM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200fm_adamw_chunk_elems(void) { return kMtChunk; }
+
 
 extern "C" int b200fm_swiglu_bwd(const void* ab, long long ld_ab, const void* dg, long long ld_dg, void* dab, long long ld_dab,
                                  long long R, int H, void* stream_) {
@@ -200,7 +275,7 @@ extern "C" int b200fm_swiglu_bwd(const void* ab, long long ld_ab, const void* dg
     if (R == 0) return 0;
     B200FM_CHECK(ab && dg && dab, "swiglu_bwd: null pointer");
     B200FM_CHECK(H % 8 == 0 && ld_ab % 8 == 0 && ld_dg % 8 == 0 && ld_dab % 8 == 0, "swiglu_bwd: H and strides must be multiples of 8");
-    swiglu_bwd_kernel<<<ew_grid(R * (H / 8), 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(ab), reinterpret_cast<const __nv_bfloat16*>(dg),
+    B200FM_LAUNCH(swiglu_bwd_kernel, dim3(ew_grid(R * (H / 8), 256)), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(ab), reinterpret_cast<const __nv_bfloat16*>(dg),
                                                                   reinterpret_cast<__nv_bfloat16*>(dab), R, H, ld_ab, ld_dg, ld_dab);
     B200FM_CUDA(cudaGetLastError());
     return 0;
@@ -213,8 +288,8 @@ extern "C" int b200fm_act_bwd(int act, const void* pre, const void* dact, void* 
     B200FM_CHECK(n % 8 == 0, "act_bwd: element count must be a multiple of 8");
     B200FM_CHECK(act == 0 || act == 1, "act_bwd: act must be 0 (gelu) or 1 (tanh)");
     const int grid = ew_grid(n / 8, 256);
-    if (act == 0) act_bwd_kernel<0><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(pre), reinterpret_cast<const __nv_bfloat16*>(dact), reinterpret_cast<__nv_bfloat16*>(dpre), n / 8);
-    else act_bwd_kernel<1><<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(pre), reinterpret_cast<const __nv_bfloat16*>(dact), reinterpret_cast<__nv_bfloat16*>(dpre), n / 8);
+    if (act == 0) B200FM_LAUNCH((act_bwd_kernel<0>), dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(pre), reinterpret_cast<const __nv_bfloat16*>(dact), reinterpret_cast<__nv_bfloat16*>(dpre), n / 8);
+    else B200FM_LAUNCH((act_bwd_kernel<1>), dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(pre), reinterpret_cast<const __nv_bfloat16*>(dact), reinterpret_cast<__nv_bfloat16*>(dpre), n / 8);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -225,7 +300,7 @@ extern "C" int b200fm_cross_entropy(const float* logits, long long ld, const int
     if (n == 0) return 0;
     B200FM_CHECK(logits && targets && loss_rows, "cross_entropy: null pointer");
     B200FM_CHECK(V > 0 && (dlogits == nullptr || ldd % 2 == 0), "cross_entropy: bad V / dlogits stride");
-    cross_entropy_kernel<<<(unsigned)n, 256, 0, stream>>>(logits, ld, targets, loss_rows, reinterpret_cast<__nv_bfloat16*>(dlogits), ldd, V);
+    B200FM_LAUNCH(cross_entropy_kernel, dim3((unsigned)n), dim3(256), 0, stream, 1, logits, ld, targets, loss_rows, reinterpret_cast<__nv_bfloat16*>(dlogits), ldd, V);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -236,7 +311,7 @@ extern "C" int b200fm_colsum_bf16(const void* x, long long ld, float* out, long 
     B200FM_CHECK(x && out, "colsum: null pointer");
     const int rpb = 256;
     dim3 grid((N + 255) / 256, (unsigned)((R + rpb - 1) / rpb));
-    colsum_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, out, R, N, rpb);
+    B200FM_LAUNCH(colsum_bf16_kernel, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(x), ld, out, R, N, rpb);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -246,7 +321,7 @@ extern "C" int b200fm_cast_f32_bf16(const float* x, void* y, long long n, void* 
     if (n == 0) return 0;
     B200FM_CHECK(x && y, "cast: null pointer");
     B200FM_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0, "cast: misaligned buffers");
-    cast_f32_bf16_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n);
+    B200FM_LAUNCH(cast_f32_bf16_kernel, dim3(ew_grid(n / 4 + 1, 256)), dim3(256), 0, stream, 1, x, reinterpret_cast<__nv_bfloat16*>(y), n);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -257,7 +332,7 @@ extern "C" int b200fm_patchify(const float* img, void* out, int B, int C, int H,
     B200FM_CHECK(img && out, "patchify: null pointer");
     B200FM_CHECK(P > 0 && H % P == 0 && W % P == 0, "Image sizes %dx%d must be divisible by patch sizes %dx%d", H, W, P, P);
     const long long total = (long long)B * C * H * W;
-    patchify_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(img, reinterpret_cast<__nv_bfloat16*>(out), B, C, H, W, P);
+    B200FM_LAUNCH(patchify_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, stream, 1, img, reinterpret_cast<__nv_bfloat16*>(out), B, C, H, W, P);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -272,7 +347,7 @@ extern "C" int b200fm_adamw(float* p, const float* g, float* m, float* v, void* 
     const float bc2s = sqrtf(1.0f - powf(beta2, (float)step));
     B200FM_CHECK(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
                  (shadow_bf16 == nullptr || (reinterpret_cast<uintptr_t>(shadow_bf16) & 7) == 0), "adamw: buffers must be 16-byte aligned");
-    adamw_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, stream>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n, lr, beta1, beta2, eps,
+    B200FM_LAUNCH(adamw_kernel, dim3(ew_grid(n / 4 + 1, 256)), dim3(256), 0, stream, 1, p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n, lr, beta1, beta2, eps,
                                                     weight_decay, bc1, bc2s, grad_scale);
     B200FM_CUDA(cudaGetLastError());
     return 0;

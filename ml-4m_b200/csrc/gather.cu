@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(1024)
 plan_kernel(const SegTable tab, int n_keep, int32_t* __restrict__ src_seg, int32_t* __restrict__ src_pos, int32_t* __restrict__ pos_id,
             uint8_t* __restrict__ pad_mask, int16_t* __restrict__ mod_mask, int16_t* __restrict__ mod_raw,
             int64_t* __restrict__ target_ids, int32_t* __restrict__ dam_out) {
+    pdl_enter();
     __shared__ int warp_tot[32];
     __shared__ int carry_s;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -118,6 +119,7 @@ plan_kernel(const SegTable tab, int n_keep, int32_t* __restrict__ src_seg, int32
 __global__ void __launch_bounds__(256)
 decoder_mask_kernel(const int32_t* __restrict__ dam, const int16_t* __restrict__ mod_raw, uint8_t* __restrict__ out, int M,
                     int causal, int sep) {
+    pdl_enter();
     extern __shared__ int sm_i[];
     int* cs = sm_i;                 // [M]
     int* md = sm_i + M;             // [M]
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(256)
 embed_kernel(const SegTable tab, const int32_t* __restrict__ src_seg, const int32_t* __restrict__ src_pos,
              const int32_t* __restrict__ pos_id, const uint8_t* __restrict__ pad_mask, const float* __restrict__ mask_token,
              float* __restrict__ x0, float* __restrict__ emb_out, long long rows, int n_keep) {
+    pdl_enter();
     constexpr int D = VEC * 128;
     const int lane = threadIdx.x & 31;
     for (long long row = blockIdx.x * 8ll + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8ll) {
@@ -195,6 +198,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 embed_bwd_scatter_kernel(const SegTable tab, const int32_t* __restrict__ src_seg, const int32_t* __restrict__ src_pos,
                          const uint8_t* __restrict__ pad_mask, const float* __restrict__ dx0, long long rows, int n_keep) {
+    pdl_enter();
     constexpr int D = VEC * 128;
     const int lane = threadIdx.x & 31;
     for (long long row = blockIdx.x * 8ll + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8ll) {
@@ -226,6 +230,7 @@ __global__ void __launch_bounds__(128)
 embed_bwd_modsum_kernel(const SegTable tab, const int32_t* __restrict__ src_seg, const uint8_t* __restrict__ pad_mask,
                         const float* __restrict__ dx0, const float* __restrict__ demb, float* __restrict__ d_mask_token,
                         long long rows, int D) {
+    pdl_enter();
     const int s = blockIdx.x, col = blockIdx.y * 128 + threadIdx.x;
     const long long per = (rows + gridDim.z - 1) / gridDim.z;
     const long long r0 = blockIdx.z * per, r1 = r0 + per < rows ? r0 + per : rows;
@@ -246,6 +251,7 @@ embed_bwd_modsum_kernel(const SegTable tab, const int32_t* __restrict__ src_seg,
 __global__ void __launch_bounds__(1024)
 head_rows_kernel(const int16_t* __restrict__ mod_mask, long long n_rows, const int* __restrict__ mod_ids, int n_mods,
                  int32_t* __restrict__ rows_out, int32_t* __restrict__ counts) {
+    pdl_enter();
     __shared__ int warp_tot[32];
     __shared__ int carry_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -277,6 +283,7 @@ head_rows_kernel(const int16_t* __restrict__ mod_mask, long long n_rows, const i
 // out[i] = src[rows[i]] : row gather used to feed the per-modality logits GEMMs (bf16 rows) and their targets (int64).
 __global__ void gather_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ rows, __nv_bfloat16* __restrict__ out,
                                         long long n, int D8) {
+    pdl_enter();
     const long long total = n * D8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / D8; const int c = (int)(i % D8);
@@ -284,11 +291,13 @@ __global__ void gather_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, c
     }
 }
 __global__ void gather_i64_kernel(const int64_t* __restrict__ src, const int32_t* __restrict__ rows, int64_t* __restrict__ out, long long n) {
+    pdl_enter();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = src[rows[i]];
 }
 // dst[rows[i]] += src[i] (fp32 accumulate of bf16 rows; each destination row is hit by at most one source row per call)
 __global__ void scatter_add_rows_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ rows, float* __restrict__ dst,
                                         long long n, int D4) {
+    pdl_enter();
     const long long total = n * D4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / D4; const int c = (int)(i % D4);
@@ -304,6 +313,7 @@ __global__ void scatter_add_rows_kernel(const __nv_bfloat16* __restrict__ src, c
 // dst[rows[i]] = src[i] for bf16 rows (destination rows are distinct)
 __global__ void scatter_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ rows, __nv_bfloat16* __restrict__ dst,
                                          long long n, int D8) {
+    pdl_enter();
     const long long total = n * D8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / D8; const int c = (int)(i % D8);
@@ -345,7 +355,7 @@ extern "C" int b200fm_select_plan(const b200fm_segment* segs, int n_seg, int mod
         B200FM_CHECK(target_ids && dam_out, "select_plan: decoder side needs target_ids and dam outputs");
         for (int i = 0; i < n_seg; ++i) B200FM_CHECK(segs[i].ids && segs[i].dam, "select_plan: decoder segment %d needs ids and dam", i);
     }
-    plan_kernel<<<B, 1024, 0, stream>>>(t, n_keep, src_seg, src_pos, pos_id, pad_mask, mod_mask, mod_raw, target_ids, dam_out);
+    B200FM_LAUNCH(plan_kernel, dim3(B), dim3(1024), 0, stream, 1, t, n_keep, src_seg, src_pos, pos_id, pad_mask, mod_mask, mod_raw, target_ids, dam_out);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -356,7 +366,7 @@ extern "C" int b200fm_decoder_attention_mask(const int32_t* dam, const int16_t* 
     if (B == 0 || M == 0) return 0;
     B200FM_CHECK(dam && mod_raw && mask_out, "decoder_attention_mask: null pointer");
     B200FM_CHECK(M <= 4096, "decoder_attention_mask: M=%d too large", M);
-    decoder_mask_kernel<<<B, 256, 2 * M * sizeof(int), stream>>>(dam, mod_raw, mask_out, M, causal, sep);
+    B200FM_LAUNCH(decoder_mask_kernel, dim3(B), dim3(256), 2 * M * sizeof(int), stream, 1, dam, mod_raw, mask_out, M, causal, sep);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -384,7 +394,7 @@ extern "C" int b200fm_embed_rows(const b200fm_segment* segs, int n_seg, int mode
     B200FM_CHECK(!decoder || mask_token, "embed_rows: decoder side needs the mask token");
     const long long rows = (long long)B * n_keep;
     const int grid = (int)((rows + 7) / 8 < 148 * 8 ? (rows + 7) / 8 : 148 * 8);
-    B200FM_VEC_SWITCH(D, (embed_kernel<V><<<grid, 256, 0, stream>>>(t, src_seg, src_pos, pos_id, pad_mask, mask_token, x0, emb_out, rows, n_keep)));
+    B200FM_VEC_SWITCH(D, (B200FM_LAUNCH((embed_kernel<V>), dim3(grid), dim3(256), 0, stream, 1, t, src_seg, src_pos, pos_id, pad_mask, mask_token, x0, emb_out, rows, n_keep)));
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -400,10 +410,10 @@ extern "C" int b200fm_embed_rows_bwd(const b200fm_segment* segs, int n_seg, int 
     B200FM_CHECK(src_seg && src_pos && pad_mask && dx0, "embed_rows_bwd: null pointer");
     const long long rows = (long long)B * n_keep;
     const int grid = (int)((rows + 7) / 8 < 148 * 8 ? (rows + 7) / 8 : 148 * 8);
-    B200FM_VEC_SWITCH(D, (embed_bwd_scatter_kernel<V><<<grid, 256, 0, stream>>>(t, src_seg, src_pos, pad_mask, dx0, rows, n_keep)));
+    B200FM_VEC_SWITCH(D, (B200FM_LAUNCH((embed_bwd_scatter_kernel<V>), dim3(grid), dim3(256), 0, stream, 1, t, src_seg, src_pos, pad_mask, dx0, rows, n_keep)));
     B200FM_CUDA(cudaGetLastError());
     const int splits = (int)(rows / 512 > 0 ? (rows / 512 > 32 ? 32 : rows / 512) : 1);
-    embed_bwd_modsum_kernel<<<dim3(n_seg, D / 128, splits), 128, 0, stream>>>(t, src_seg, pad_mask, dx0, demb, d_mask_token, rows, D);
+    B200FM_LAUNCH(embed_bwd_modsum_kernel, dim3(dim3(n_seg, D / 128, splits)), dim3(128), 0, stream, 1, t, src_seg, pad_mask, dx0, demb, d_mask_token, rows, D);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -413,7 +423,7 @@ extern "C" int b200fm_head_rows(const int16_t* mod_mask, long long n_rows, const
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (n_rows == 0 || n_mods == 0) return 0;
     B200FM_CHECK(mod_mask && mod_ids_dev && rows_out && counts, "head_rows: null pointer");
-    head_rows_kernel<<<1, 1024, 0, stream>>>(mod_mask, n_rows, mod_ids_dev, n_mods, rows_out, counts);
+    B200FM_LAUNCH(head_rows_kernel, dim3(1), dim3(1024), 0, stream, 1, mod_mask, n_rows, mod_ids_dev, n_mods, rows_out, counts);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -424,7 +434,7 @@ extern "C" int b200fm_gather_rows_bf16(const void* src, const int32_t* rows, voi
     B200FM_CHECK(src && rows && out && D % 8 == 0, "gather_rows_bf16: bad arguments");
     const long long total = n * (D / 8);
     const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-    gather_rows_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), rows, reinterpret_cast<__nv_bfloat16*>(out), n, D / 8);
+    B200FM_LAUNCH(gather_rows_bf16_kernel, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(src), rows, reinterpret_cast<__nv_bfloat16*>(out), n, D / 8);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -433,7 +443,7 @@ extern "C" int b200fm_gather_i64(const int64_t* src, const int32_t* rows, int64_
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (n == 0) return 0;
     B200FM_CHECK(src && rows && out, "gather_i64: null pointer");
-    gather_i64_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(src, rows, out, n);
+    B200FM_LAUNCH(gather_i64_kernel, dim3((int)((n + 255) / 256)), dim3(256), 0, stream, 1, src, rows, out, n);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -444,7 +454,7 @@ extern "C" int b200fm_scatter_add_rows(const void* src_bf16, const int32_t* rows
     B200FM_CHECK(src_bf16 && rows && dst && D % 4 == 0, "scatter_add_rows: bad arguments");
     const long long total = n * (D / 4);
     const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-    scatter_add_rows_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src_bf16), rows, dst, n, D / 4);
+    B200FM_LAUNCH(scatter_add_rows_kernel, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(src_bf16), rows, dst, n, D / 4);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -455,7 +465,7 @@ extern "C" int b200fm_scatter_rows_bf16(const void* src, const int32_t* rows, vo
     B200FM_CHECK(src && rows && dst && D % 8 == 0, "scatter_rows_bf16: bad arguments");
     const long long total = n * (D / 8);
     const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-    scatter_rows_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), rows, reinterpret_cast<__nv_bfloat16*>(dst), n, D / 8);
+    B200FM_LAUNCH(scatter_rows_bf16_kernel, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(src), rows, reinterpret_cast<__nv_bfloat16*>(dst), n, D / 8);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }

@@ -145,6 +145,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     tc_fence_before();
     if constexpr (CTA2) cluster_sync_all(); else __syncthreads();      // peer barriers must be initialised before any remote signal
     tc_fence_after();
+    pdl_trigger();      // TMEM is held: a dependent grid can no longer starve this one of columns
+    pdl_wait();         // everything below touches global memory
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == kEpiWarps) {
@@ -424,19 +426,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
     const int units = (CTA2 ? (a.num_m_blocks + 1) / 2 : a.num_m_blocks) * a.num_n_blocks * a.k_splits;
     if constexpr (CTA2) {
         const int clusters = units < sm_count() / 2 ? units : sm_count() / 2;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * clusters);
-        cfg.blockDim = dim3(kGemmThreads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        B200FM_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, a));
+        B200FM_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(kGemmThreads), smem, stream, 2, ta, tb, a));
     } else {
         const int grid = units < sm_count() ? units : sm_count();
-        kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, a);
+        B200FM_CUDA(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), smem, stream, 1, ta, tb, a));
     }
     B200FM_CUDA(cudaGetLastError());
     return 0;

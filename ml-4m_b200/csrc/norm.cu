@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ add, float* __restrict__ x_out,
                      const float* __restrict__ gamma, const float* __restrict__ beta,
                      void* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, float eps) {
+    pdl_enter();
     constexpr int D = VEC * 128;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float4 g[VEC], b[VEC];
@@ -69,6 +70,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, c
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ dres,
                      float* __restrict__ dx_out, __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, int rows) {
+    pdl_enter();
     constexpr int D = VEC * 128;
     __shared__ float red[kLnWarps][128 + 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -165,8 +167,8 @@ extern "C" int b200fm_add_layernorm_fwd(const float* x, const void* add_bf16, fl
     const int grid = ln_grid(rows);
 #define LN_FWD(V)                                                                                                        \
     case V:                                                                                                              \
-        if (y_is_bf16) layernorm_fwd_kernel<V, true><<<grid, kLnWarps * 32, 0, stream>>>(x, add, x_out, gamma, beta, y, mean, rstd, rows, eps); \
-        else layernorm_fwd_kernel<V, false><<<grid, kLnWarps * 32, 0, stream>>>(x, add, x_out, gamma, beta, y, mean, rstd, rows, eps);          \
+        if (y_is_bf16) B200FM_LAUNCH((layernorm_fwd_kernel<V, true>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, x, add, x_out, gamma, beta, y, mean, rstd, rows, eps); \
+        else B200FM_LAUNCH((layernorm_fwd_kernel<V, false>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, x, add, x_out, gamma, beta, y, mean, rstd, rows, eps);          \
         break;
     switch (D / 128) {
         LN_FWD(1) LN_FWD(2) LN_FWD(3) LN_FWD(4) LN_FWD(5) LN_FWD(6) LN_FWD(8) LN_FWD(10) LN_FWD(12) LN_FWD(16)
@@ -188,8 +190,8 @@ extern "C" int b200fm_layernorm_bwd(const void* dy, int dy_is_bf16, const float*
     if (grid > 148 * 2) grid = 148 * 2;       // fewer blocks -> fewer column atomics
 #define LN_BWD(V)                                                                                                          \
     case V:                                                                                                                \
-        if (dy_is_bf16) layernorm_bwd_kernel<V, true><<<grid, kLnWarps * 32, 0, stream>>>(dy, x, gamma, mean, rstd, dres, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows); \
-        else layernorm_bwd_kernel<V, false><<<grid, kLnWarps * 32, 0, stream>>>(dy, x, gamma, mean, rstd, dres, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows);          \
+        if (dy_is_bf16) B200FM_LAUNCH((layernorm_bwd_kernel<V, true>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, dy, x, gamma, mean, rstd, dres, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows); \
+        else B200FM_LAUNCH((layernorm_bwd_kernel<V, false>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, dy, x, gamma, mean, rstd, dres, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows);          \
         break;
     switch (D / 128) {
         LN_BWD(1) LN_BWD(2) LN_BWD(3) LN_BWD(4) LN_BWD(5) LN_BWD(6) LN_BWD(8) LN_BWD(10) LN_BWD(12) LN_BWD(16)

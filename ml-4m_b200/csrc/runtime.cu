@@ -1,6 +1,7 @@
 // Host runtime glue for the C ABI: last-error string, device properties, TMA descriptor encoding.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -9,6 +10,16 @@
 #include "tmap.cuh"
 
 namespace b200fm {
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200FM_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 
 static thread_local char g_err[1024] = "";
 

@@ -21,6 +21,7 @@ constexpr int kVqDMax = 64;
 // et[j][k] = (cosine ? e[k][j] / max(|e_k|, 1e-12) : e[k][j]);  ee[k] = |e_k|^2 (Euclidean only); padded codes: 0.
 __global__ void vq_prep_codebook(const float* __restrict__ e, float* __restrict__ et, float* __restrict__ ee, int K, int Kpad,
                                  int d, int cosine) {
+    pdl_enter();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= Kpad) return;
     if (k >= K) {
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(kVqThreads, 2)
 vq_scan_kernel(const float* __restrict__ z, const float* __restrict__ et, const float* __restrict__ ee,
                const float* __restrict__ e_raw, int64_t* __restrict__ idx_out, float* __restrict__ quant_out, long long n,
                int K, int Kpad, int cosine) {
+    pdl_enter();
     extern __shared__ __align__(16) float smem_f[];
     float* zs = smem_f;                                   // [D][128]  (latents transposed, normalised)
     float* es = zs + D * kVqTile;                         // 2 x [D][128]
@@ -180,7 +182,7 @@ static int launch_vq(const float* z, const float* et, const float* ee, const flo
         configured = true;
     }
     const long long grid = (n + kVqTile - 1) / kVqTile;
-    kern<<<(unsigned)grid, kVqThreads, smem, stream>>>(z, et, ee, e_raw, idx, quant, n, K, Kpad, cosine);
+    B200FM_LAUNCH(kern, dim3((unsigned)grid), dim3(kVqThreads), smem, stream, 1, z, et, ee, e_raw, idx, quant, n, K, Kpad, cosine);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -204,7 +206,7 @@ extern "C" int b200fm_vq_argmax(const float* z, const float* codebook, int64_t* 
     B200FM_CUDA(cudaMallocAsync(&ws, (size_t)(d + 1) * Kpad * sizeof(float), stream));
     float* et = ws;
     float* ee = ws + (size_t)d * Kpad;
-    vq_prep_codebook<<<(Kpad + 255) / 256, 256, 0, stream>>>(codebook, et, ee, K, Kpad, d, cosine);
+    B200FM_LAUNCH(vq_prep_codebook, dim3((Kpad + 255) / 256), dim3(256), 0, stream, 1, codebook, et, ee, K, Kpad, d, cosine);
     int rc = 0;
     switch (d) {
         case 8: rc = launch_vq<8>(z, et, ee, codebook, idx_out, quant_out, n, K, Kpad, cosine, stream); break;

@@ -1,0 +1,57 @@
+"""FusedAdamW (b200fm_adamw / b200fm_adamw_multi) against torch.optim.AdamW as the reference configures it
+(fourm/utils/optim_factory.py:239-240).  fp32 elementwise: tolerance 2e-6 relative (fma contraction / sqrt rounding)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _params(dev, seed):
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(768, 768), (2048, 768), (768,), (1,), (7, 13), (8192 + 5,), (3, 8192), (64, 3, 16, 16)]
+    return [torch.nn.Parameter(torch.randn(*s, generator=g).to(dev)) for s in shapes]
+
+
+@pytest.mark.parametrize("wd", [0.0, 0.05])
+def test_fused_adamw_matches_torch(wd):
+    from b200fm import functional as BF
+    from b200fm.optim import FusedAdamW
+    dev = torch.device("cuda")
+    ours, ref = _params(dev, 1), _params(dev, 1)
+    shadow = BF.weight_bf16(ours[0])            # a bf16 mirror the optimizer has to keep fresh
+    o1 = FusedAdamW([dict(params=ours[:4], weight_decay=wd), dict(params=ours[4:], weight_decay=0.0)], lr=1e-3, betas=(0.9, 0.95))
+    o2 = torch.optim.AdamW([dict(params=ref[:4], weight_decay=wd), dict(params=ref[4:], weight_decay=0.0)], lr=1e-3, betas=(0.9, 0.95))
+    g = torch.Generator().manual_seed(2)
+    for step in range(4):
+        for a, b in zip(ours, ref):
+            gr = torch.randn(a.shape, generator=g).to(dev)
+            if step == 2 and a.ndim == 1:
+                a.grad = b.grad = None          # a parameter without a gradient this step is skipped by both
+                continue
+            a.grad, b.grad = gr.clone(), gr.clone()
+        o1.step()
+        o2.step()
+    for a, b in zip(ours, ref):
+        torch.testing.assert_close(a.data, b.data, rtol=2e-6, atol=2e-7)
+    for a, b in zip(ours, ref):
+        sa, sb = o1.state[a], o2.state[b]
+        torch.testing.assert_close(sa["exp_avg"], sb["exp_avg"], rtol=2e-6, atol=1e-7)
+        torch.testing.assert_close(sa["exp_avg_sq"], sb["exp_avg_sq"], rtol=2e-6, atol=1e-7)
+    assert torch.equal(BF.weight_bf16(ours[0]), ours[0].data.to(torch.bfloat16))
+    assert BF.weight_bf16(ours[0]).data_ptr() == shadow.data_ptr()
+
+
+def test_fused_adamw_grad_scale():
+    from b200fm.optim import FusedAdamW
+    dev = torch.device("cuda")
+    ours, ref = _params(dev, 3), _params(dev, 3)
+    o1 = FusedAdamW(ours, lr=2e-3, betas=(0.9, 0.95), weight_decay=0.05)
+    o2 = torch.optim.AdamW(ref, lr=2e-3, betas=(0.9, 0.95), weight_decay=0.05)
+    g = torch.Generator().manual_seed(4)
+    for a, b in zip(ours, ref):
+        gr = torch.randn(a.shape, generator=g).to(dev)
+        a.grad, b.grad = gr.clone(), gr * 0.25
+    o1.step(grad_scale=0.25)
+    o2.step()
+    for a, b in zip(ours, ref):
+        torch.testing.assert_close(a.data, b.data, rtol=2e-6, atol=2e-7)
