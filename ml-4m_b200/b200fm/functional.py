@@ -80,6 +80,35 @@ def clear_weight_cache():
     _shadow_views.clear()
 
 
+class _ZeroArena:
+    """Hands out small zero-initialised fp32 vectors (LayerNorm dgamma / dbeta, embedding-sum gradients -- buffers the
+    kernels ACCUMULATE into) as slices of one pre-zeroed chunk per device: one fill per ~1000 requests instead of one
+    per request.  A slice is handed out once; the chunk lives as long as any slice of it does."""
+    CHUNK = 1 << 20
+
+    def __init__(self):
+        self._chunks = {}
+
+    def take(self, n, device):
+        n_pad = (n + 3) & ~3                                  # keep every slice 16 B aligned
+        if n_pad > self.CHUNK // 8:
+            return torch.zeros(n, device=device, dtype=torch.float32)
+        key = (device.type, device.index)
+        ent = self._chunks.get(key)
+        if ent is None or ent[1] + n_pad > self.CHUNK:
+            ent = self._chunks[key] = [torch.zeros(self.CHUNK, device=device, dtype=torch.float32), 0]
+        out = ent[0][ent[1]:ent[1] + n]
+        ent[1] += n_pad
+        return out
+
+
+_zero_arena = _ZeroArena()
+
+
+def zeros_f32(n, device):
+    return _zero_arena.take(n, device)
+
+
 def _as2d(x):
     return x.reshape(-1, x.shape[-1])
 
@@ -106,8 +135,8 @@ class LayerNormFn(torch.autograd.Function):
         x2, weight, mean, rstd = ctx.saved_tensors
         dy2 = _as2d(dy).contiguous()
         D = x2.shape[1]
-        dgamma = torch.zeros(D, device=x2.device, dtype=torch.float32) if weight.requires_grad else None
-        dbeta = torch.zeros(D, device=x2.device, dtype=torch.float32) if ctx.has_bias else None
+        dgamma = zeros_f32(D, x2.device) if weight.requires_grad else None
+        dbeta = zeros_f32(D, x2.device) if ctx.has_bias else None
         dx, _ = ops.layernorm_bwd(dy2, x2, weight, mean, rstd, dgamma=dgamma, dbeta=dbeta)
         return dx.view(ctx.shape), dgamma, dbeta, None, None
 
@@ -393,11 +422,11 @@ class EmbedRowsFn(torch.autograd.Function):
                 else:
                     gm = torch.zeros(mshape, device=dev, dtype=torch.float32)
                     d["d_token_emb"] = gm
-            ge = torch.zeros(D, device=dev, dtype=torch.float32) if need_mod else None
+            ge = zeros_f32(D, dev) if need_mod else None
             d["d_mod_emb"] = ge
             grads += [gm, None if ge is None else ge.view(eshape)]
             segs.append(d)
-        dmt = torch.zeros(D, device=dev, dtype=torch.float32) if (ctx.mask_token_shape is not None and ctx.needs_input_grad[4]) else None
+        dmt = zeros_f32(D, dev) if (ctx.mask_token_shape is not None and ctx.needs_input_grad[4]) else None
         ops.embed_rows_bwd(plan, segs, dx0.contiguous(), None if demb is None else demb.contiguous(), dmt, D)
         return (None, None, None, None, None if dmt is None else dmt.view(ctx.mask_token_shape), *grads)
 
@@ -482,8 +511,8 @@ class SelfAttnSubLayerFn(torch.autograd.Function):
         dh = ops.gemm(dqkv, weight_bf16(qkv_w)[:3 * D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
         dqkv_w = ops.gemm(dqkv, h, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if qkv_w.requires_grad else None
         dqkv_b = ops.colsum_bf16(dqkv) if has_qb else None
-        dgamma = torch.zeros(D, device=s2.device, dtype=torch.float32) if nw.requires_grad else None
-        dbeta = torch.zeros(D, device=s2.device, dtype=torch.float32) if nb_grad else None
+        dgamma = zeros_f32(D, s2.device) if nw.requires_grad else None
+        dbeta = zeros_f32(D, s2.device) if nb_grad else None
         dx, dxb = ops.layernorm_bwd(dh, s2, nw, mean, rstd, dres=d2, want_bf16=has_pend, dgamma=dgamma, dbeta=dbeta)
         return (dx.view(B, N, D), dxb.view(B, N, D) if has_pend else None, None, dgamma, dbeta, dqkv_w, dqkv_b, dproj_w, dproj_b,
                 None, None, None)
@@ -528,14 +557,14 @@ class CrossAttnSubLayerFn(torch.autograd.Function):
         dq_b = ops.colsum_bf16(dq) if has_qb else None
         dkv_w = ops.gemm(dkv, hc, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if kv_w.requires_grad else None
         dkv_b = ops.colsum_bf16(dkv) if has_kvb else None
-        dqg = torch.zeros(D, device=dev, dtype=torch.float32) if qnw.requires_grad else None
-        dqb = torch.zeros(D, device=dev, dtype=torch.float32) if qnb_grad else None
+        dqg = zeros_f32(D, dev) if qnw.requires_grad else None
+        dqb = zeros_f32(D, dev) if qnb_grad else None
         dx, dxb = ops.layernorm_bwd(dhq, s2, qnw, qmean, qrstd, dres=d2, want_bf16=has_pend, dgamma=dqg, dbeta=dqb)
         dctx = dcg = dcb = None
         if ctx.needs_input_grad[2]:
             dhc = ops.gemm(dkv, weight_bf16(kv_w)[:2 * D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
-            dcg = torch.zeros(D, device=dev, dtype=torch.float32) if cnw.requires_grad else None
-            dcb = torch.zeros(D, device=dev, dtype=torch.float32) if cnb_grad else None
+            dcg = zeros_f32(D, dev) if cnw.requires_grad else None
+            dcb = zeros_f32(D, dev) if cnb_grad else None
             dctx, _ = ops.layernorm_bwd(dhc, c2, cnw, cmean, crstd, dgamma=dcg, dbeta=dcb)
             dctx = dctx.view(B, M, D)
         return (dx.view(B, N, D), dxb.view(B, N, D) if has_pend else None, dctx, None, dqg, dqb, dcg, dcb, dq_w, dq_b, dkv_w, dkv_b,
@@ -586,8 +615,8 @@ class GatedMlpSubLayerFn(torch.autograd.Function):
         if has_b13:
             dbias = ops.colsum_bf16(dab)
             db1, db3 = dbias[:H], dbias[Hp:Hp + H]
-        dgamma = torch.zeros(D, device=s2.device, dtype=torch.float32) if nw.requires_grad else None
-        dbeta = torch.zeros(D, device=s2.device, dtype=torch.float32) if nb_grad else None
+        dgamma = zeros_f32(D, s2.device) if nw.requires_grad else None
+        dbeta = zeros_f32(D, s2.device) if nb_grad else None
         dx, dxb = ops.layernorm_bwd(dh, s2, nw, mean, rstd, dres=d2, want_bf16=has_pend, dgamma=dgamma, dbeta=dbeta)
         return dx.view(shape), dxb.view(shape) if has_pend else None, dgamma, dbeta, dw1, dw3, dw2, db1, db3, db2, None
 
@@ -620,8 +649,8 @@ class NormLinearResidualFn(torch.autograd.Function):
         dh = ops.gemm(db, weight_bf16(w)[:w.shape[0]], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
         dw = ops.gemm(db, h, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if w.requires_grad else None
         dbias = ops.colsum_bf16(db) if has_b else None
-        dgamma = torch.zeros(D, device=s2.device, dtype=torch.float32) if nw.requires_grad else None
-        dbeta = torch.zeros(D, device=s2.device, dtype=torch.float32) if nb_grad else None
+        dgamma = zeros_f32(D, s2.device) if nw.requires_grad else None
+        dbeta = zeros_f32(D, s2.device) if nb_grad else None
         dx, dxb = ops.layernorm_bwd(dh, s2, nw, mean, rstd, want_bf16=has_pend, dgamma=dgamma, dbeta=dbeta)
         return dx.view(xshape), dxb.view(xshape) if has_pend else None, dgamma, dbeta, dw, dbias, dout.view(rshape), None
 
@@ -646,7 +675,7 @@ class AddLayerNormFn(torch.autograd.Function):
         dh2 = dh.reshape(-1, D)
         if not dh2.is_contiguous():
             dh2 = dh2.contiguous()
-        dgamma = torch.zeros(D, device=s2.device, dtype=torch.float32) if nw.requires_grad else None
-        dbeta = torch.zeros(D, device=s2.device, dtype=torch.float32) if nb_grad else None
+        dgamma = zeros_f32(D, s2.device) if nw.requires_grad else None
+        dbeta = zeros_f32(D, s2.device) if nb_grad else None
         dx, dxb = ops.layernorm_bwd(dh2, s2, nw, mean, rstd, want_bf16=has_pend, dgamma=dgamma, dbeta=dbeta)
         return dx.view(shape), dxb.view(shape) if has_pend else None, dgamma, dbeta, None

@@ -228,10 +228,20 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     const int qrow = qt * 128 + r;
                     const bool row_ok = qrow < args.Nq;
                     const uint8_t* mrow = args.mask ? args.mask + b * args.mask_b_stride + (row_ok ? qrow : 0) * args.mask_q_stride : nullptr;
-                    const float m = m_[qt], inv = inv_[qt], Dr = D_[qt];
-                    uint32_t mb[2];
+                    // p = exp2(s*scale_log2 - m) * inv = exp2(fma(s, scale_log2, log2(inv) - m)); rows past Nq get exp2(-inf) = 0.
+                    // A masked key has p = exp2(kMaskedScore - m) * inv: inv on a fully masked row (m == kMaskedScore), else 0.
+                    const float m = m_[qt], inv = inv_[qt];
+                    const float shift = row_ok ? (__log2f(inv) - m) : -INFINITY;
+                    const float p_masked = (row_ok && m == kMaskedScore) ? inv : 0.f;
+                    const float neg_ds = -D_[qt] * args.scale;                       // ds = p * (dp*scale - D*scale)
+                    uint32_t mb[2], tail[2];
 #pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) mb[cc] = attn_mask_bits32(mrow, kt * 128 + (half * 2 + cc) * 32, args.Nk);
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int col0 = kt * 128 + (half * 2 + cc) * 32;
+                        mb[cc] = attn_mask_bits32(mrow, col0, args.Nk);
+                        const int valid = args.Nk - col0;
+                        tail[cc] = valid >= 32 ? 0u : (valid <= 0 ? 0xffffffffu : (0xffffffffu << valid));
+                    }
                     mbar_wait(sdp_full, stepc & 1);
                     tc_fence_after();
 #pragma unroll
@@ -244,22 +254,32 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                             tmem_ld_x32(t_lane + kColS + c * 32, ss);
                             tmem_ld_x32(t_lane + kColDP + c * 32, dd);
                             tmem_ld_wait();
-                            const uint32_t mbits = mb[cc];
+                            const uint32_t mbits = mb[cc], tbits = tail[cc];
+                            if (!__any_sync(0xffffffffu, (mbits | tbits) != 0u)) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 2) {
-                                float p[2], ds[2];
-#pragma unroll
-                                for (int e = 0; e < 2; ++e) {
-                                    const bool masked = (mbits >> (j + e)) & 1u;
-                                    float t = __uint_as_float(ss[j + e]) * args.scale_log2;
-                                    if (masked) t = kMaskedScore;
-                                    float pe = fast_exp2(t - m) * inv;
-                                    if (!row_ok || col0 + j + e >= args.Nk) pe = 0.f;
-                                    p[e] = pe;
-                                    ds[e] = masked ? 0.f : pe * (__uint_as_float(dd[j + e]) - Dr) * args.scale;
+                                for (int j = 0; j < 32; j += 2) {
+                                    const float p0 = fast_exp2(fmaf(__uint_as_float(ss[j]), args.scale_log2, shift));
+                                    const float p1 = fast_exp2(fmaf(__uint_as_float(ss[j + 1]), args.scale_log2, shift));
+                                    pk[j >> 1] = pack_bf16x2(p0, p1);
+                                    dk_[j >> 1] = pack_bf16x2(p0 * fmaf(__uint_as_float(dd[j]), args.scale, neg_ds),
+                                                             p1 * fmaf(__uint_as_float(dd[j + 1]), args.scale, neg_ds));
                                 }
-                                pk[j >> 1] = pack_bf16x2(p[0], p[1]);
-                                dk_[j >> 1] = pack_bf16x2(ds[0], ds[1]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 2) {
+                                    float p[2], ds[2];
+#pragma unroll
+                                    for (int e = 0; e < 2; ++e) {
+                                        float pe = fast_exp2(fmaf(__uint_as_float(ss[j + e]), args.scale_log2, shift));
+                                        float de = pe * fmaf(__uint_as_float(dd[j + e]), args.scale, neg_ds);
+                                        if ((mbits >> (j + e)) & 1u) { pe = p_masked; de = 0.f; }       // masked_fill: no gradient to the score
+                                        if ((tbits >> (j + e)) & 1u) { pe = 0.f; de = 0.f; }
+                                        p[e] = pe;
+                                        ds[e] = de;
+                                    }
+                                    pk[j >> 1] = pack_bf16x2(p[0], p[1]);
+                                    dk_[j >> 1] = pack_bf16x2(ds[0], ds[1]);
+                                }
                             }
                         } else {
 #pragma unroll

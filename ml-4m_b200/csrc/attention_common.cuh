@@ -19,8 +19,9 @@ B200FM_DEVINL float fast_exp2(float x) {
 }
 
 B200FM_DEVINL uint32_t nonzero_bytes_to_bits(uint32_t w) {
-    const uint32_t m = __vcmpne4(w, 0u) & 0x01010101u;
-    return (m & 1u) | ((m >> 7) & 2u) | ((m >> 14) & 4u) | ((m >> 21) & 8u);
+    // per byte: bit 7 of ((b & 0x7f) + 0x7f) | b is set iff b != 0; the multiply gathers the four flags into bits 24..27
+    const uint32_t nz = ((w | ((w & 0x7f7f7f7fu) + 0x7f7f7f7fu)) >> 7) & 0x01010101u;
+    return (nz * 0x01020408u) >> 24;
 }
 
 // Bit j set <=> key (col0 + j) is masked for this query row; keys >= Nk report 0.  mrow may be nullptr (no mask).

@@ -144,30 +144,41 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             const uint8_t* mrow = args.mask ? args.mask + b * args.mask_b_stride + (row_ok ? qrow : 0) * args.mask_q_stride : nullptr;
 
             // mask bits of the whole row are fetched before the scores are ready (hides the global-load latency)
-            uint32_t mb[NKT * 4];
+            uint32_t mb[NKT * 4], tail[NKT * 4];
+            uint32_t any_masked = 0u;
 #pragma unroll
-            for (int c = 0; c < NKT * 4; ++c) mb[c] = attn_mask_bits32(mrow, c * 32, args.Nk);
+            for (int c = 0; c < NKT * 4; ++c) {
+                mb[c] = attn_mask_bits32(mrow, c * 32, args.Nk);                   // keys >= Nk report 0
+                const int valid = args.Nk - c * 32;                                // keys of this chunk that exist
+                tail[c] = valid >= 32 ? 0u : (valid <= 0 ? 0xffffffffu : (0xffffffffu << valid));
+                any_masked |= mb[c];
+            }
             mbar_wait(s_full, par);
             tc_fence_after();
-            // pass 1: row maximum of t = s * scale * log2e (masked -> -3e38, padding keys -> -inf)
-            float m = -INFINITY;
+            // pass 1: row maximum over the unmasked keys, on the raw scores (scale > 0 keeps the order); a masked key counts as
+            // kMaskedScore in the log2 domain, exactly like masked_fill(-finfo.max) followed by the softmax's max
+            float mu = -INFINITY;
 #pragma unroll
             for (int c = 0; c < NKT * 4; ++c) {
                 if (c * 32 < args.Nk) {
                     uint32_t rr[32];
                     tmem_ld_x32(t_lane + c * 32, rr);
                     tmem_ld_wait();
-                    const uint32_t mbits = mb[c];
+                    const uint32_t ex = mb[c] | tail[c];
+                    if (!__any_sync(0xffffffffu, ex != 0u)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float t = __uint_as_float(rr[j]) * args.scale_log2;
-                        if ((mbits >> j) & 1u) t = kMaskedScore;
-                        if (c * 32 + j >= args.Nk) t = -INFINITY;
-                        m = fmaxf(m, t);
+                        for (int j = 0; j < 32; ++j) mu = fmaxf(mu, __uint_as_float(rr[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mu = fmaxf(mu, ((ex >> j) & 1u) ? -INFINITY : __uint_as_float(rr[j]));
                     }
                 }
             }
-            // pass 2: p = exp2(t - m), row sum, bf16 P into swizzled smem
+            float m = mu * args.scale_log2;                                        // -inf when every key is masked
+            if (any_masked) m = fmaxf(m, kMaskedScore);
+            const float p_masked = (m == kMaskedScore) ? 1.0f : 0.0f;              // exp2(kMaskedScore - m): uniform row iff all masked
+            const float neg_m = -m;
+            // pass 2: p = exp2(s * scale_log2 - m) in one fma + ex2, row sum, bf16 P into swizzled smem
             float sum = 0.f;
 #pragma unroll
             for (int c = 0; c < NKT * 4; ++c) {
@@ -176,19 +187,27 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     uint32_t rr[32];
                     tmem_ld_x32(t_lane + c * 32, rr);
                     tmem_ld_wait();
-                    const uint32_t mbits = mb[c];
+                    const uint32_t mbits = mb[c], tbits = tail[c];
+                    if (!__any_sync(0xffffffffu, (mbits | tbits) != 0u)) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float t0 = __uint_as_float(rr[j]) * args.scale_log2, t1 = __uint_as_float(rr[j + 1]) * args.scale_log2;
-                        if ((mbits >> j) & 1u) t0 = kMaskedScore;
-                        if ((mbits >> (j + 1)) & 1u) t1 = kMaskedScore;
-                        float p0 = fast_exp2(t0 - m), p1 = fast_exp2(t1 - m);
-                        if (c * 32 + j >= args.Nk) p0 = 0.f;
-                        if (c * 32 + j + 1 >= args.Nk) p1 = 0.f;
-                        const uint32_t w = pack_bf16x2(p0, p1);
-                        const float2 pr = unpack_bf16x2(w);      // sum what the tensor core will actually multiply
-                        sum += pr.x + pr.y;
-                        pk[j >> 1] = w;
+                        for (int j = 0; j < 32; j += 2) {
+                            const float p0 = fast_exp2(fmaf(__uint_as_float(rr[j]), args.scale_log2, neg_m));
+                            const float p1 = fast_exp2(fmaf(__uint_as_float(rr[j + 1]), args.scale_log2, neg_m));
+                            sum += p0 + p1;
+                            pk[j >> 1] = pack_bf16x2(p0, p1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            float p0 = fast_exp2(fmaf(__uint_as_float(rr[j]), args.scale_log2, neg_m));
+                            float p1 = fast_exp2(fmaf(__uint_as_float(rr[j + 1]), args.scale_log2, neg_m));
+                            if ((mbits >> j) & 1u) p0 = p_masked;
+                            if ((mbits >> (j + 1)) & 1u) p1 = p_masked;
+                            if ((tbits >> j) & 1u) p0 = 0.f;
+                            if ((tbits >> (j + 1)) & 1u) p1 = 0.f;
+                            sum += p0 + p1;
+                            pk[j >> 1] = pack_bf16x2(p0, p1);
+                        }
                     }
                 } else {
 #pragma unroll

@@ -185,6 +185,12 @@ B200FM_DEVINL void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group
 // ------------------------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ------------------------------------------------------------------------------------------------------------
+// d/da, d/db of silu(a) * b given the incoming gradient g (fm_utils.py:143): s = sigmoid(a)
+B200FM_DEVINL void swiglu_grad(float a, float b, float g, float& da, float& db) {
+    const float s = 1.0f / (1.0f + __expf(-a));
+    da = g * b * s * (1.0f + a * (1.0f - s));
+    db = g * a * s;
+}
 B200FM_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 B200FM_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -251,8 +257,11 @@ B200FM_DEVINL uint32_t mapa_u32(const void* local, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(smem_u32(local)), "r"(rank));
     return out;
 }
+// Used to hand a TMEM accumulator back to the leader's MMA thread: the tcgen05 fences order the TMEM reads, no global or
+// shared data is published through this arrive, so the default (release.cta) form is enough -- a cluster-scope release
+// would add a MEMBAR that waits for all of the epilogue's outstanding global stores.
 B200FM_DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion bytes are signalled on an mbarrier given by its shared::cluster address (the leader's barrier)
 B200FM_DEVINL void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int32_t c_inner, int32_t c_outer,

@@ -44,9 +44,11 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ ab, const __
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const float2 a = unpack_bf16x2(aw[e]), b = unpack_bf16x2(bw[e]), g = unpack_bf16x2(gw[e]);
-            const float s0 = 1.0f / (1.0f + __expf(-a.x)), s1 = 1.0f / (1.0f + __expf(-a.y));
-            da[e] = pack_bf16x2(g.x * b.x * s0 * (1.0f + a.x * (1.0f - s0)), g.y * b.y * s1 * (1.0f + a.y * (1.0f - s1)));
-            db[e] = pack_bf16x2(g.x * a.x * s0, g.y * a.y * s1);
+            float dax, dbx, day, dby;
+            swiglu_grad(a.x, b.x, g.x, dax, dbx);
+            swiglu_grad(a.y, b.y, g.y, day, dby);
+            da[e] = pack_bf16x2(dax, day);
+            db[e] = pack_bf16x2(dbx, dby);
         }
         *reinterpret_cast<uint4*>(dab + row * ld_dab + c) = make_uint4(da[0], da[1], da[2], da[3]);
         *reinterpret_cast<uint4*>(dab + row * ld_dab + H + c) = make_uint4(db[0], db[1], db[2], db[3]);

@@ -483,12 +483,26 @@ extern "C" int b200fm_gemm_bf16(int layout, int epilogue, int M, int N, int K, c
         const int tiles256 = a.num_m_blocks * ((N + 255) / 256);
         const int num_kb = (K + kBK - 1) / kBK;
         if (epilogue == B200FM_EPI_F32 && bias == nullptr && N > 128 && tiles256 < 2 * sm_count() && num_kb >= 32) {
-            // few output tiles, long K (weight gradients): keep the 128x256 tile and split K across CTAs (fp32 atomics)
+            // few output tiles, long K (weight gradients): keep the 128x256 tile and split K across CTAs (fp32 atomics).
+            // Work items = output units x K slices are dealt round-robin to the resident CTAs (pairs), so the slice count is
+            // chosen to fill whole rounds: best machine fill first, fewer slices (less atomic traffic) on ties.
             BN = 256;
-            int splits = (2 * sm_count() + tiles256 - 1) / tiles256;
-            if (splits > num_kb / 8) splits = num_kb / 8;
-            if (splits < 1) splits = 1;
-            a.kb_per_split = (num_kb + splits - 1) / splits;
+            const bool will_pair = use_cta_pairs() && a.num_m_blocks >= 2;
+            const int units = (will_pair ? (a.num_m_blocks + 1) / 2 : a.num_m_blocks) * ((N + 255) / 256);
+            const int slots = will_pair ? sm_count() / 2 : sm_count();
+            int best_s = 1;
+            double best_score = -1.0;
+            for (int s = 1; s <= num_kb / 8 && s <= 32; ++s) {
+                const int per = (num_kb + s - 1) / s;
+                const int real = (num_kb + per - 1) / per;                 // slices actually produced
+                if (real != s) continue;
+                const long long items = 1ll * units * s;
+                const long long rounds = (items + slots - 1) / slots;
+                const double fill = static_cast<double>(items) / static_cast<double>(rounds * slots);
+                const double score = fill - 0.004 * s;
+                if (score > best_score) { best_score = score; best_s = s; }
+            }
+            a.kb_per_split = (num_kb + best_s - 1) / best_s;
             a.k_splits = (num_kb + a.kb_per_split - 1) / a.kb_per_split;
         } else if (N <= 128 || tiles256 < sm_count()) {
             BN = 128;

@@ -55,3 +55,13 @@ def test_fused_adamw_grad_scale():
     o2.step()
     for a, b in zip(ours, ref):
         torch.testing.assert_close(a.data, b.data, rtol=2e-6, atol=2e-7)
+
+
+def test_device_prefetcher_yields_batches_in_order():
+    from b200fm.data import DevicePrefetcher
+    host = [{"rgb": {"tensor": torch.full((4, 8), float(i)).pin_memory()}, "cap": {"tensor": torch.arange(5) + i}} for i in range(5)]
+    seen = []
+    for batch in DevicePrefetcher(host, "cuda", depth=2):
+        assert batch["rgb"]["tensor"].is_cuda
+        seen.append((float(batch["rgb"]["tensor"][0, 0]), int(batch["cap"]["tensor"][0])))
+    assert seen == [(float(i), i) for i in range(5)]

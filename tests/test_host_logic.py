@@ -114,3 +114,14 @@ def test_bench_reference_arm_contract_under_torchrun_world2():
     j = json.loads(lines[0])
     assert j["impl"] == "reference" and j["metric"] == "tokens_per_sec" and j["value"] > 0 and j["n_gpus"] == 2
     assert j["cpu_baseline"]["kind"] == "port" and j["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_device_prefetcher_order_cpu_fallback_refused():
+    """DevicePrefetcher is CUDA-only plumbing: constructing it without a GPU must fail loudly (no silent CPU path)."""
+    import pytest
+    import torch
+    from b200fm.data import DevicePrefetcher
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(Exception):
+        DevicePrefetcher([], "cuda")
