@@ -65,13 +65,23 @@ int b200fm_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const f
                          const float* rstd, const float* dres, float* dx_out, void* dx_bf16, float* dgamma, float* dbeta,
                          int rows, int D, void* stream);
 
+/* Per-head LayerNorm over head_dim 64 on q / k (qk_norm presets: NormAttention / NormCrossAttention, fm_utils.py:222-307).
+ * x bf16 [rows, ldx], head h = columns [h*64, h*64+64) (may be a column slice of a packed qkv); y bf16 [rows, ldy];
+ * stats fp32 [rows, H, 2] = (mean, rstd).  Backward: dx bf16, dgamma / dbeta fp32 [64] ACCUMULATED into (may be NULL).     */
+int b200fm_headnorm_fwd(const void* x, long long ldx, const float* gamma, const float* beta, void* y, long long ldy, float* stats,
+                        long long rows, int H, float eps, void* stream);
+int b200fm_headnorm_bwd(const void* dy, long long lddy, const void* x, long long ldx, const float* gamma, const float* stats, void* dx,
+                        long long lddx, float* dgamma, float* dbeta, long long rows, int H, void* stream);
+
 /* ---- fused multi-head attention (fourm/models/fm_utils.py:160-180, 197-219; vq/models/vit_models.py:165-197) --
  * q rows [B*Nq, ldq], k/v rows [B*Nk, ldk/ldv] bf16, head h occupies columns [h*64, h*64+64) from each base pointer
  * (so q/k/v may alias one packed qkv buffer).  mask: uint8/bool, 1 = masked (reference convention), addressed as
  * mask[b*mask_b_stride + i*mask_q_stride + j]; NULL = no mask.  Masked scores are filled with -FLT_MAX-like
  * finite value (fully masked rows -> uniform attention, like masked_fill(-finfo.max)).
  * out bf16 [B*Nq, ldo]; lse ("stats") fp32 [B, H, Nq, 2] = (row max of s*scale*log2e, 1/rowsum), saved for backward.
- * head_dim is fixed at 64.  attention_bwd needs dsum_ws: fp32 [B, H, Nq] scratch (receives rowsum(dO o O)).                  */
+ * head_dim is fixed at 64.  attention_fwd: Nk <= 256 keeps all keys of a (b, h, 128-query) item resident; Nk > 256 (the
+ * generation callers, generate.py:407-445, 886-913) streams 128-key tiles with the running-max rescale.  attention_bwd:
+ * Nq, Nk <= 256; needs dsum_ws: fp32 [B, H, Nq] scratch (receives rowsum(dO o O)).                                           */
 int b200fm_attention_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                          const uint8_t* mask, long long mask_b_stride, long long mask_q_stride, void* out, long long ldo,
                          float* lse, int B, int H, int Nq, int Nk, float scale, void* stream);

@@ -330,6 +330,35 @@ class AttentionFn(torch.autograd.Function):
         return dq, dk, dv, None, None, None, None, None, None
 
 
+class HeadNormFn(torch.autograd.Function):
+    """LayerNorm over head_dim on every (row, head) of q or k (fm_utils.py:244-245, 290-291; qk_norm presets)."""
+
+    @staticmethod
+    def forward(ctx, x, H, weight, bias, eps):
+        y, stats = ops.headnorm_fwd(x, H, weight, bias, eps)
+        ctx.save_for_backward(x, stats, weight)
+        ctx.H = H
+        ctx.bias_grad = bias is not None and bias.requires_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stats, weight = ctx.saved_tensors
+        if dy.dtype != torch.bfloat16 or dy.stride(1) != 1:
+            dy = dy.to(torch.bfloat16).contiguous()
+        dgamma = zeros_f32(64, x.device) if weight.requires_grad else None
+        dbeta = zeros_f32(64, x.device) if ctx.bias_grad else None
+        dx = ops.headnorm_bwd(dy, x, weight, stats, ctx.H, dgamma, dbeta)
+        return dx, None, dgamma, dbeta, None
+
+
+def head_norm(x, H, norm):
+    """x bf16 [R, H*64] (may be a column slice of a packed qkv) through `norm` = LayerNorm(head_dim)."""
+    if tuple(norm.weight.shape) != (64,):
+        raise NotImplementedError("q/k LayerNorm is implemented for head_dim 64 (every reference preset)")
+    return HeadNormFn.apply(x, H, norm.weight, getattr(norm, "bias", None), float(norm.eps))
+
+
 def attention(q, k, v, mask, B, H, Nq, Nk, scale):
     return AttentionFn.apply(q, k, v, mask, B, H, Nq, Nk, scale)
 

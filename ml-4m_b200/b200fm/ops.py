@@ -155,6 +155,29 @@ def _mask_args(mask, B, Nq, Nk):
     return mask, mask.data_ptr(), bs, qs
 
 
+def headnorm_fwd(x, H, gamma, beta, eps):
+    """Per-head LayerNorm over head_dim 64: x bf16 [R, >=H*64] view (unit inner stride) -> (y bf16 [R, H*64], stats [R, H, 2])."""
+    _need_cuda(x, gamma, beta)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1 and x.shape[1] == H * 64
+    R = x.shape[0]
+    y = torch.empty(R, H * 64, device=x.device, dtype=torch.bfloat16)
+    stats = torch.empty(R, H, 2, device=x.device, dtype=torch.float32)
+    lib.call("b200fm_headnorm_fwd", _ptr(x), x.stride(0), _ptr(gamma), _ptr(beta), _ptr(y), y.stride(0), _ptr(stats), R, H, float(eps),
+             _stream())
+    return y, stats
+
+
+def headnorm_bwd(dy, x, gamma, stats, H, dgamma=None, dbeta=None):
+    """dx bf16 [R, H*64]; dgamma / dbeta fp32 [64] are accumulated into when given."""
+    _need_cuda(dy, x, gamma, stats)
+    assert dy.dtype == torch.bfloat16 and dy.stride(1) == 1 and x.stride(1) == 1
+    R = x.shape[0]
+    dx = torch.empty(R, H * 64, device=x.device, dtype=torch.bfloat16)
+    lib.call("b200fm_headnorm_bwd", _ptr(dy), dy.stride(0), _ptr(x), x.stride(0), _ptr(gamma), _ptr(stats), _ptr(dx), dx.stride(0),
+             _ptr(dgamma), _ptr(dbeta), R, H, _stream())
+    return dx
+
+
 def attention_fwd(q, k, v, B, H, Nq, Nk, mask=None, scale=None):
     """q [B*Nq, >=H*64], k/v [B*Nk, >=H*64] bf16 views with unit inner stride (may be column slices of a packed qkv).
     Returns (out bf16 [B*Nq, H*64], stats fp32 [B, H, Nq, 2])."""

@@ -278,6 +278,11 @@ static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const C
     return 0;
 }
 
+// attention_fwd_long.cu: streamed-key variant for Nk > 256
+int launch_attention_fwd_long(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const uint8_t* mask,
+                              long long mask_b_stride, long long mask_q_stride, __nv_bfloat16* out, long long ldo, float* stats, int B,
+                              int H, int Nq, int Nk, float scale_log2, cudaStream_t stream);
+
 }  // namespace b200fm
 
 using namespace b200fm;
@@ -288,7 +293,7 @@ extern "C" int b200fm_attention_fwd(const void* q, long long ldq, const void* k,
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (B == 0 || H == 0 || Nq == 0) return 0;
     B200FM_CHECK(q && k && v && out, "attention_fwd: null pointer");
-    B200FM_CHECK(Nk >= 1 && Nk <= 256, "attention_fwd: Nk=%d outside the resident-key range [1, 256]", Nk);
+    B200FM_CHECK(Nk >= 1, "attention_fwd: Nk=%d", Nk);
     B200FM_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "attention_fwd: row strides must be multiples of 8 elements");
     B200FM_CHECK((reinterpret_cast<uintptr_t>(out) & 15) == 0, "attention_fwd: out must be 16-byte aligned");
     CUtensorMap tq, tk, tv;
@@ -296,6 +301,9 @@ extern "C" int b200fm_attention_fwd(const void* q, long long ldq, const void* k,
     if ((rc = make_tmap_3d(&tq, q, TmapDtype::BF16, (uint64_t)H * 64, Nq, B, (uint64_t)ldq * 2, (uint64_t)Nq * ldq * 2, 64, 128, true))) return rc;
     if ((rc = make_tmap_3d(&tk, k, TmapDtype::BF16, (uint64_t)H * 64, Nk, B, (uint64_t)ldk * 2, (uint64_t)Nk * ldk * 2, 64, 128, true))) return rc;
     if ((rc = make_tmap_3d(&tv, v, TmapDtype::BF16, (uint64_t)H * 64, Nk, B, (uint64_t)ldv * 2, (uint64_t)Nk * ldv * 2, 64, 128, true))) return rc;
+    if (Nk > 256)
+        return launch_attention_fwd_long(tq, tk, tv, mask, mask_b_stride, mask_q_stride, reinterpret_cast<__nv_bfloat16*>(out), ldo, stats, B, H,
+                                         Nq, Nk, scale * 1.4426950408889634f, stream);
     AttnFwdArgs a;
     a.mask = mask; a.mask_b_stride = mask_b_stride; a.mask_q_stride = mask_q_stride;
     a.out = reinterpret_cast<__nv_bfloat16*>(out); a.ldo = ldo; a.stats = stats;

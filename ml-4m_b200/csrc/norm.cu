@@ -141,7 +141,80 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, c
     }
 }
 
+// ---- per-head LayerNorm over head_dim = 64 (qk_norm presets: NormAttention / NormCrossAttention, fm_utils.py:244-245, 290-291)
+// x bf16 [rows, ldx]: head h occupies columns [h*64, h*64+64) (x may be a column slice of a packed qkv buffer);
+// y bf16 [rows, ldy] = bf16(LN_fp32(x) * gamma + beta) -- F.layer_norm under autocast computes in fp32, the following
+// q @ k^T casts to bf16.  One warp per (row, head), two elements per lane, statistics kept for the backward.
+__global__ void __launch_bounds__(256)
+headnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    __nv_bfloat16* __restrict__ y, long long ldy, float2* __restrict__ stats, long long rows, int H, float eps) {
+    pdl_enter();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float g0 = gamma[2 * lane], g1 = gamma[2 * lane + 1];
+    const float b0 = beta ? beta[2 * lane] : 0.f, b1 = beta ? beta[2 * lane + 1] : 0.f;
+    const long long total = rows * H;
+    for (long long i = static_cast<long long>(blockIdx.x) * 8 + warp; i < total; i += static_cast<long long>(gridDim.x) * 8) {
+        const long long row = i / H;
+        const int h = static_cast<int>(i % H);
+        const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + row * ldx + h * 64 + 2 * lane));
+        float s = v.x + v.y;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * (1.0f / 64.0f);
+        const float d0 = v.x - mean, d1 = v.y - mean;
+        float q = d0 * d0 + d1 * d1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q * (1.0f / 64.0f) + eps);
+        *reinterpret_cast<uint32_t*>(y + row * ldy + h * 64 + 2 * lane) = pack_bf16x2(d0 * rstd * g0 + b0, d1 * rstd * g1 + b1);
+        if (lane == 0 && stats) stats[i] = make_float2(mean, rstd);
+    }
+}
+
+// dy bf16 [rows, lddy] -> dx bf16 [rows, lddx]; dgamma / dbeta fp32 [64] are ACCUMULATED into (may be NULL)
+__global__ void __launch_bounds__(256)
+headnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const __nv_bfloat16* __restrict__ x, long long ldx,
+                    const float* __restrict__ gamma, const float2* __restrict__ stats, __nv_bfloat16* __restrict__ dx, long long lddx,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int H) {
+    pdl_enter();
+    __shared__ float red[8][128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float g0 = gamma[2 * lane], g1 = gamma[2 * lane + 1];
+    float ag0 = 0.f, ag1 = 0.f, ab0 = 0.f, ab1 = 0.f;
+    const long long total = rows * H;
+    for (long long i = static_cast<long long>(blockIdx.x) * 8 + warp; i < total; i += static_cast<long long>(gridDim.x) * 8) {
+        const long long row = i / H;
+        const int h = static_cast<int>(i % H);
+        const float2 st = stats[i];
+        const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + row * ldx + h * 64 + 2 * lane));
+        const float2 d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dy + row * lddy + h * 64 + 2 * lane));
+        const float xh0 = (v.x - st.x) * st.y, xh1 = (v.y - st.x) * st.y;
+        const float e0 = d.x * g0, e1 = d.y * g1;
+        float c1 = e0 + e1, c2 = e0 * xh0 + e1 * xh1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+            c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+        }
+        c1 *= (1.0f / 64.0f); c2 *= (1.0f / 64.0f);
+        *reinterpret_cast<uint32_t*>(dx + row * lddx + h * 64 + 2 * lane) =
+            pack_bf16x2(st.y * (e0 - c1 - xh0 * c2), st.y * (e1 - c1 - xh1 * c2));
+        ag0 += d.x * xh0; ag1 += d.y * xh1; ab0 += d.x; ab1 += d.y;
+    }
+    red[warp][2 * lane] = ag0; red[warp][2 * lane + 1] = ag1;
+    red[warp][64 + 2 * lane] = ab0; red[warp][64 + 2 * lane + 1] = ab1;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        if (threadIdx.x < 64) { if (dgamma) atomicAdd(dgamma + threadIdx.x, t); }
+        else if (dbeta) atomicAdd(dbeta + threadIdx.x - 64, t);
+    }
+}
+
 }  // namespace b200fm
+
 
 using namespace b200fm;
 
@@ -198,6 +271,36 @@ extern "C" int b200fm_layernorm_bwd(const void* dy, int dy_is_bf16, const float*
         default: B200FM_CHECK(false, "layernorm_bwd: D=%d has no instantiation", D);
     }
 #undef LN_BWD
+    B200FM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200fm_headnorm_fwd(const void* x, long long ldx, const float* gamma, const float* beta, void* y, long long ldy,
+                                   float* stats, long long rows, int H, float eps, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (rows == 0 || H == 0) return 0;
+    B200FM_CHECK(x && gamma && y, "headnorm_fwd: null pointer");
+    B200FM_CHECK(ldx % 2 == 0 && ldy % 2 == 0 && (reinterpret_cast<uintptr_t>(x) & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 3) == 0,
+                 "headnorm_fwd: rows must be 4-byte aligned (even strides)");
+    const long long blocks = (rows * H + 7) / 8;
+    const int grid = static_cast<int>(blocks < 148 * 8 ? blocks : 148 * 8);
+    B200FM_LAUNCH(headnorm_fwd_kernel, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(x), ldx, gamma, beta,
+                  reinterpret_cast<__nv_bfloat16*>(y), ldy, reinterpret_cast<float2*>(stats), rows, H, eps);
+    B200FM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200fm_headnorm_bwd(const void* dy, long long lddy, const void* x, long long ldx, const float* gamma, const float* stats,
+                                   void* dx, long long lddx, float* dgamma, float* dbeta, long long rows, int H, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (rows == 0 || H == 0) return 0;
+    B200FM_CHECK(dy && x && gamma && stats && dx, "headnorm_bwd: null pointer");
+    B200FM_CHECK(lddy % 2 == 0 && ldx % 2 == 0 && lddx % 2 == 0, "headnorm_bwd: strides must be even");
+    const long long blocks = (rows * H + 7) / 8;
+    const int grid = static_cast<int>(blocks < 148 * 4 ? blocks : 148 * 4);
+    B200FM_LAUNCH(headnorm_bwd_kernel, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(dy), lddy,
+                  reinterpret_cast<const __nv_bfloat16*>(x), ldx, gamma, reinterpret_cast<const float2*>(stats),
+                  reinterpret_cast<__nv_bfloat16*>(dx), lddx, dgamma, dbeta, rows, H);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }

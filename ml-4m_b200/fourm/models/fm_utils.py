@@ -242,8 +242,8 @@ def _check_attn_support(mod, C):
 
 
 class NormAttention(Attention):
-    """Self-attention with LayerNorm on q and k per head (reference fm_utils.py:222-261; qk_norm presets).
-    API kept; the fused kernel has no per-head q/k LayerNorm prologue yet."""
+    """Self-attention with LayerNorm on q and k per head (reference fm_utils.py:222-261; qk_norm presets): the packed qkv GEMM,
+    a per-head LayerNorm kernel on the q and k column slices, then the fused attention kernel."""
 
     def __init__(self, dim, num_heads=8, qkv_bias=False, proj_bias=True, norm_layer=nn.LayerNorm, attn_drop=0., proj_drop=0.,
                  allow_zero_attn=False):
@@ -253,11 +253,16 @@ class NormAttention(Attention):
         self.k_norm = norm_layer(head_dim)
 
     def attend(self, x, mask=None):
-        raise NotImplementedError("qk_norm attention (swiglu_qknorm presets) is not implemented on the B200 path yet")
+        B, N, C = x.shape
+        _check_attn_support(self, C)
+        qkv = _linear(self.qkv, x).reshape(B * N, 3 * C)
+        q = BF.head_norm(qkv[:, :C], self.num_heads, self.q_norm)
+        k = BF.head_norm(qkv[:, C:2 * C], self.num_heads, self.k_norm)
+        return BF.attention(q, k, qkv[:, 2 * C:], _prep_mask(mask, B, N, N), B, self.num_heads, N, N, self.scale).view(B, N, C)
 
 
 class NormCrossAttention(CrossAttention):
-    """Cross-attention with q/k LayerNorm (reference fm_utils.py:264-307).  API kept, see NormAttention."""
+    """Cross-attention with q/k LayerNorm (reference fm_utils.py:264-307), see NormAttention."""
 
     def __init__(self, dim, num_heads=8, qkv_bias=False, proj_bias=True, norm_layer=nn.LayerNorm, attn_drop=0., proj_drop=0.,
                  allow_zero_attn=False):
@@ -267,7 +272,13 @@ class NormCrossAttention(CrossAttention):
         self.k_norm = norm_layer(head_dim)
 
     def attend(self, x, context, mask=None):
-        raise NotImplementedError("qk_norm attention (swiglu_qknorm presets) is not implemented on the B200 path yet")
+        B, N, C = x.shape
+        M = context.shape[1]
+        _check_attn_support(self, C)
+        q = BF.head_norm(_linear(self.q, x).reshape(B * N, C), self.num_heads, self.q_norm)
+        kv = _linear(self.kv, context).reshape(B * M, 2 * C)
+        k = BF.head_norm(kv[:, :C], self.num_heads, self.k_norm)
+        return BF.attention(q, k, kv[:, C:], _prep_mask(mask, B, N, M), B, self.num_heads, N, M, self.scale).view(B, N, C)
 
 
 def _residual_ok(block):

@@ -257,12 +257,22 @@ def _sdpa(q, k, v, mask, scale):
     return attn @ v
 
 
+def _qk_norm(q, k, sd, pfx):
+    """fm_utils.py:244-245, 290-291 (NormAttention / NormCrossAttention): LayerNorm over head_dim on q and k when the
+    state dict carries q_norm / k_norm (qk_norm presets, fm.py:1059-1130); identity otherwise."""
+    if pfx + "q_norm.weight" not in sd:
+        return q, k
+    return (layer_norm(q, sd[pfx + "q_norm.weight"], sd.get(pfx + "q_norm.bias")),
+            layer_norm(k, sd[pfx + "k_norm.weight"], sd.get(pfx + "k_norm.bias")))
+
+
 def self_attention(x, sd, pfx, heads, mask=None):
     """fm_utils.py:147-180 Attention.forward; mask [B,1|N,N]."""
     B, N, C = x.shape
     qkv = F.linear(x, sd[pfx + "qkv.weight"], sd.get(pfx + "qkv.bias"))
     qkv = qkv.reshape(B, N, 3, heads, C // heads).permute(2, 0, 3, 1, 4)
-    o = _sdpa(qkv[0], qkv[1], qkv[2], None if mask is None else mask[:, None], (C // heads) ** -0.5)
+    q, k = _qk_norm(qkv[0], qkv[1], sd, pfx)
+    o = _sdpa(q, k, qkv[2], None if mask is None else mask[:, None], (C // heads) ** -0.5)
     o = o.transpose(1, 2).reshape(B, N, C)
     return F.linear(o, sd[pfx + "proj.weight"], sd.get(pfx + "proj.bias"))
 
@@ -274,7 +284,8 @@ def cross_attention(x, ctx, sd, pfx, heads, mask=None):
     q = F.linear(x, sd[pfx + "q.weight"], sd.get(pfx + "q.bias")).reshape(B, N, heads, C // heads).permute(0, 2, 1, 3)
     kv = F.linear(ctx, sd[pfx + "kv.weight"], sd.get(pfx + "kv.bias"))
     kv = kv.reshape(B, M, 2, heads, C // heads).permute(2, 0, 3, 1, 4)
-    o = _sdpa(q, kv[0], kv[1], None if mask is None else mask[:, None], (C // heads) ** -0.5)
+    q, k = _qk_norm(q, kv[0], sd, pfx)
+    o = _sdpa(q, k, kv[1], None if mask is None else mask[:, None], (C // heads) ** -0.5)
     o = o.transpose(1, 2).reshape(B, N, C)
     return F.linear(o, sd[pfx + "proj.weight"], sd.get(pfx + "proj.bias"))
 

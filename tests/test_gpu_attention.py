@@ -58,6 +58,40 @@ def test_attention_fwd(B, H, Nq, Nk, mk):
     torch.testing.assert_close(out.float().cpu(), ref, rtol=2e-2, atol=2e-2)
 
 
+LONG_CASES = [(1, 2, 196, 300), (2, 3, 64, 513), (1, 4, 290, 1900), (2, 2, 257, 257), (1, 32, 256, 1024)]
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk", LONG_CASES)
+@pytest.mark.parametrize("mk", ["none", "key", "dense", "causal"])
+def test_attention_fwd_streamed_keys(B, H, Nq, Nk, mk):
+    """Nk > 256 (generation callers, generate.py:407-445 / 886-913): keys streamed in 128-key tiles with the running-max rescale.
+    'key' has a fully masked sample, 'dense' fully masked rows and tiles whose keys are all masked for a row, 'causal' is the AR
+    decoder mask."""
+    from b200fm import ops
+    q, k, v = _inputs(B, H, Nq, Nk, 11, packed=False)
+    if mk == "causal":
+        mask = torch.triu(torch.ones(Nq, Nk, dtype=torch.bool), diagonal=1 + max(0, Nk - Nq))[None].expand(B, Nq, Nk).contiguous()
+    else:
+        mask = _mask(mk, B, Nq, Nk, 12)
+        if mk == "dense":
+            mask[:, 1, : min(Nk, 256)] = True           # first two key tiles fully masked for row 1, later tiles decide
+    out, stats = ops.attention_fwd(q.cuda(), k.cuda(), v.cuda(), B, H, Nq, Nk, None if mask is None else mask.cuda())
+    torch.cuda.synchronize()
+    ref = _ref(q, k, v, B, H, Nq, Nk, mask)
+    torch.testing.assert_close(out.float().cpu(), ref, rtol=2e-2, atol=2e-2)
+    # saved statistics: 1/sum and the log2-domain row max reproduce the oracle's log-sum-exp
+    qf = q.float().reshape(B, Nq, H, 64).permute(0, 2, 1, 3)
+    kf = k.float().reshape(B, Nk, H, 64).permute(0, 2, 1, 3)
+    s = (qf @ kf.transpose(-1, -2)) * (64 ** -0.5)
+    if mask is not None:
+        s = s.masked_fill(mask[:, None], -torch.finfo(torch.float32).max)
+    lse_ref = torch.logsumexp(s, dim=-1)
+    st = stats.cpu()
+    lse = (st[..., 0] - torch.log2(st[..., 1])) * 0.6931471805599453
+    ok = lse_ref > -1e30                                   # fully masked rows: the reference's lse is -finfo.max + log(Nk)
+    torch.testing.assert_close(lse[ok], lse_ref[ok], rtol=1e-3, atol=1e-2)
+
+
 def test_attention_fwd_full_size_cfg2():
     """cfg-2 size (B=128, h=12, N=128) -- linearity property in V and agreement on a strided subsample."""
     from b200fm import ops

@@ -155,3 +155,54 @@ def test_scan_kats_torch_and_c():
     sc = V.scan_scores(z, s["l2_embed"], False)
     assert float((sc.gather(1, idx[:, None]) - sc.gather(1, s["l2_idx"][:, None])).abs()[bad].max() if bad.any() else 0.0) <= 1e-4
     assert bad.sum() <= 2
+
+
+# ---- qk_norm presets (a13: NormAttention / NormCrossAttention, fm_utils.py:222-307) ---------------------------------------------
+@pytest.fixture(scope="module")
+def tiny_qknorm():
+    gold = H.load_golden("fourm_tiny_qknorm_golden.pt")
+    specs = O.mod7_specs()
+    sd = H.fill_fourm_buffers(H.golden_state_dict(gold), specs, 384)
+    for k, c in gold["weight_checksums"].items():
+        assert abs(float(sd[k].double().sum()) - c) <= 1e-6 * max(1.0, abs(c)), f"fixture weight drift in {k}"
+    assert "encoder.0.attn.q_norm.weight" in sd and "decoder.0.cross_attn.k_norm.weight" in sd
+    return gold, specs, sd
+
+
+@pytest.mark.parametrize("tag", ["fp32_128", "bf16_128"])
+def test_fourm_qknorm_forward_matches_reference(tiny_qknorm, tag):
+    gold, specs, sd = tiny_qknorm
+    c = gold["cases"][tag]
+    batch = O.synthetic_mod7_batch(2, seed=c["batch_seed"], extra_valid=c["extra_valid"])
+    cfg = O.PRESETS[gold["model"]]
+    with torch.autocast("cpu", dtype=torch.bfloat16, enabled=c["amp"]):
+        loss, mod_loss = O.fourm_forward(sd, cfg, specs, batch, c["N"], c["M"], c["decoder_order"], "mod")
+        logits = O.fourm_forward(sd, cfg, specs, batch, c["N"], c["M"], c["decoder_order"], return_logits=True)
+    tol = 2e-3 if c["amp"] else 1e-5
+    assert abs(float(loss) - float(c["loss"])) <= tol
+    for m, v in c["mod_loss"].items():
+        assert abs(float(mod_loss[m]) - float(v)) <= tol, m
+    for m, v in c["logits_slices"].items():
+        torch.testing.assert_close(logits[m][:, :4, :32].float(), v, rtol=tol * 10, atol=tol * 10)
+
+
+def test_fourm_qknorm_backward_matches_reference(tiny_qknorm):
+    gold, specs, sd = tiny_qknorm
+    c = gold["cases"]["fp32_128"]
+    names = set(gold["param_names"])
+    sdg = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in sd.items()}
+    for m in specs:
+        e, d = f"encoder_embeddings.{m}.mod_emb", f"decoder_embeddings.{m}.mod_emb"
+        if e in sdg and d in sdg:
+            sdg[d] = sdg[e]
+        t, l = f"decoder_embeddings.{m}.token_emb.weight", f"decoder_embeddings.{m}.to_logits.weight"
+        if t in sdg:
+            sdg[l] = sdg[t]
+    batch = O.synthetic_mod7_batch(2, seed=c["batch_seed"])
+    loss, _ = O.fourm_forward(sdg, O.PRESETS[gold["model"]], specs, batch, c["N"], c["M"], c["decoder_order"])
+    loss.backward()
+    for k in ("encoder.0.attn.q_norm.weight", "encoder.3.attn.k_norm.weight", "decoder.0.cross_attn.q_norm.weight",
+              "decoder.2.self_attn.q_norm.weight", "encoder.0.attn.qkv.weight"):
+        ref_norm = c["grads"]["norm"][k]
+        assert abs(float(sdg[k].grad.norm()) - ref_norm) <= 1e-4 * max(ref_norm, 1e-3), k
+        torch.testing.assert_close(sdg[k].grad.flatten()[:64], c["grads"]["slices"][k], rtol=1e-3, atol=1e-6)
