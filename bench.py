@@ -90,6 +90,15 @@ def cpu_threads():
     return int(env) if env else min(os.cpu_count() or 1, 16)
 
 
+def gemm_traffic_per_launch():
+    """DRAM bytes (read + write) per GEMM launch of a 4M-B step, from the committed ncu capture (never measured in this process)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_step_traffic.json")) as f:
+            return float(json.load(f)["gemm"]["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def cpu_reference_steps(steps, warmup, sample_B, n_tok, threads=None):
     """Times fwd+bwd of the oracle restatement of FourM.forward (4M-B mod7, fp32, host threads per cpu_threads())."""
     import random
@@ -228,7 +237,8 @@ def run_b200_arm(args):
     net = model
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False,
-                                                        gradient_as_bucket_view=True, broadcast_buffers=False)
+                                                        gradient_as_bucket_view=True, broadcast_buffers=False,
+                                                        bucket_cap_mb=int(os.environ.get("B200FM_DDP_BUCKET_MB", "25")))
     import random
     random.seed(rank)
     a, b, c, d = budgets_for(n_tok)
@@ -336,7 +346,8 @@ def run_b200_arm(args):
                     model_tflops_per_gpu=model_tflops / world,
                     frac_of_bf16_peak=model_tflops / world / peaks["bf16"],
                     roofline=dict(bound="tensor", kernel="gemm_kernel<BN,LAYOUT,EPI> (all tcgen05 GEMM launches of a step)", achieved=achieved,
-                                  peak=peaks["bf16"], unit="TFLOP/s", frac=achieved / peaks["bf16"], traffic=None, peak_source=peaks["src"],
+                                  peak=peaks["bf16"], unit="TFLOP/s", frac=achieved / peaks["bf16"], traffic=gemm_traffic_per_launch(),
+                                  traffic_unit="bytes/launch (dram read+write, ncu: profiles/r1_step_traffic.json)", peak_source=peaks["src"],
                                   launches_per_step=n_gemm // 2, gemm_ms_per_step=gemm_ms / 2),
                     clocks=clocks)
         if cpu is not None:

@@ -182,3 +182,29 @@ def test_large_config_shapes_cfg3():
     assert torch.isfinite(loss) and 8.0 < float(loss) < 12.0
     g = model.encoder[3].mlp.fc2.weight.grad
     assert g is not None and g.shape == (1024, 2730) and torch.isfinite(g).all() and float(g.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("N,M,causal", [(600, 196, False), (1900, 64, True), (257, 290, True)])
+def test_generation_shaped_stack_calls(tiny, N, M, causal):
+    """a19: the calls fourm/models/generate.py makes on the model (forward_encoder on a data-dependent N > 256 context in eval
+    mode, generate.py:407-445; forward_decoder with sa_mask all-False (MaskGIT / ROAR) or causal (AR loop, :886-913) and
+    cross-attention over all N context keys) against the oracle stacks on the same weights, fp32."""
+    gold, specs, sd, model = tiny
+    cfg = O.PRESETS[gold["model"]]
+    g = torch.Generator().manual_seed(N + M)
+    B, D = 1, 384
+    x = torch.randn(B, N, D, generator=g)
+    y = torch.randn(B, M, D, generator=g)
+    enc_mask = torch.zeros(B, 1, N, dtype=torch.bool)
+    enc_mask[:, :, N - 37:] = True                                        # padded tail of the context
+    sa_mask = torch.triu(torch.ones(M, M, dtype=torch.bool), diagonal=1)[None] if causal else torch.zeros(B, M, M, dtype=torch.bool)
+    model.eval()
+    with torch.no_grad():
+        ctx = model.forward_encoder(x.cuda(), enc_mask.cuda())
+        out = model.forward_decoder(y.cuda(), ctx, enc_mask.cuda(), sa_mask.cuda())
+    model.train()
+    ctx_ref = O.run_encoder(x, sd, cfg, enc_mask)
+    out_ref = O.run_decoder(y, ctx_ref, sd, cfg, enc_mask, sa_mask)
+    # 6+6 layers of bf16 contractions against an fp32 oracle on unit-variance activations (LayerNorm'd outputs, O(1) entries)
+    torch.testing.assert_close(ctx.float().cpu(), ctx_ref, rtol=5e-2, atol=5e-2)
+    torch.testing.assert_close(out.float().cpu(), out_ref, rtol=5e-2, atol=5e-2)
