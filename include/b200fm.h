@@ -201,6 +201,16 @@ int b200fm_vq_argmax(const float* z, const float* codebook, int64_t* idx_out, fl
 int b200fm_vq_argmax_host(const float* z_host, const float* codebook_dev, int64_t* idx_host, long long n, int K, int d,
                           int cosine, void* stream);
 
+/* Training-side codebook statistics (quantize_lucid.py:404-419 / 286-292) without the one-hot [n, K]: bins[idx[r]] += 1,
+ * embed_sum[idx[r], :] += (cosine ? l2norm(z[r]) : z[r]).  bins fp32 [K], embed_sum fp32 [K, d] are ACCUMULATED into (zero
+ * them first; they may be two slices of one packed buffer so that sync_codebook needs a single all-reduce).               */
+int b200fm_vq_ema_stats(const float* z, const long long* idx, long long n, int K, int d, int cosine, float* bins, float* embed_sum,
+                        void* stream);
+/* Cosine codebook EMA (quantize_lucid.py:413-425), in place: cluster_size = cs*decay + bins*(1-decay);
+ * embed[k] = embed[k]*decay + (bins[k] == 0 ? l2norm(embed[k]) : l2norm(embed_sum[k] / bins[k])) * (1-decay).             */
+int b200fm_vq_ema_update_cosine(float* embed, float* cluster_size, const float* bins, const float* embed_sum, int K, int d, float decay,
+                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

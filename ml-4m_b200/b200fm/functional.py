@@ -186,6 +186,34 @@ class LinearFn(torch.autograd.Function):
         return (dx.view(ctx.in_shape) if dx is not None else None), dw, db
 
 
+class PatchEmbedFn(torch.autograd.Function):
+    """tokens(fp32) = pos + bf16(patches W_lin^T + b): the k = s = P Conv2d patch projection of the ViT tokenizers
+    (vq/models/vit_models.py:482-489) as patchify + one GEMM with the positional rows in the epilogue.  conv_weight is the
+    module's [O, C, P, P] parameter (state_dict contract); patches are laid out '(ph pw c)', so W_lin = W.permute(0, 2, 3, 1).
+    Backward: dW (TN GEMM on the saved bf16 patches, mapped back to the conv layout), db; images get no gradient."""
+
+    @staticmethod
+    def forward(ctx, img, conv_weight, conv_bias, pos_rows, w_lin_bf16, patch):
+        patches = ops.patchify(img.float().contiguous(), patch)                       # [B*N, P*P*C] bf16
+        bias = conv_bias.detach().float() if conv_bias is not None else None
+        out = ops.gemm(patches, w_lin_bf16, epilogue=ops.EPI_RESID, bias=bias, resid=pos_rows)
+        ctx.save_for_backward(patches)
+        ctx.wshape, ctx.has_bias = conv_weight.shape, conv_bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (patches,) = ctx.saved_tensors
+        d2 = _to_bf16_2d(dout)
+        O, C, P, _ = ctx.wshape
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            dw = ops.gemm(d2, patches, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32).view(O, P, P, C).permute(0, 3, 1, 2)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = ops.colsum_bf16(d2)
+        return None, dw, db, None, None, None
+
+
 class LinearF32Fn(torch.autograd.Function):
     """y(fp32) = x W^T : logits (decoder_embeddings.py:141-152) when the caller wants them materialised."""
 

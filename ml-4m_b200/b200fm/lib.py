@@ -57,6 +57,8 @@ SIGNATURES = {
     "b200fm_gather_i64": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p],
     "b200fm_scatter_rows_bf16": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "b200fm_scatter_add_rows": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
+    "b200fm_vq_ema_stats": [c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "b200fm_vq_ema_update_cosine": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p],
     "b200fm_headnorm_fwd": [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_int, c_float, c_void_p],
     "b200fm_headnorm_bwd": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "b200fm_adamw_multi": [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_void_p],

@@ -394,3 +394,22 @@ def scatter_add_rows(src_bf16, rows, dst, n):
 
 def scatter_rows_bf16(src, rows, dst, n):
     lib.call("b200fm_scatter_rows_bf16", _ptr(src), _ptr(rows), _ptr(dst), n, dst.shape[-1], _stream())
+
+
+def vq_ema_stats(flat, idx, K, cosine, stats=None):
+    """Packed codebook statistics [K * (d + 1)] fp32 = [bins | embed_sum (K x d)] of one batch (quantize_lucid.py:409-419)."""
+    _need_cuda(flat, idx)
+    n, d = flat.shape
+    assert flat.dtype == torch.float32 and flat.is_contiguous() and idx.dtype == torch.int64 and idx.numel() == n
+    if stats is None:
+        stats = torch.zeros(K * (d + 1), device=flat.device, dtype=torch.float32)
+    lib.call("b200fm_vq_ema_stats", _ptr(flat), _ptr(idx), n, K, d, int(bool(cosine)), _ptr(stats), stats.data_ptr() + 4 * K, _stream())
+    return stats
+
+
+def vq_ema_update_cosine(embed, cluster_size, stats, decay):
+    """In-place EMA of the cosine codebook buffers from the (all-reduced) packed statistics."""
+    K, d = embed.shape
+    assert embed.dtype == torch.float32 and embed.is_contiguous() and cluster_size.is_contiguous() and stats.numel() == K * (d + 1)
+    lib.call("b200fm_vq_ema_update_cosine", _ptr(embed), _ptr(cluster_size), _ptr(stats), stats.data_ptr() + 4 * K, K, d, float(decay),
+             _stream())

@@ -1,5 +1,6 @@
-"""Overlay of `fourm.vq` (apple/ml-4m): the tokenization path (VQ encoder + quantizer) is B200-native; decoders
-(VQVAE / DiVAE / VQControlNet, diffusion schedulers, UNets) keep resolving to the reference tree when it is on sys.path."""
+"""Overlay of `fourm.vq` (apple/ml-4m): the tokenization path (VQ encoder + quantizer) and the VQ-VAE training model (ViT decoder,
+codebook EMA) are B200-native; the diffusion decoders (DiVAE / VQControlNet, schedulers, UNets) keep resolving to the reference
+tree when it is on sys.path."""
 import os
 import pkgutil
 
@@ -7,12 +8,12 @@ import torch
 
 __path__ = pkgutil.extend_path(__path__, __name__)
 
-from .vqvae import VQ  # noqa: E402
+from .vqvae import VQ, VQVAE  # noqa: E402
 
 
 def __getattr__(name):
-    """VQVAE / DiVAE / VQControlNet live in the reference's vqvae.py (they need `diffusers`); import them lazily from there."""
-    if name in ("VQVAE", "DiVAE", "VQControlNet"):
+    """DiVAE / VQControlNet live in the reference's vqvae.py (they need `diffusers`); import them lazily from there."""
+    if name in ("DiVAE", "VQControlNet"):
         import importlib.util
         for p in __path__[1:]:
             f = os.path.join(p, "vqvae.py")
@@ -52,7 +53,8 @@ def get_image_tokenizer(tokenizer_id: str, tokenizers_root: str = './tokenizer_c
         sd = {k: v for k, v in ckpt['model'].items() if not (k.startswith('decoder') or k.startswith('post_quant'))}
         msg = model.load_state_dict(sd, strict=False)
     else:
-        model = __getattr__('VQVAE' if getattr(args, 'model_type', 'VQVAE') == 'VQVAE' else getattr(args, 'model_type'))(**kw)
+        model_type = getattr(args, 'model_type', 'VQVAE')
+        model = (VQVAE if model_type == 'VQVAE' else __getattr__(model_type))(**kw)
         msg = model.load_state_dict(ckpt['model'], strict=False)
     if verbose:
         print(msg)

@@ -188,11 +188,12 @@ class ViTEncoder(nn.Module):
     def tokens(self, x: torch.Tensor):
         """[B, C, H, W] -> fp32 token stream [B, N, D] after the transformer (and the post-MLP), plus (N_H, N_W)."""
         B, C, H, W = x.shape
+        train_proj = self.patch_proj and torch.is_grad_enabled() and self.proj.weight.requires_grad
         if self.patch_proj:
             assert (H % self.P_H == 0) and (W % self.P_W == 0), f'Image sizes {H}x{W} must be divisible by patch sizes {self.P_H}x{self.P_W}'
             assert self.P_H == self.P_W, "square patches only on the B200 path"
             N_H, N_W = H // self.P_H, W // self.P_W
-            patches = ops.patchify(x.float().contiguous(), self.P_H)                 # [B*N, P*P*C] bf16
+            patches = None if train_proj else ops.patchify(x.float().contiguous(), self.P_H)     # [B*N, P*P*C] bf16
         else:
             N_H, N_W = H, W
             patches = ops.cast_bf16(x.float().permute(0, 2, 3, 1).reshape(B * H * W, C).contiguous())
@@ -201,8 +202,12 @@ class ViTEncoder(nn.Module):
             pe = F.interpolate(pe, size=(N_H, N_W), mode='bicubic', align_corners=False)   # reference :486 (identity when sizes match)
         pe = pe.flatten(2).transpose(1, 2).float().expand(B, -1, -1).reshape(B * N_H * N_W, self.dim_tokens).contiguous()
         w = _ConvAsLinear.weight(self.proj)
-        bias = self.proj.bias.detach().float() if self.proj.bias is not None else None
-        t = ops.gemm(patches, w, epilogue=ops.EPI_RESID, bias=bias, resid=pe).view(B, N_H * N_W, self.dim_tokens)
+        if train_proj:
+            # tokenizer training (VQVAE.forward): same kernels, plus the weight / bias gradients of the patch projection
+            t = BF.PatchEmbedFn.apply(x, self.proj.weight, self.proj.bias, pe, w, self.P_H).view(B, N_H * N_W, self.dim_tokens)
+        else:
+            bias = self.proj.bias.detach().float() if self.proj.bias is not None else None
+            t = ops.gemm(patches, w, epilogue=ops.EPI_RESID, bias=bias, resid=pe).view(B, N_H * N_W, self.dim_tokens)
         t = self.blocks(t)
         if hasattr(self, 'post_mlp'):
             h = BF.layer_norm(t, self.norm_mlp.weight, self.norm_mlp.bias, self.norm_mlp.eps, True)
@@ -226,3 +231,70 @@ def _vit_factory(dim, depth, heads):
 vit_s_enc = _vit_factory(512, 8, 8)        # reference vit_models.py:664-692
 vit_b_enc = _vit_factory(768, 12, 12)      # :695-725
 vit_l_enc = _vit_factory(1024, 24, 16)     # :728-759
+
+
+class ViTDecoder(nn.Module):
+    """Latent feature map [B, dim_tokens, N_H, N_W] -> image [B, C, H, W] (reference vit_models.py:504-659): positional
+    embedding, the same transformer blocks as the encoder, optional Tanh post-MLP, a Linear to P*P*C per token and the
+    '(c ph pw)' un-patchify.  Tokenizer-training side (VQVAE.forward / decode_quant)."""
+
+    def __init__(self, *, out_channels: int = 3, patch_size: int = 16, resolution: int = 256, dim_tokens: int = 768, depth: int = 12,
+                 num_heads: int = 12, mlp_ratio: float = 4.0, qkv_bias: bool = True, drop_rate: float = 0.0, attn_drop_rate: float = 0.0,
+                 drop_path_rate: float = 0.0, norm_layer: nn.Module = partial(nn.LayerNorm, eps=1e-6), sincos_pos_emb: bool = True,
+                 learnable_pos_emb: bool = False, patch_proj: bool = True, post_mlp: bool = False, out_conv: bool = False, **ignore_kwargs):
+        super().__init__()
+        self.out_channels = out_channels
+        self.P_H, self.P_W = pair(patch_size)
+        self.H, self.W = pair(resolution)
+        self.dim_tokens, self.patch_proj = dim_tokens, patch_proj
+        assert (self.H % self.P_H == 0) and (self.W % self.P_W == 0), \
+            f'Image sizes {self.H}x{self.W} must be divisible by patch sizes {self.P_H}x{self.P_W}'
+        N_H, N_W = self.H // self.P_H, self.W // self.P_W
+        if sincos_pos_emb:
+            self.pos_emb = nn.Parameter(build_2d_sincos_posemb(h=N_H, w=N_W, embed_dim=dim_tokens), requires_grad=learnable_pos_emb)
+        else:
+            self.pos_emb = nn.Parameter(torch.zeros(1, dim_tokens, N_H, N_W))
+            trunc_normal_(self.pos_emb, std=0.02)
+        if drop_path_rate > 0.:
+            raise NotImplementedError("drop_path > 0 is not supported by the B200 ViT blocks")
+        self.blocks = nn.Sequential(*[Block(dim=dim_tokens, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, drop=drop_rate,
+                                            attn_drop=attn_drop_rate, drop_path=0., norm_layer=norm_layer) for _ in range(depth)])
+        if post_mlp:
+            self.norm_mlp = norm_layer(dim_tokens)
+            self.post_mlp = Mlp(dim_tokens, int(mlp_ratio * dim_tokens), act_layer=nn.Tanh)
+        self.out_proj = nn.Linear(dim_tokens, out_channels * self.P_H * self.P_W if patch_proj else out_channels)
+        if out_conv:
+            raise NotImplementedError("out_conv (ConvNeXt blocks after the decoder) is not on the B200 path")
+        _init_vit(self)
+
+    def get_num_layers(self) -> int:
+        return len(self.blocks)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        B, D, N_H, N_W = x.shape
+        t = x.flatten(2).transpose(1, 2).float()
+        pe = self.pos_emb
+        if pe.shape[-2:] != (N_H, N_W):
+            pe = F.interpolate(pe, size=(N_H, N_W), mode='bicubic', align_corners=False)
+        t = t + pe.flatten(2).transpose(1, 2).float()
+        t = self.blocks(t.contiguous())
+        if hasattr(self, 'post_mlp'):
+            h = BF.layer_norm(t, self.norm_mlp.weight, self.norm_mlp.bias, self.norm_mlp.eps, True)
+            t = self.post_mlp.forward_residual(h, t)
+        y = BF.LinearFn.apply(t, self.out_proj.weight, self.out_proj.bias)                # bf16, like nn.Linear under autocast
+        ph, pw = (self.P_H, self.P_W) if self.patch_proj else (1, 1)
+        y = y.view(B, N_H, N_W, self.out_channels, ph, pw).permute(0, 3, 1, 4, 2, 5)         # 'b (nh nw) (c ph pw) -> b c (nh ph) (nw pw)'
+        return y.reshape(B, self.out_channels, N_H * ph, N_W * pw)
+
+
+def _vit_dec_factory(dim, depth, heads):
+    def make(out_channels, patch_size=16, resolution=256, patch_proj=True, post_mlp=False, out_conv=False, **kw):
+        return ViTDecoder(out_channels=out_channels, patch_size=patch_size, resolution=resolution, dim_tokens=dim, depth=depth,
+                          num_heads=heads, mlp_ratio=4, qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6),
+                          patch_proj=patch_proj, post_mlp=post_mlp, out_conv=out_conv, **kw)
+    return make
+
+
+vit_s_dec = _vit_dec_factory(512, 8, 8)        # reference vit_models.py:762-792
+vit_b_dec = _vit_dec_factory(768, 12, 12)      # :795-825
+vit_l_dec = _vit_dec_factory(1024, 24, 16)     # :828-858

@@ -4,8 +4,9 @@ Drop-in for the inference surface of `fourm/vq/quantizers/quantize_lucid.py` (ap
 `CosineSimCodebook`, `EuclideanCodebook` keep their constructor arguments and buffer names (`embed`, `cluster_size`,
 `initted`, `embed_avg`) so tokenizer checkpoints load unchanged.  The reference computes a full fp32 [n, K] similarity
 matrix, an arg-max and a [n, K] one-hot (quantize_lucid.py:402-407 / 275-284); here one kernel scans the codebook with
-fp32 FMAs and returns indices (+ the codebook rows).  Training-time codebook maintenance (EMA update, dead-code expiry,
-k-means init: quantize_lucid.py:235-261, 286-299, 409-426) is not on the hot path and not implemented yet.
+fp32 FMAs and returns indices (+ the codebook rows).  Training mode adds the codebook maintenance of quantize_lucid.py:286-299 /
+409-426: per-code counts and latent sums by an index scatter kernel (no one-hot, no second GEMM), one packed all-reduce when
+the codebook is synchronised, the EMA in one pass over the codebook, dead-code expiry; k-means init is not implemented.
 """
 import torch
 import torch.nn as nn
@@ -33,6 +34,7 @@ class _Codebook(nn.Module):
         self.decay, self.codebook_size, self.kmeans_iters, self.eps = decay, codebook_size, kmeans_iters, eps
         self.threshold_ema_dead_code, self.code_replacement_policy = threshold_ema_dead_code, code_replacement_policy
         self.sample_codebook_temp, self.use_ddp, self.learnable_codebook = sample_codebook_temp, use_ddp, learnable_codebook
+        self._initted_seen = False
         if kmeans_init:
             embed = torch.zeros(codebook_size, dim)
         else:
@@ -56,11 +58,87 @@ class _Codebook(nn.Module):
         idx, quant = ops.vq_argmax(flat, self.embed.detach().float().contiguous(), cosine=self.cosine, want_quant=True)
         return quant.view(shape), idx.view(shape[:-1])
 
+    # ------------------------------------------------------------------ training-side maintenance (reference :263-301, :388-426)
+    def _ddp(self):
+        return self.use_ddp and torch.distributed.is_available() and torch.distributed.is_initialized()
+
+    @torch.no_grad()
+    def _ema_update(self, flat, idx):
+        """bins / per-code latent sums by scatter (no one-hot, no second GEMM), ONE packed all-reduce when the codebook is
+        synchronised, then the EMA of `cluster_size` and `embed` (cosine: one kernel; Euclidean: via `embed_avg`)."""
+        K, d = self.embed.shape
+        stats = ops.vq_ema_stats(flat, idx.reshape(-1), K, self.cosine)
+        if self._ddp():
+            torch.distributed.all_reduce(stats)
+        if self.cosine:
+            ops.vq_ema_update_cosine(self.embed.data, self.cluster_size, stats, self.decay)
+        else:
+            bins, esum = stats[:K], stats[K:].view(K, d)
+            self.cluster_size.mul_(self.decay).add_(bins, alpha=1 - self.decay)
+            self.embed_avg.mul_(self.decay).add_(esum, alpha=1 - self.decay)
+            total = self.cluster_size.sum()
+            smoothed = (self.cluster_size + self.eps) / (total + K * self.eps) * total
+            self.embed.data.copy_(self.embed_avg / smoothed.unsqueeze(1))
+
+    def _sample(self, samples, num):
+        """quantize_lucid.py:62-71 sample_vectors / :100-113 sample_vectors_distributed."""
+        def local(s, k):
+            n = s.shape[0]
+            ind = torch.randperm(n, device=s.device)[:k] if n >= k else torch.randint(0, n, (k,), device=s.device)
+            return s[ind]
+        if not self._ddp():
+            return local(samples, num)
+        dist = torch.distributed
+        world, rank = dist.get_world_size(), dist.get_rank()
+        sizes = torch.zeros(world, dtype=torch.long, device=samples.device)
+        sizes[rank] = samples.shape[0]
+        dist.all_reduce(sizes)
+        if rank == 0:       # multinomial split of `num` over the ranks, proportional to their sample counts (:75-98)
+            per = torch.distributions.Multinomial(total_count=num, probs=sizes.float().cpu() / sizes.sum().item()).sample().long().to(samples.device)
+        else:
+            per = torch.empty(world, dtype=torch.long, device=samples.device)
+        dist.broadcast(per, src=0)
+        per = per.tolist()
+        mine = local(samples, per[rank])
+        out = []
+        for r, k in enumerate(per):
+            t = mine if r == rank else samples.new_empty(k, samples.shape[1])
+            dist.broadcast(t, src=r)
+            out.append(t)
+        return torch.cat(out, dim=0)
+
+    @torch.no_grad()
+    def expire_codes_(self, batch_samples):
+        """quantize_lucid.py:238-256 / 365-383: codes whose EMA cluster size fell below the threshold are re-seeded."""
+        if self.threshold_ema_dead_code == 0:
+            return
+        expired = self.cluster_size < self.threshold_ema_dead_code
+        n_exp = int(expired.sum().item())                     # host read, like the reference's torch.any / mask.sum().item()
+        if n_exp == 0:
+            return
+        if self.code_replacement_policy == 'batch_random':
+            samples = l2norm(batch_samples.reshape(-1, batch_samples.shape[-1]).float())
+            self.embed.data[expired] = self._sample(samples, n_exp)
+        elif self.code_replacement_policy == 'linde_buzo_gray':
+            most_used = self.embed.data[self.cluster_size.argsort(descending=True)[:n_exp]]
+            noise = torch.randn_like(most_used)
+            if self._ddp():
+                torch.distributed.broadcast(noise, src=0)
+            self.embed.data[expired] = l2norm(most_used + noise * 1e-10)
+        else:
+            raise ValueError(f'{self.code_replacement_policy} is not a valid dead code replacement strategy.')
+
     def forward(self, x):
+        if not self._initted_seen:                            # one host read, then cached (initted only ever goes 0 -> 1)
+            if not bool(self.initted.item()):
+                raise NotImplementedError("k-means codebook initialisation (kmeans_init=True) is not on the B200 path; no shipped config uses it")
+            self._initted_seen = True
+        quantize, embed_ind = self.scan(x)                    # quantize = embed[idx] from the codebook BEFORE this step's update
         if self.training:
-            raise NotImplementedError("codebook EMA / dead-code expiry (training mode) is not implemented on the B200 path yet; "
-                                      "call .eval() for tokenization")
-        return self.scan(x)
+            flat = x.detach().reshape(-1, x.shape[-1]).float().contiguous()
+            self._ema_update(flat, embed_ind)
+            self.expire_codes_(x.detach())
+        return quantize, embed_ind
 
 
 class CosineSimCodebook(_Codebook):
@@ -116,7 +194,13 @@ class VectorQuantize(nn.Module):
         if self.norm_latents:
             z = l2norm(z)
         quantize, embed_ind = self._codebook(z)
-        loss = torch.tensor([0.], device=x.device)
+        loss = torch.tensor([0.], device=x.device, requires_grad=self.training)
+        if self.training:
+            quantize = z + (quantize - z).detach()                               # straight-through (reference :532)
+            if self.commitment_weight > 0:
+                loss = loss + F.mse_loss(quantize.detach(), z) * self.commitment_weight
+            if self.orthogonal_reg_weight > 0:
+                raise NotImplementedError("orthogonal codebook regularisation is not used by any shipped tokenizer config")
         if self.accept_image_fmap:
             quantize = quantize.reshape(B, Hq, Wq, C).permute(0, 3, 1, 2)
             embed_ind = embed_ind.reshape(B, Hq, Wq)

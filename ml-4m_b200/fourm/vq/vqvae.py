@@ -145,3 +145,54 @@ class VQ(nn.Module, PyTorchModelHubMixin):
     def forward(self, x: torch.Tensor, **kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
         quant, code_loss, _ = self.encode(x)
         return quant, code_loss
+
+
+
+class VQVAE(VQ):
+    """VQ encoder + ViT decoder with a plain reconstruction objective (reference vqvae.py:395-481): the tokenizer TRAINING model
+    (run_training_vqvae.py).  Same constructor arguments and state_dict keys (`decoder.*`, `post_quant_proj.{weight,bias}` on
+    top of VQ's); `forward` -> (dec, code_loss).  Only the ViT decoders are on the B200 path."""
+
+    def __init__(self, dec_type: str = 'vit_b_dec', out_conv: bool = False, image_size_dec: int = None, patch_size_dec: int = None,
+                 config: Optional[Dict[str, Any]] = None, *args, **kwargs):
+        if config is not None:
+            self.__init__(**copy.deepcopy(config))
+            return
+        ckpt_path = kwargs.get('ckpt_path', None)
+        kwargs['ckpt_path'] = None                                   # load after the decoder exists (reference :424-427)
+        super().__init__(*args, **kwargs)
+        self.ckpt_path = ckpt_path
+        out_channels = self.n_channels if self.n_labels is None else self.n_labels
+        if 'vit' not in dec_type:
+            raise NotImplementedError(f'{dec_type}: only the ViT decoders are on the B200 path')
+        self.decoder = getattr(vit_models, dec_type)(out_channels=out_channels, patch_size=patch_size_dec or self.patch_size,
+                                                     resolution=image_size_dec or self.image_size, out_conv=out_conv,
+                                                     post_mlp=self.post_mlp, patch_proj=self.patch_proj)
+        self.dec_dim = self.decoder.dim_tokens
+        self.post_quant_proj = torch.nn.Conv2d(self.latent_dim, self.dec_dim, 1)
+        if self.ckpt_path is not None:
+            self.init_from_ckpt(self.ckpt_path, ignore_keys=self.ignore_keys)
+
+    def decode_quant(self, quant: torch.Tensor, **kwargs) -> torch.Tensor:
+        """quant [B, d, Hq, Wq] -> image [B, C, H, W] (reference vqvae.py:441-452): 1x1 post_quant_proj as a GEMM, ViT decoder."""
+        B, d, Hq, Wq = quant.shape
+        z = quant.permute(0, 2, 3, 1).reshape(B * Hq * Wq, d)
+        w = self.post_quant_proj.weight.reshape(self.dec_dim, self.latent_dim)
+        t = BF.LinearFn.apply(z, w, self.post_quant_proj.bias)                              # bf16 [B*N, dec_dim]
+        return self.decoder(t.view(B, Hq, Wq, self.dec_dim).permute(0, 3, 1, 2))
+
+    def decode_tokens(self, tokens: torch.LongTensor, **kwargs) -> torch.Tensor:
+        return self.decode_quant(self.tokens_to_embedding(tokens), **kwargs)
+
+    def forward(self, x: torch.Tensor, **kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Reference vqvae.py:454-471 -> (dec [B, C, H, W], code_loss)."""
+        if self.freeze_enc:
+            with torch.no_grad():
+                quant, code_loss, _ = self.encode(x)
+        else:
+            quant, code_loss, _ = self.encode(x)
+        return self.decode_quant(quant), code_loss
+
+    def autoencode(self, x: torch.Tensor, **kwargs) -> torch.Tensor:
+        dec, _ = self.forward(x)
+        return dec

@@ -125,3 +125,45 @@ def test_device_prefetcher_order_cpu_fallback_refused():
         pytest.skip("CPU-only check")
     with pytest.raises(Exception):
         DevicePrefetcher([], "cuda")
+
+
+def _sample_worker(rank, world, port, q):
+    import os
+    import sys
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ml-4m_b200"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fourm.vq.quantizers.quantize_lucid import CosineSimCodebook
+    cb = CosineSimCodebook(dim=8, codebook_size=16, use_ddp=True)
+    torch.manual_seed(100 + rank)
+    samples = torch.nn.functional.normalize(torch.randn(5 + 7 * rank, 8), dim=-1) + 10.0 * rank     # rank is recognisable
+    out = cb._sample(samples, 9)
+    allsamp = [torch.empty(5 + 7 * r, 8) for r in range(world)]
+    for r in range(world):
+        t = samples if r == rank else allsamp[r]
+        dist.broadcast(t, src=r)
+        allsamp[r] = t
+    q.put((rank, out, torch.cat(allsamp)))
+    dist.destroy_process_group()
+
+
+def test_dead_code_resampling_is_identical_on_all_ranks_gloo():
+    """sync_codebook dead-code re-seeding (quantize_lucid.py:100-113): every rank must end up with the SAME replacement vectors,
+    drawn from the union of the ranks' latents (world_size 2, gloo, CPU tensors: pure host logic, no kernel involved)."""
+    import torch
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650
+    procs = [ctx.Process(target=_sample_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+    (_, o0, pool), (_, o1, _) = res
+    assert o0.shape == (9, 8) and torch.equal(o0, o1)
+    d = (o0[:, None, :] - pool[None]).abs().sum(-1).min(dim=1).values
+    assert float(d.max()) == 0.0                                  # every row is one of the pooled latents

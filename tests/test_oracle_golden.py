@@ -206,3 +206,62 @@ def test_fourm_qknorm_backward_matches_reference(tiny_qknorm):
         ref_norm = c["grads"]["norm"][k]
         assert abs(float(sdg[k].grad.norm()) - ref_norm) <= 1e-4 * max(ref_norm, 1e-3), k
         torch.testing.assert_close(sdg[k].grad.flatten()[:64], c["grads"]["slices"][k], rtol=1e-3, atol=1e-6)
+
+
+# ---- VQ-VAE training side (a25): codebook EMA update + one VQVAE training step -------------------------------------------------
+def test_codebook_ema_updates_match_reference():
+    gold = H.load_golden("vq_train_golden.pt")
+    c = gold["cosine"]
+    embed, cs = c["embed0"].clone(), torch.zeros(512)
+    for z, st in zip(c["z"], c["steps"]):
+        q, idx, embed, cs = V.cosine_codebook_train_step(z, embed, cs, 0.9)
+        assert torch.equal(idx, st["idx"])
+        torch.testing.assert_close(q.double().sum(-1), st["quant_sum"], rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(embed, st["embed"], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(cs, st["cluster_size"], rtol=1e-6, atol=1e-6)
+    e = gold["euclid"]
+    embed, avg, cs = e["embed0"].clone(), e["embed0"].clone(), torch.zeros(300)
+    for z, st in zip(c["z"], e["steps"]):
+        q, idx, embed, avg, cs = V.euclid_codebook_train_step(z, embed, avg, cs, 0.8)
+        assert torch.equal(idx, st["idx"])
+        torch.testing.assert_close(embed, st["embed"], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(avg, st["embed_avg"], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(cs, st["cluster_size"], rtol=1e-6, atol=1e-6)
+
+
+def _vqvae_fixture():
+    gold = H.load_golden("vq_train_golden.pt")["vqvae"]
+    sd = {}
+    for k, shape in gold["shapes"].items():
+        if k.endswith("pos_emb"):
+            sd[k] = V.sincos_2d_grid(shape[2], shape[3], shape[1])
+        elif k.endswith("initted"):
+            sd[k] = torch.ones(shape)
+        elif k.endswith("cluster_size"):
+            sd[k] = torch.zeros(shape)
+        elif k.endswith("_codebook.embed"):
+            sd[k] = torch.nn.functional.normalize(O.deterministic_tensor("quantize._codebook.embed", shape, 1.0), dim=-1)
+        else:
+            sd[k] = O.deterministic_tensor(k, shape, 0.05 if len(shape) > 1 else 0.02)
+    for k, c in gold["weight_checksums"].items():
+        assert abs(float(sd[k].double().sum()) - c) <= 1e-5 * max(1.0, abs(c)), f"fixture weight drift in {k}"
+    x = torch.randn(4, 3, 64, 64, generator=torch.Generator().manual_seed(7))
+    return gold, sd, x
+
+
+def test_vqvae_training_step_matches_reference():
+    gold, sd, x = _vqvae_fixture()
+    names = set(gold["param_names"])
+    sdg = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in sd.items()}
+    dec, code_loss, idx, new_embed, new_cs = V.vqvae_forward_train(x, sdg, gold["kw"])
+    rec = torch.nn.functional.mse_loss(dec, x)
+    (rec + code_loss.sum()).backward()
+    assert abs(float(rec) - float(gold["rec_loss"])) <= 1e-4 * float(gold["rec_loss"])
+    assert abs(float(code_loss) - float(gold["code_loss"])) <= 1e-4 * float(gold["code_loss"])
+    torch.testing.assert_close(dec[:, :, :8, :8].detach(), gold["dec_slice"], rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(new_embed.detach(), gold["embed_after"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(new_cs.detach(), gold["cluster_size_after"], rtol=1e-6, atol=1e-6)
+    for k, ref in gold["grad_norm"].items():
+        assert abs(float(sdg[k].grad.norm()) - ref) <= 2e-3 * max(ref, 1e-3), k
+    for k, sl in gold["grad_slices"].items():
+        torch.testing.assert_close(sdg[k].grad.flatten()[:64], sl, rtol=5e-3, atol=1e-4 * float(sl.abs().max()) + 1e-7)
