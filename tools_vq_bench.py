@@ -65,4 +65,31 @@ with torch.no_grad():
 ms = e0.elapsed_time(e1) / 10
 out["tokenize_vit_b_256"] = dict(batch=B, ms=ms, img_per_s=B / (ms * 1e-3), tokens_per_s=B * 256 / (ms * 1e-3),
                                  tflops=48.6e9 * B / (ms * 1e-3) / 1e12)
+# --- cfg-5: one VQ-VAE training step (ViT-B encoder + ViT-B decoder @256^2, K = 16384, d = 32, EMA codebook, MSE loss, fused AdamW), B = 64
+from b200fm.optim import FusedAdamW
+vae = vq.VQVAE(enc_type="vit_b_enc", dec_type="vit_b_dec", image_size=256, patch_size=16, codebook_size=16384, latent_dim=32, norm_codes=True,
+               post_mlp=True, sync_codebook=False, ema_decay=0.99).to(dev).train()
+opt = FusedAdamW([p for p in vae.parameters() if p.requires_grad], lr=1e-4, betas=(0.9, 0.99), weight_decay=0.0)
+
+
+def vae_step():
+    dec, code_loss = vae(x)
+    loss = F.mse_loss(dec.float(), x) + code_loss.sum()
+    loss.backward()
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+    return loss
+
+
+for _ in range(3):
+    vae_step()
+torch.cuda.synchronize(); e0.record()
+for _ in range(10):
+    l = vae_step()
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 10
+n_par = sum(p.numel() for p in vae.parameters())
+# fwd+bwd FLOPs: encoder + decoder ViT-B at 256 tokens = 2 x 48.6 GFLOP fwd per image, x3 for fwd+bwd
+out["vqvae_train_vit_b_256"] = dict(batch=B, ms=ms, img_per_s=B / (ms * 1e-3), params_m=n_par / 1e6, loss=float(l),
+                                    model_tflops=3 * 2 * 48.6e9 * B / (ms * 1e-3) / 1e12)
 print(json.dumps(out))
