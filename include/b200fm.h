@@ -141,6 +141,8 @@ int b200fm_adamw_chunk_elems(void);
 #define B200FM_KIND_IMG 0     /* pixel patches: x rows come from the patch-projection GEMM (x_rows)  */
 #define B200FM_KIND_TOK_IMG 1 /* tokenised image: ids [B, L]                                         */
 #define B200FM_KIND_SEQ 2     /* token sequence: ids [B, L], decoder side uses the teacher-forcing shift */
+#define B200FM_KIND_SEQ_EMB 3 /* pre-computed sequence features (T5-XXL, encoder_embeddings.py:312-421): x rows from the
+                                 emb_proj GEMM (x_rows) like KIND_IMG, positions ranked among valid inputs like KIND_SEQ */
 typedef struct b200fm_segment {
     const uint8_t* mask;      /* [B, L] bool, 1 = masked: input_mask (encoder) / target_mask (decoder)            */
     const void* ids;          /* [B, L] int32 or int64 token ids (NULL for KIND_IMG)                              */
@@ -148,7 +150,7 @@ typedef struct b200fm_segment {
     const float* token_emb;   /* [V, D] fp32 table                                                                */
     const float* pos_emb;     /* [P, D] fp32 positional table                                                     */
     const float* mod_emb;     /* [D]                                                                              */
-    const void* x_rows;       /* KIND_IMG: bf16 [B*L, D] projected patches                                        */
+    const void* x_rows;       /* KIND_IMG / KIND_SEQ_EMB: bf16 [B*L, D] projected patches / features              */
     float* d_token_emb;       /* backward: [V, D] fp32 gradient table, accumulated into (may be NULL)             */
     float* d_mod_emb;         /* backward: [D] fp32, accumulated into (may be NULL)                               */
     void* dx_rows;            /* backward, KIND_IMG: bf16 [B*L, D] gradient rows (pre-zeroed by the caller)       */

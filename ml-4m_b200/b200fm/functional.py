@@ -9,7 +9,7 @@ import weakref
 
 import torch
 
-from . import ops
+from . import lib, ops
 
 # ----------------------------------------------------------------------------------------------------------------------
 # bf16 weight shadows
@@ -450,7 +450,7 @@ class EmbedRowsFn(torch.autograd.Function):
         for i, st in enumerate(seg_static):
             d = dict(st)
             main, mod = tensors[2 * i], tensors[2 * i + 1]
-            if st["kind"] == 0:
+            if st["kind"] in (lib.KIND_IMG, lib.KIND_SEQ_EMB):
                 d["x_rows"] = main
             else:
                 d["token_emb"] = main
@@ -473,7 +473,7 @@ class EmbedRowsFn(torch.autograd.Function):
             need_main, need_mod = ctx.needs_input_grad[5 + 2 * i], ctx.needs_input_grad[5 + 2 * i + 1]
             gm = None
             if need_main:
-                if st["kind"] == 0:
+                if st["kind"] in (lib.KIND_IMG, lib.KIND_SEQ_EMB):
                     gm = torch.zeros(mshape, device=dev, dtype=torch.bfloat16)
                     d["dx_rows"] = gm
                 else:

@@ -19,7 +19,7 @@ class Segment(ctypes.Structure):
 
 
 MAX_SEGMENTS = 24
-KIND_IMG, KIND_TOK_IMG, KIND_SEQ = 0, 1, 2
+KIND_IMG, KIND_TOK_IMG, KIND_SEQ, KIND_SEQ_EMB = 0, 1, 2, 3
 
 # name -> argtypes  (restype is int unless noted); must list every symbol declared in include/b200fm.h
 SIGNATURES = {

@@ -23,6 +23,8 @@ struct SegTable {
 };
 
 // effective number of positions a segment contributes: decoder sequences lose one (teacher-forcing shift, fm.py:312-319)
+__host__ __device__ inline bool seg_rows_from_gemm(const b200fm_segment& s) { return s.kind == B200FM_KIND_IMG || s.kind == B200FM_KIND_SEQ_EMB; }
+__host__ __device__ inline bool seg_seq_positions(const b200fm_segment& s) { return s.kind == B200FM_KIND_SEQ || s.kind == B200FM_KIND_SEQ_EMB; }
 __host__ __device__ inline int seg_len(const b200fm_segment& s, int decoder) { return (decoder && s.kind == B200FM_KIND_SEQ) ? s.L - 1 : s.L; }
 
 B200FM_DEVINL bool seg_masked(const b200fm_segment& s, int decoder, int b, int l) {
@@ -88,7 +90,7 @@ plan_kernel(const SegTable tab, int n_keep, int32_t* __restrict__ src_seg, int32
                 // positional index: rank among the segment's valid RAW positions (encoder: input_mask, decoder: target_mask),
                 // encoder_embeddings.py:110-112, decoder_embeddings.py:125-128; image modalities use the patch index.
                 int pid = l;
-                if (sg.kind == B200FM_KIND_SEQ) {
+                if (seg_seq_positions(sg)) {
                     const uint8_t* m = sg.mask + (long long)b * sg.L;
                     int rk = 0;
                     for (int i = 0; i <= l; ++i) rk += m[i] ? 0 : 1;
@@ -165,7 +167,7 @@ embed_kernel(const SegTable tab, const int32_t* __restrict__ src_seg, const int3
         const uint2* xb = nullptr;
         if (tab.decoder && sg.kind != B200FM_KIND_SEQ) {
             xs = reinterpret_cast<const float4*>(mask_token);
-        } else if (sg.kind == B200FM_KIND_IMG) {
+        } else if (seg_rows_from_gemm(sg)) {
             xb = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(sg.x_rows) + ((long long)b * sg.L + l) * D);
         } else {
             const long long id = sg.ids_is_i64 ? reinterpret_cast<const int64_t*>(sg.ids)[(long long)b * sg.L + l]
@@ -207,7 +209,7 @@ embed_bwd_scatter_kernel(const SegTable tab, const int32_t* __restrict__ src_seg
         if (tab.decoder && sg.kind != B200FM_KIND_SEQ) continue;              // mask-token rows: handled by the modality sums
         const int b = (int)(row / n_keep), l = src_pos[row];
         const float4* g = reinterpret_cast<const float4*>(dx0 + row * D);
-        if (sg.kind == B200FM_KIND_IMG) {
+        if (seg_rows_from_gemm(sg)) {
             if (sg.dx_rows == nullptr) continue;
             uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(sg.dx_rows) + ((long long)b * sg.L + l) * D);
 #pragma unroll

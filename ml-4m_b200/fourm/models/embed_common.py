@@ -6,7 +6,7 @@ import torch
 from b200fm import functional as BF
 from b200fm import lib, ops
 
-KIND_IMG, KIND_TOK_IMG, KIND_SEQ = lib.KIND_IMG, lib.KIND_TOK_IMG, lib.KIND_SEQ
+KIND_IMG, KIND_TOK_IMG, KIND_SEQ, KIND_SEQ_EMB = lib.KIND_IMG, lib.KIND_TOK_IMG, lib.KIND_SEQ, lib.KIND_SEQ_EMB
 
 
 def as_mask_u8(mask):
@@ -20,6 +20,7 @@ def materialise(module, d, mask_key, decoder_clamp):
     """Write d['x'] (token / patch embedding) and d['emb'] (pos + mod) for EVERY position of one modality with the
     plan + embed kernels in identity mode."""
     seg_static, main, mod = module.segment(d, mask_key, decoder_side=decoder_clamp)
+    seg_static.setdefault("mod_id", 0)               # a lone modality: the id only feeds mod_mask, which is not returned here
     B = d['tensor'].shape[0]
     L = seg_static["L"]
     dev = mod.device

@@ -12,7 +12,7 @@ import torch.nn as nn
 from b200fm import functional as BF
 from b200fm import ops
 
-from .embed_common import KIND_IMG, KIND_SEQ, KIND_TOK_IMG, as_mask_u8, materialise
+from .embed_common import KIND_IMG, KIND_SEQ, KIND_SEQ_EMB, KIND_TOK_IMG, as_mask_u8, materialise
 from .fm_utils import build_1d_sincos_posemb, build_2d_sincos_posemb, pair
 
 
@@ -158,7 +158,8 @@ class ImageEncoderEmbedding(nn.Module):
 
 class SequenceEmbEncoderEmbedding(nn.Module):
     """Pre-computed sequence features such as T5-XXL embeddings (reference encoder_embeddings.py:312-421; 4M-21 only).
-    Constructor / parameters kept; its projection is not wired into the fused gather yet."""
+    The projection is one GEMM over all positions; the selection / embedding kernels read its rows (segment kind SEQ_EMB:
+    feature rows like the pixel patches, positions ranked among the valid inputs like token sequences)."""
 
     def __init__(self, max_length: int, dim_tokens: Optional[int] = None, sincos_pos_emb: bool = True, max_sincos_pos_emb: int = 512,
                  padding_idx: int = 0, orig_emb_dim: int = 4096, bottleneck_dim: int = 64, use_bottleneck: bool = False):
@@ -191,5 +192,23 @@ class SequenceEmbEncoderEmbedding(nn.Module):
     def no_weight_decay(self):
         return set()
 
+    def project(self, feats):
+        """emb_proj (Linear orig_emb_dim -> D, or the bottleneck pair) on every position -> bf16 [B*L, D] (reference :403)."""
+        x = feats.reshape(-1, feats.shape[-1])
+        layers = list(self.emb_proj) if isinstance(self.emb_proj, nn.Sequential) else [self.emb_proj]
+        for lin in layers:
+            x = BF.LinearFn.apply(x, lin.weight, lin.bias)
+        return x
+
+    def segment(self, d, mask_key='input_mask', decoder_side=False):
+        feats = d['tensor']
+        assert self.dim_tokens is not None, 'Need to call init(dim_tokens) function first'
+        B, L = feats.shape[0], feats.shape[1]
+        x_rows = self.project(feats)
+        pos = self.pos_emb if self.pos_emb.dim() == 2 else self.pos_emb.reshape(-1, self.dim_tokens)
+        st = dict(mask=as_mask_u8(d[mask_key]), ids=None, L=L, kind=KIND_SEQ_EMB, pos_emb=pos, padding_idx=-1, max_length=0)
+        return st, x_rows, self.mod_emb
+
     def forward(self, d):
-        raise NotImplementedError("SequenceEmbEncoderEmbedding (T5 features, 4M-21) is not on the B200 path yet")
+        d['x'], d['emb'] = materialise(self, d, 'input_mask', False)
+        return d

@@ -114,6 +114,18 @@ def embed_sequence(ids: torch.Tensor, mask: torch.Tensor, token_emb: torch.Tenso
     return x, pe + mod_emb
 
 
+def embed_sequence_features(feats: torch.Tensor, mask: torch.Tensor, proj: Sequence[Tuple[torch.Tensor, Optional[torch.Tensor]]],
+                            pos_emb: torch.Tensor, mod_emb: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """SequenceEmbEncoderEmbedding.forward (encoder_embeddings.py:387-421; T5-XXL features of 4M-21): x = emb_proj(feats) on every
+    position (`proj` = [(W, b)] or the bottleneck pair), emb = sincos1d[rank among valid inputs] (zeroed where masked) + mod_emb."""
+    x = feats
+    for w, b in proj:
+        x = F.linear(x, w, b)
+    pos = _seq_pos_ids(mask, None)
+    pe = pos_emb[0][pos].masked_fill(mask[..., None], 0.0)
+    return x, pe + mod_emb
+
+
 def embed_image_tokens(ids: torch.Tensor, token_emb: torch.Tensor, pos_emb: torch.Tensor,
                        mod_emb: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """ImageTokenEncoderEmbedding.forward (encoder_embeddings.py:184-211) and

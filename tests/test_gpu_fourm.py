@@ -208,3 +208,73 @@ def test_generation_shaped_stack_calls(tiny, N, M, causal):
     # 6+6 layers of bf16 contractions against an fp32 oracle on unit-variance activations (LayerNorm'd outputs, O(1) entries)
     torch.testing.assert_close(ctx.float().cpu(), ctx_ref, rtol=5e-2, atol=5e-2)
     torch.testing.assert_close(out.float().cpu(), out_ref, rtol=5e-2, atol=5e-2)
+
+
+@pytest.mark.parametrize("tag", ["plain", "bottleneck"])
+def test_sequence_feature_embedding_module(tag):
+    """a6: SequenceEmbEncoderEmbedding (T5-XXL features of 4M-21) -- the emb_proj GEMM + the selection / embedding kernels in
+    identity mode (segment kind SEQ_EMB) against the golden outputs and gradients of the unmodified reference module."""
+    from fourm.models.encoder_embeddings import SequenceEmbEncoderEmbedding
+    c = H.load_golden("seqemb_golden.pt")["cases"][tag]
+    g = torch.Generator().manual_seed(41)                        # == tests/golden/make_golden_seqemb.inputs()
+    feats = torch.randn(3, 77, 4096, generator=g)
+    mask = torch.rand(3, 77, generator=g) < 0.35
+    mask[0] = False
+    mask[1, 5:] = True
+    wx = torch.randn(3, 77, 384, generator=g)
+    we = torch.randn(3, 77, 384, generator=g)
+    m = SequenceEmbEncoderEmbedding(max_length=77, dim_tokens=384, orig_emb_dim=4096, **c["kw"])
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == c["shapes"]
+    sd = {k: (O.sincos_1d(512, 384) if k == "pos_emb" else O.deterministic_tensor("seqemb." + k, shape, 0.02)) for k, shape in c["shapes"].items()}
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    d = m(dict(tensor=feats.cuda(), input_mask=mask.cuda()))
+    (d["x"].float() * wx.cuda()).sum().add((d["emb"] * we.cuda()).sum()).backward()
+    # positional / modality part: fp32 gather, exact; projected features: bf16 GEMM over K = 4096 (values ~1.3, ulp 2^-8)
+    assert torch.equal(d["emb"].detach().cpu()[:, :6, :48], c["emb_slice"])
+    assert torch.equal(d["emb"].detach().double().sum(-1).cpu(), c["emb_sum"])
+    torch.testing.assert_close(d["x"].detach().float().cpu()[:, :6, :48], c["x_slice"], rtol=2e-2, atol=2e-2)
+    for k, p in m.named_parameters():
+        ref = c["grad_norm"][k]
+        assert abs(float(p.grad.float().norm()) - ref) <= 3e-2 * max(ref, 1e-6), k
+        sl = c["grad_slices"][k]
+        assert (p.grad.flatten()[:64].float().cpu() - sl).abs().max() <= 8e-2 * sl.abs().max() + 1e-7, k
+
+
+def test_embedding_modules_forward_contract(tiny):
+    """The reference's per-module API that fourm/models/generate.py drives (`encoder_embeddings[mod](d)` -> d['x'], d['emb'];
+    `decoder_embeddings[mod].forward_embed(d)` -> + d['ids']): every position of the modality, no selection.  Against the
+    oracle's restatement of encoder_embeddings.py:87-121, 184-211, 280-309 and decoder_embeddings.py:98-139, 226-255.
+    Token / positional / modality rows are fp32 gathers (exact); the rgb patch projection is a bf16 GEMM."""
+    gold, specs, sd, model = tiny
+    batch = O.synthetic_mod7_batch(2, seed=11)
+    cb = _to_cuda(batch)
+    with torch.no_grad():
+        for mod, d in batch.items():
+            s = specs[mod]
+            if mod in model.encoder_embeddings:
+                out = model.encoder_embeddings[mod](dict(cb[mod]))
+                pfx = f"encoder_embeddings.{mod}."
+                if s["kind"] == "seq":
+                    x, emb = O.embed_sequence(d["tensor"], d["input_mask"], sd[pfx + "token_emb.weight"], sd[pfx + "pos_emb"], sd[pfx + "mod_emb"], None)
+                elif s["kind"] == "tok_img":
+                    x, emb = O.embed_image_tokens(d["tensor"], sd[pfx + "token_emb.weight"], sd[pfx + "pos_emb"], sd[pfx + "mod_emb"])
+                else:
+                    x, emb = O.embed_image_pixels(d["tensor"], sd[pfx + "proj.weight"], sd[pfx + "pos_emb"], sd[pfx + "mod_emb"], s["patch_size"])
+                assert out["x"].shape == x.shape and out["emb"].shape == emb.shape
+                assert torch.equal(out["emb"].cpu(), emb.expand_as(out["emb"].cpu())), mod
+                if s["kind"] == "img":
+                    torch.testing.assert_close(out["x"].float().cpu(), x, rtol=2e-2, atol=2e-2)
+                else:
+                    assert torch.equal(out["x"].float().cpu(), x), mod
+            if mod in model.decoder_embeddings:
+                out = model.decoder_embeddings[mod].forward_embed(dict(cb[mod]))
+                pfx = f"decoder_embeddings.{mod}."
+                if s["kind"] == "seq":
+                    x, emb = O.embed_sequence(d["tensor"], d["target_mask"], sd[pfx + "token_emb.weight"], sd[pfx + "pos_emb"], sd[pfx + "mod_emb"],
+                                              s["max_length"])
+                else:
+                    x, emb = O.embed_image_tokens(d["tensor"], sd[pfx + "token_emb.weight"], sd[pfx + "pos_emb"], sd[pfx + "mod_emb"])
+                assert torch.equal(out["ids"].cpu(), d["tensor"].reshape(d["tensor"].shape[0], -1))     # 'b h w -> b (h w)' for image tokens
+                assert torch.equal(out["emb"].cpu(), emb.expand_as(out["emb"].cpu())), mod
+                assert torch.equal(out["x"].float().cpu(), x), mod

@@ -265,3 +265,29 @@ def test_vqvae_training_step_matches_reference():
         assert abs(float(sdg[k].grad.norm()) - ref) <= 2e-3 * max(ref, 1e-3), k
     for k, sl in gold["grad_slices"].items():
         torch.testing.assert_close(sdg[k].grad.flatten()[:64], sl, rtol=5e-3, atol=1e-4 * float(sl.abs().max()) + 1e-7)
+
+
+# ---- a6: SequenceEmbEncoderEmbedding (T5-XXL features, 4M-21) ----------------------------------------------------------------
+def _seqemb_case(tag):
+    c = H.load_golden("seqemb_golden.pt")["cases"][tag]
+    g = torch.Generator().manual_seed(41)                        # == make_golden_seqemb.inputs()
+    feats = torch.randn(3, 77, 4096, generator=g)
+    mask = torch.rand(3, 77, generator=g) < 0.35
+    mask[0] = False
+    mask[1, 5:] = True
+    wx = torch.randn(3, 77, 384, generator=g)
+    we = torch.randn(3, 77, 384, generator=g)
+    sd = {k: (O.sincos_1d(512, 384) if k == "pos_emb" else O.deterministic_tensor("seqemb." + k, shape, 0.02)) for k, shape in c["shapes"].items()}
+    return c, sd, feats, mask, wx, we
+
+
+@pytest.mark.parametrize("tag", ["plain", "bottleneck"])
+def test_sequence_feature_embedding_matches_reference(tag):
+    c, sd, feats, mask, wx, we = _seqemb_case(tag)
+    proj = [(sd["emb_proj.weight"], sd["emb_proj.bias"])] if tag == "plain" else \
+        [(sd["emb_proj.0.weight"], sd["emb_proj.0.bias"]), (sd["emb_proj.1.weight"], sd["emb_proj.1.bias"])]
+    x, emb = O.embed_sequence_features(feats, mask, proj, sd["pos_emb"], sd["mod_emb"])
+    torch.testing.assert_close(x[:, :6, :48], c["x_slice"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(x.double().sum(-1), c["x_sum"], rtol=1e-4, atol=1e-3)
+    assert torch.equal(emb[:, :6, :48], c["emb_slice"])
+    assert torch.equal(emb.double().sum(-1), c["emb_sum"])
