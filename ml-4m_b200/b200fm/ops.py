@@ -66,6 +66,17 @@ def gemm(a, b, layout=LAYOUT_NT, epilogue=EPI_BF16, out=None, out1=None, bias=No
             out = torch.empty((M, N), device=dev, dtype=torch.bfloat16)
     if two and out1 is None:
         out1 = torch.empty((M, N), device=a.device, dtype=torch.bfloat16)
+    if M == 0 or N == 0 or K == 0:
+        # degenerate problems (a modality without target rows: fm.py:589 `y[mod_mask == id]` can be empty): nothing to launch;
+        # an empty contraction dimension leaves the (bias-free) output at zero, like the reference's matmul
+        if K == 0 and M and N:
+            if epilogue == EPI_RESID and resid is not None:
+                out.copy_(resid)
+            else:
+                out.zero_()
+            if out1 is not None:
+                out1.zero_()
+        return (out, out1) if two else out
     if PROFILE is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()

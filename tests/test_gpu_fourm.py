@@ -278,3 +278,31 @@ def test_embedding_modules_forward_contract(tiny):
                 assert torch.equal(out["ids"].cpu(), d["tensor"].reshape(d["tensor"].shape[0], -1))     # 'b h w -> b (h w)' for image tokens
                 assert torch.equal(out["emb"].cpu(), emb.expand_as(out["emb"].cpu())), mod
                 assert torch.equal(out["x"].float().cpu(), x), mod
+
+
+@pytest.mark.parametrize("tag", ["fp32_128", "fp32_trunc", "fp32_pad"])
+def test_reference_shaped_selection_helpers(tiny, tag):
+    """The reference-shaped entry points that generate.py and downstream code call on the model -- per-module forward,
+    `forward_mask_encoder`, `forward_mask_decoder` (fm.py:338-438), `forward_logits` -- reproduce the golden artefacts that
+    make_golden.py recorded from exactly these calls on the unmodified reference."""
+    gold, specs, sd, model = tiny
+    c = gold["cases"][tag]
+    b = _to_cuda(O.synthetic_mod7_batch(2, seed=c["batch_seed"], extra_valid=c["extra_valid"]))
+    random.seed(c["py_seed"])
+    with torch.no_grad():
+        enc_d = {m: model.encoder_embeddings[m](dict(d)) for m, d in b.items() if m in model.encoder_embeddings}
+        et, ee, em, emod = model.forward_mask_encoder(enc_d, c["N"])
+        dec_d = {m: model.decoder_embeddings[m].forward_embed(dict(d)) for m, d in b.items() if m in model.decoder_embeddings}
+        dt, de, dm, tgt, damask, dmod = model.forward_mask_decoder(dec_d, c["M"])
+        logits = model.forward_logits(torch.zeros(2, c["M"], 384, device="cuda"), dec_d, dmod)
+    assert torch.equal(em.cpu(), c["enc_mask"]) and torch.equal(emod.cpu(), c["enc_mod"])
+    assert torch.equal(dm.cpu(), c["dec_mask"]) and torch.equal(dmod.cpu(), c["dec_mod"])
+    assert torch.equal(tgt.cpu().long(), c["target_ids"].long())
+    assert torch.equal(damask.cpu(), c["dec_attn_mask"])
+    assert torch.equal((dt + de).double().sum(-1).cpu(), c["dec_y0_sum"])
+    rgb = emod.cpu() == specs["rgb@224"]["id"]
+    got, ref = (et.float() + ee).double().sum(-1).cpu(), c["enc_x0_sum"]
+    assert torch.equal(got[~rgb], ref[~rgb])
+    torch.testing.assert_close(got[rgb], ref[rgb], rtol=0, atol=0.5)            # bf16 patch projection (autocast contract)
+    for m, lg in logits.items():
+        assert lg.shape == (int((dmod == specs[m]["id"]).sum()), specs[m]["vocab"])

@@ -106,3 +106,16 @@ def test_gemm_wgrad_split_k(M, N, K):
     torch.testing.assert_close(out, ref, rtol=2e-3, atol=2e-2 * (K ** 0.5) / 8)
     out2 = ops.gemm(a, b, layout=2, epilogue=ops.EPI_F32, alpha=0.5)
     torch.testing.assert_close(out2, ref * 0.5, rtol=2e-3, atol=2e-2 * (K ** 0.5) / 8)
+
+
+def test_gemm_degenerate_shapes():
+    """A modality without target rows gives M = 0 in the head's forward GEMM and K = 0 in its wgrad (fm.py:589-597): empty
+    result / all-zero gradient, no launch."""
+    from b200fm import ops
+    w = _mk((512, 128), 31)
+    x0 = torch.empty(0, 128, dtype=torch.bfloat16, device="cuda")
+    out = ops.gemm(x0, w, epilogue=ops.EPI_F32)
+    assert out.shape == (0, 512) and out.dtype == torch.float32
+    dy0 = torch.empty(0, 512, dtype=torch.bfloat16, device="cuda")
+    dw = ops.gemm(dy0, x0, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32)               # [512, 128] from zero rows
+    assert dw.shape == (512, 128) and float(dw.abs().sum()) == 0.0
