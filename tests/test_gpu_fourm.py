@@ -306,3 +306,45 @@ def test_reference_shaped_selection_helpers(tiny, tag):
     torch.testing.assert_close(got[rgb], ref[rgb], rtol=0, atol=0.5)            # bf16 patch projection (autocast contract)
     for m, lg in logits.items():
         assert lg.shape == (int((dmod == specs[m]["id"]).sum()), specs[m]["vocab"])
+
+
+@pytest.mark.parametrize("kw", [dict(num_register_tokens=4), dict(decoder_causal_mask=True), dict(decoder_sep_mask=False),
+                                dict(decoder_causal_mask=True, decoder_sep_mask=False, num_register_tokens=2)])
+def test_constructor_variants_match_oracle(kw):
+    """FourM options outside the shipped presets (fm.py:96-104): register tokens prepended to the encoder sequence
+    (fm.py:372-383), causal decoder mask and no modality separation (fm.py:440-475) -- forward loss and a few gradients against
+    the oracle on the same weights."""
+    from functools import partial
+    import torch.nn as nn
+    from b200fm.compat import build_mod7_embeddings
+    from fourm.models.fm import FourM
+    from fourm.models.fm_utils import LayerNorm
+    torch.manual_seed(0)
+    enc, dec, info = build_mod7_embeddings()
+    model = FourM(enc, dec, info, dim=256, encoder_depth=2, decoder_depth=2, num_heads=4, qkv_bias=False, proj_bias=False, mlp_bias=False,
+                  norm_layer=partial(LayerNorm, eps=1e-6, bias=False), act_layer=nn.SiLU, gated_mlp=True, **kw).cuda()
+    if kw.get("num_register_tokens"):
+        with torch.no_grad():
+            model.register_tokens.normal_(std=0.5)
+    batch = O.synthetic_mod7_batch(2, seed=13)
+    random.seed(2)
+    loss, _ = model(_to_cuda(batch), 128, 128)
+    loss.backward()
+    torch.cuda.synchronize()
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    keys = ["encoder.0.attn.qkv.weight", "decoder.1.self_attn.proj.weight", "decoder.0.cross_attn.kv.weight"] + \
+        (["register_tokens"] if kw.get("num_register_tokens") else [])
+    for k in keys:
+        sd[k] = sd[k].clone().requires_grad_(True)
+    random.seed(2)
+    order = random.sample([m for m in batch if m in model.decoder_embeddings], len(model.decoder_embeddings))
+    cfg = O.model_cfg(256, 4, 2, 2, causal=kw.get("decoder_causal_mask", False), sep=kw.get("decoder_sep_mask", True),
+                      num_register_tokens=kw.get("num_register_tokens", 0))
+    ref, _ = O.fourm_forward(sd, cfg, O.mod7_specs(), batch, 128, 128, order)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 5e-3, (float(loss), float(ref))
+    params = dict(model.named_parameters())
+    for k in keys:
+        g, r = params[k].grad.float().cpu(), sd[k].grad
+        assert g.shape == r.shape
+        assert abs(float(g.norm()) - float(r.norm())) <= 3e-2 * float(r.norm()) + 1e-6, k
