@@ -22,13 +22,22 @@ def _pad_rows(n, mult=8):
     return (n + mult - 1) // mult * mult
 
 
+def _root(p):
+    """The tensor whose identity / version counter stands for `p`: a reshaped view of a parameter (the 1x1 Conv2d weights used as
+    Linear weights are `.reshape(out, in)` views created per call) is represented by its base, so repeated views share one cache
+    entry instead of adding a new one on every call."""
+    b = p._base
+    return b if b is not None and b.numel() == p.numel() and p.is_contiguous() and b.is_contiguous() else p
+
+
 def weight_bf16(*params):
     """bf16 copy of one fp32 weight, or of several concatenated along dim 0 (e.g. [fc1; fc3]), refreshed when any
     source tensor's version counter changes (optimizer steps, load_state_dict).  Rows are zero-padded to a multiple of 8."""
-    key = tuple(id(p) for p in params)
-    ver = tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)
+    roots = [_root(p) for p in params]
+    key = tuple((id(r), tuple(p.shape)) for r, p in zip(roots, params))
+    ver = tuple(r._version for r in roots) + tuple(p.data_ptr() for p in params)
     hit = _shadow.get(key)
-    if hit is not None and hit[0] == ver and all(r() is p for r, p in zip(hit[2], params)):     # id() may be recycled: check identity
+    if hit is not None and hit[0] == ver and all(w() is r for w, r in zip(hit[2], roots)):     # id() may be recycled: check identity
         return hit[1]
     with torch.no_grad():
         rows = [p.shape[0] for p in params]
@@ -38,20 +47,37 @@ def weight_bf16(*params):
         if buf is None:
             buf = torch.zeros(sum(prow), cols, device=params[0].device, dtype=torch.bfloat16)
         off = 0
-        for p, r, pr in zip(params, rows, prow):
+        for p, root, r, pr in zip(params, roots, rows, prow):
             src = p.detach()
             if src.dtype != torch.float32 or not src.is_contiguous():
                 src = src.float().contiguous()
             view = buf[off:off + r]
             ops.cast_bf16(src, view)
-            ent = _shadow_views.get(id(p))
-            if ent is None or ent[0]() is not p:
-                ent = _shadow_views[id(p)] = (weakref.ref(p), [])
+            ent = _shadow_views.get(id(root))
+            if ent is None or ent[0]() is not root:
+                ent = _shadow_views[id(root)] = (weakref.ref(root), [])
             if not any(v.data_ptr() == view.data_ptr() for v in ent[1]):
                 ent[1].append(view)
             off += pr
-    _shadow[key] = (ver, buf, tuple(weakref.ref(p) for p in params))
+    _shadow[key] = (ver, buf, tuple(weakref.ref(r) for r in roots))
     return buf
+
+
+def mark_updated(params):
+    """`params` were rewritten IN PLACE through raw pointers (fused AdamW), together with every bf16 mirror registered for them
+    in `_shadow_views`.  Bump their version counters so that any other cache keyed on the version (K-padded shadows, the conv
+    weight re-layouts of the ViT tokenizers, user code) sees the change, and re-stamp the mirrors that were refreshed in the same
+    pass so they are not cast again."""
+    params = list(params)
+    if not params:
+        return
+    torch._C._autograd._unsafe_set_version_counter(params, [p._version + 1 for p in params])
+    ids = {id(p) for p in params}
+    for key, hit in list(_shadow.items()):
+        if len(key) and isinstance(key[0], tuple) and all(k[0] in ids for k in key):
+            roots = [w() for w in hit[2]]
+            if all(r is not None for r in roots):
+                _shadow[key] = (tuple(r._version for r in roots) + hit[0][len(roots):], hit[1], hit[2])
 
 
 def weight_bf16_padk(param, k_pad):

@@ -56,7 +56,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 loss = closure()
         for gi, group in enumerate(self.param_groups):
             b1, b2 = group["betas"]
-            tensors, extra_casts, step_no = [], [], None
+            tensors, extra_casts, step_no, updated = [], [], None, []
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -66,6 +66,7 @@ class FusedAdamW(torch.optim.Optimizer):
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["step"] += 1
+                updated.append(p)
                 if step_no is None:
                     step_no = st["step"]
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
@@ -89,8 +90,9 @@ class FusedAdamW(torch.optim.Optimizer):
                          ops._stream())
             for p, view in extra_casts:          # a weight mirrored in more than one operand buffer
                 ops.cast_bf16(p.data, view)
-            # the kernels write through raw pointers: p._version is unchanged and the bf16 mirrors were refreshed in the same
-            # pass, so the weight cache stays valid without a re-cast.
+            # the kernels wrote through raw pointers: bump the version counters (other version-keyed caches must notice) and
+            # re-stamp the bf16 mirrors that were refreshed in the same pass
+            BF.mark_updated(updated)
         return loss
 
 

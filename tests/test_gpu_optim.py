@@ -65,3 +65,62 @@ def test_device_prefetcher_yields_batches_in_order():
         assert batch["rgb"]["tensor"].is_cuda
         seen.append((float(batch["rgb"]["tensor"][0, 0]), int(batch["cap"]["tensor"][0])))
     assert seen == [(float(i), i) for i in range(5)]
+
+
+def test_weight_caches_follow_fused_adamw():
+    """FusedAdamW rewrites weights and their registered bf16 mirrors through raw pointers; every OTHER version-keyed cache (the
+    K-padded fc2 shadows of odd SwiGLU widths, the conv-as-linear re-layouts of the ViT tokenizers, reshaped 1x1-conv views)
+    must still notice the update: the loss after a step equals the loss computed with all caches dropped."""
+    import random
+    from functools import partial
+    import torch.nn as nn
+    from b200fm import functional as BF
+    from b200fm.compat import build_mod7_embeddings
+    from b200fm.optim import FusedAdamW
+    from fourm.models.fm import FourM
+    from fourm.models.fm_utils import LayerNorm
+    from fourm.vq.models.vit_models import _ConvAsLinear
+    from oracle import fourm_oracle as O
+    import fourm.vq as vq
+    torch.manual_seed(0)
+    enc, dec, info = build_mod7_embeddings()
+    model = FourM(enc, dec, info, dim=256, encoder_depth=1, decoder_depth=1, num_heads=4, qkv_bias=False, proj_bias=False, mlp_bias=False,
+                  norm_layer=partial(LayerNorm, eps=1e-6, bias=False), act_layer=nn.SiLU, gated_mlp=True).cuda()      # H = 682: K-padded fc2
+    batch = {m: {k: v.cuda() for k, v in d.items()} for m, d in O.synthetic_mod7_batch(2, seed=3).items()}
+    opt = FusedAdamW(model.parameters(), lr=1e-2, betas=(0.9, 0.95), weight_decay=0.0)
+    for _ in range(2):
+        random.seed(0)
+        loss, _ = model(batch, 128, 128)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+    with torch.no_grad():
+        random.seed(0)
+        l1, _ = model(batch, 128, 128)
+        BF.clear_weight_cache()
+        random.seed(0)
+        l2, _ = model(batch, 128, 128)
+    assert float(l1) == float(l2), (float(l1), float(l2))
+
+    vae = vq.VQVAE(enc_type="vit_s_enc", dec_type="vit_s_dec", image_size=64, patch_size=16, codebook_size=128, latent_dim=32,
+                   post_mlp=True, sync_codebook=False, threshold_ema_dead_code=0.0).cuda().train()
+    x = torch.randn(4, 3, 64, 64, device="cuda")
+    opt = FusedAdamW(vae.parameters(), lr=1e-2, betas=(0.9, 0.95), weight_decay=0.0)
+    n_before = len(BF._shadow)
+    for _ in range(3):
+        dec, code_loss = vae(x)
+        (torch.nn.functional.mse_loss(dec.float(), x) + code_loss.sum()).backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+    grown = len(BF._shadow) - n_before
+    vae.eval()
+    with torch.no_grad():
+        d1, _ = vae(x)
+        BF.clear_weight_cache()
+        _ConvAsLinear._cache.clear()
+        d2, _ = vae(x)
+    assert torch.equal(d1, d2)
+    vae.train()
+    dec, code_loss = vae(x)                                    # repeated forwards must not add cache entries for the reshaped conv weights
+    dec, code_loss = vae(x)
+    assert len(BF._shadow) <= n_before + grown, (len(BF._shadow), n_before, grown)
