@@ -1,6 +1,6 @@
 """Host-side cost per C-ABI call (issue only, GPU kept busy but never waited on inside the loop)."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "ml-4m_b200"))
 import torch
 from b200fm import ops, lib

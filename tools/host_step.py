@@ -1,7 +1,7 @@
 """Host-bound step time: the same train step at a tiny batch (GPU work negligible, launch count identical), wall-clocked, then
 cProfile'd for the split between the autograd Functions, the ctypes calls and torch's own ops."""
 import cProfile, os, pstats, random, sys, time
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "ml-4m_b200"))
 import torch
 from b200fm import lib

@@ -1,6 +1,6 @@
 """GPU time per kernel family for one steady-state training step (CUPTI via torch.profiler; complements the ncu launch list)."""
 import collections, os, random, re, sys
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "ml-4m_b200"))
 import torch
 from torch.profiler import ProfilerActivity, profile

@@ -1,7 +1,7 @@
 """Stand-alone launches of the hot kernels at 4M-B (cfg-2) shapes for `ncu --set full` captures (kept tiny on purpose: ncu
-replays every kernel ~40 times).  Usage: ncu --set full ... python tools_ncu_kernels.py"""
+replays every kernel ~40 times).  Usage: ncu --set full ... python tools/ncu_kernels.py"""
 import os, sys
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "ml-4m_b200"))
 import torch
 from b200fm import ops

@@ -5,7 +5,7 @@ import pstats
 import random
 import sys
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "ml-4m_b200"))
 import torch
 from b200fm.compat import build_mod7_embeddings, create_model

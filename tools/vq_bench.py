@@ -1,6 +1,6 @@
 """VQ tokenizer measurements (secondary metric of BASELINE.md): codebook scan micro-benchmark (cfg-5 size) and ViT-B tokenize."""
 import json, os, sys, time
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "ml-4m_b200"))
 import torch
 import torch.nn.functional as F
