@@ -1,3 +1,5 @@
+// nvcc -gencode arch=compute_100a,code=sm_100a -o cluster_probe tools/cluster_probe.cu && ./cluster_probe
+// B200 result (round 1): cluster 1: 148 CTAs, 2: 74 clusters (148), 4: 33 (132), 8: 15 (120), 16: 7 (112).
 // How many clusters of size c (one 200 KB CTA per SM) can be co-resident on this GPU?
 #include <cstdio>
 #include <cuda_runtime.h>

@@ -1,3 +1,5 @@
+"""Back-to-back timing of the 4M-B GEMM shapes in isolation (hot L2, boost clocks): the upper bound the in-step numbers of
+profiles/r1_gemm_shapes_*.json are compared with."""
 import os, sys, torch
 import os
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ml-4m_b200"))
@@ -23,4 +25,4 @@ for name, fn, fl in [("NT 16384x2304x768", lambda: ops.gemm(x, w_qkv), 2 * R * 2
                      ("TN 768x768x16384", lambda: ops.gemm(x, x, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32), 2 * R * 768 * 768),
                      ("TN 768x2048x16384", lambda: ops.gemm(x, xk, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32), 2 * R * 768 * 2048)]:
     us = t(fn)
-    print(f"{os.environ.get('B200FM_GEMM_DEBUG_SKIP_B','0')} {name:28s} {us:7.1f} us  {fl / us / 1e6:7.1f} TF/s")
+    print(f"{name:28s} {us:7.1f} us  {fl / us / 1e6:7.1f} TF/s")
