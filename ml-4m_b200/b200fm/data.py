@@ -2,18 +2,28 @@
 
 run_training_4m.py:712-716 moves every tensor of the loader's (pinned) batch with `.to(device, non_blocking=True)` on the
 compute stream, so the copy of step i+1 waits behind the kernels of step i.  DevicePrefetcher issues the same copies on a
-side stream one batch ahead: the 80 MB mod7 batch (an fp32 RGB image per sample) rides under the previous step's compute
-instead of in front of the next one.  Same tensors, same bytes, no change to what the model sees."""
+side stream from a background thread, `depth` batches ahead: the 80 MB mod7 batch (an fp32 RGB image per sample) rides under
+the previous step's compute instead of in front of the next one.  The thread matters on hosts where the copy call itself
+blocks (pageable or slowly-pinned memory: two pool boxes moved the batch at ~3 GB/s with the calling thread stuck in the
+copy, starving the launch queue); the stream alone only helps when the call returns immediately.  Same tensors, same bytes,
+no change to what the model sees."""
+import queue
+import threading
+
 import torch
+
+_END = object()
 
 
 class DevicePrefetcher:
-    """Iterate `batches` (an iterable of {modality: {key: pinned CPU tensor}}) as device-resident mod_dicts, copying one
-    batch ahead on a dedicated stream."""
+    """Iterate `batches` (an iterable of {modality: {key: CPU tensor, ideally pinned}}) as device-resident mod_dicts."""
 
-    def __init__(self, batches, device, depth=1):
+    def __init__(self, batches, device, depth=2):
         self.batches = batches
-        self.device = torch.device(device)
+        dev = torch.device(device)
+        if dev.type == "cuda" and dev.index is None:        # the worker thread pins itself to an explicit device
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
         self.depth = max(1, int(depth))
         self.stream = torch.cuda.Stream(device=self.device)
 
@@ -23,15 +33,44 @@ class DevicePrefetcher:
             ev = self.stream.record_event()
         return dev, ev
 
+    def _worker(self, q, stop):
+        try:
+            torch.cuda.set_device(self.device)
+            for hb in self.batches:
+                if stop.is_set():
+                    return
+                item = self._stage(hb)
+                while not stop.is_set():
+                    try:
+                        q.put(item, timeout=0.1)
+                        break
+                    except queue.Full:
+                        continue
+            item = _END
+        except BaseException as e:          # surfaced in the consumer thread
+            item = e
+        while not stop.is_set():
+            try:
+                q.put(item, timeout=0.1)
+                break
+            except queue.Full:
+                continue
+
     def __iter__(self):
-        it = iter(self.batches)
-        queue = []
-        for hb in it:
-            queue.append(self._stage(hb))
-            if len(queue) > self.depth:
-                yield self._hand_over(queue.pop(0))
-        while queue:
-            yield self._hand_over(queue.pop(0))
+        q = queue.Queue(maxsize=self.depth)
+        stop = threading.Event()
+        t = threading.Thread(target=self._worker, args=(q, stop), daemon=True)
+        t.start()
+        try:
+            while True:
+                item = q.get()
+                if item is _END:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                yield self._hand_over(item)
+        finally:
+            stop.set()
 
     def _hand_over(self, staged):
         dev, ev = staged
