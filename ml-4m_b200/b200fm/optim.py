@@ -97,13 +97,16 @@ class FusedAdamW(torch.optim.Optimizer):
 
 
 def param_groups_like_reference(model, weight_decay=0.05):
-    """fourm/utils/optim_factory.py:111-168: no weight decay for 1-D tensors, biases, and names the model lists."""
+    """The decay / no-decay split of fourm/utils/optim_factory.py:111-168 (`get_parameter_groups` as `create_optimizer` calls it,
+    :188-199): no weight decay for names containing "norm." / ".norm", ending in ".bias", ".lookup_table_weight" or ".gamma", and
+    for the model's own `no_weight_decay()` list; everything else decays.  (No layer-wise lr scaling: 4M pre-training does not use it.)"""
     skip = model.no_weight_decay() if hasattr(model, "no_weight_decay") else set()
     decay, no_decay = [], []
     for name, p in model.named_parameters():
         if not p.requires_grad:
             continue
-        if p.ndim == 1 or name.endswith(".bias") or name in skip or "norm." in name or ".norm" in name:
+        if ("norm." in name or ".norm" in name or name.endswith(".bias") or name.endswith(".lookup_table_weight")
+                or name.endswith(".gamma") or name in skip):
             no_decay.append(p)
         else:
             decay.append(p)

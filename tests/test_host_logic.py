@@ -167,3 +167,22 @@ def test_dead_code_resampling_is_identical_on_all_ranks_gloo():
     assert o0.shape == (9, 8) and torch.equal(o0, o1)
     d = (o0[:, None, :] - pool[None]).abs().sum(-1).min(dim=1).values
     assert float(d.max()) == 0.0                                  # every row is one of the pooled latents
+
+
+def test_param_groups_match_reference_optim_factory():
+    """a18: the decay / no-decay split of `b200fm.optim.param_groups_like_reference` equals what the unmodified reference's
+    `get_parameter_groups` (optim_factory.py:111-168) produced for the same model (fixture: tests/golden/make_golden_param_groups.py)."""
+    import json
+    import os
+    from b200fm.compat import build_mod7_embeddings, create_model
+    from b200fm.optim import param_groups_like_reference
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "param_groups_golden.json")))
+    for tag, kw in {"tiny": {}, "tiny_qknorm": dict(qk_norm=True)}.items():
+        enc, dec, info = build_mod7_embeddings()
+        model = create_model("fm_tiny_6e_6d_swiglu_nobias", encoder_embeddings=enc, decoder_embeddings=dec, modality_info=info, **kw)
+        names = {id(p): n for n, p in model.named_parameters()}
+        groups = param_groups_like_reference(model, 0.05)
+        got = {("decay" if g["weight_decay"] > 0 else "no_decay"): sorted(names[id(p)] for p in g["params"]) for g in groups}
+        assert got["decay"] == gold[tag]["decay"], tag
+        assert got["no_decay"] == gold[tag]["no_decay"], tag
+        assert sorted(model.no_weight_decay()) == gold[tag]["skip_list"]
