@@ -186,3 +186,54 @@ def test_param_groups_match_reference_optim_factory():
         assert got["decay"] == gold[tag]["decay"], tag
         assert got["no_decay"] == gold[tag]["no_decay"], tag
         assert sorted(model.no_weight_decay()) == gold[tag]["skip_list"]
+
+
+def test_all_13_presets_match_reference_state_dict_contract():
+    """Every registered model name builds the same state_dict (keys, order, shapes, dtypes: compared as a digest) and the same number of
+    parameters as the unmodified reference constructor (fixture: tests/golden/make_golden_presets.py; initialisation patched out so the
+    2.8 B parameter XL presets build in seconds from untouched memory)."""
+    import hashlib
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("_mgp", os.path.join(here, "golden", "make_golden_presets.py"))
+    mgp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mgp)
+    from b200fm.compat import build_mod7_embeddings, create_model
+    gold = json.load(open(os.path.join(here, "golden", "presets_golden.json")))
+    assert len(gold) == 13
+    for name, ref in gold.items():
+        with mgp.no_init():
+            enc, dec, info = build_mod7_embeddings()
+            model = create_model(name, encoder_embeddings=enc, decoder_embeddings=dec, modality_info=info)
+        got = mgp.digest(model)
+        assert got == ref, (name, got, ref)
+        del model
+
+
+def test_tokenizer_constructors_match_reference_state_dict_contract():
+    """`fourm.vq.VQ` / `VQVAE` of the overlay build the reference's state_dict (digest of keys, order, shapes, dtypes) for the ViT-S/B/L
+    encoders / decoders, patch 8 / 16, cosine and Euclidean codebooks, class-label inputs (fixture: make_golden_vq_presets.py)."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location("_" + name, os.path.join(here, "golden", name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.path.insert(0, os.path.join(here, "golden"))
+        try:
+            spec.loader.exec_module(mod)
+        finally:
+            sys.path.remove(os.path.join(here, "golden"))
+        return mod
+    cases = load("make_golden_vq_presets")
+    mgp = load("make_golden_presets")
+    import fourm.vq as vq
+    gold = json.load(open(os.path.join(here, "golden", "vq_presets_golden.json")))
+    for tag, (cls, kw) in cases.CASES.items():
+        with mgp.no_init():
+            m = getattr(vq, cls)(sync_codebook=False, **kw)
+        assert mgp.digest(m) == gold[tag], (tag, mgp.digest(m), gold[tag])
