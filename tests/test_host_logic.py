@@ -237,3 +237,34 @@ def test_tokenizer_constructors_match_reference_state_dict_contract():
         with mgp.no_init():
             m = getattr(vq, cls)(sync_codebook=False, **kw)
         assert mgp.digest(m) == gold[tag], (tag, mgp.digest(m), gold[tag])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/fourm"), reason="needs the reference tree (authoring container only)")
+def test_overlay_resolves_ahead_of_reference_tree():
+    """INTEGRATION.md level 1: with `ml-4m_b200/` ahead of the reference on sys.path, exactly the hot-path modules resolve to the overlay
+    (fourm.models.fm / fm_utils / *_embeddings, fourm.vq) while fourm.utils, fourm.data and fourm.models.generate stay the reference's;
+    the reference's own `create_model` + `MODALITY_INFO` factories then build the overlay classes and `GenerationSampler` wraps them."""
+    code = r'''
+import sys
+sys.path.insert(0, "{root}/tests/golden")
+import ref_import
+ref_import.install(extra_first_paths=["{root}/ml-4m_b200"])
+import fourm.models.fm as fm, fourm.models.fm_utils as fu, fourm.models.encoder_embeddings as ee, fourm.vq as vq
+import fourm.utils as utils, fourm.models.generate as gen
+from fourm.data.modality_info import MODALITY_INFO
+ov, ref = "{root}/ml-4m_b200/", "/root/reference/"
+assert fm.__file__.startswith(ov) and fu.__file__.startswith(ov) and ee.__file__.startswith(ov) and vq.__file__.startswith(ov)
+assert utils.__file__.startswith(ref) and gen.__file__.startswith(ref)
+mods = ["rgb@224", "caption", "tok_depth@224"]
+mk = lambda m, side: MODALITY_INFO[m][side]() if MODALITY_INFO[m]["type"] != "img" else MODALITY_INFO[m][side](patch_size=16, image_size=224)
+enc = {{m: mk(m, "encoder_embedding") for m in mods}}
+dec = {{m: mk(m, "decoder_embedding") for m in mods[1:]}}
+model = utils.create_model("fm_tiny_6e_6d_swiglu_nobias", encoder_embeddings=enc, decoder_embeddings=dec, modality_info={{m: MODALITY_INFO[m] for m in mods}})
+assert type(model).__module__ == "fourm.models.fm" and sys.modules["fourm.models.fm"].__file__.startswith(ov)
+assert hasattr(model.encoder[0], "forward_pending")            # the overlay's block, not the reference's
+gen.GenerationSampler(model)
+print("OK")
+'''.format(root=ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd="/tmp",
+                         env={**os.environ, "PYTHONPATH": ""})
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-2000:]
