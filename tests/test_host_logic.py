@@ -268,3 +268,24 @@ print("OK")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd="/tmp",
                          env={**os.environ, "PYTHONPATH": ""})
     assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-2000:]
+
+
+def test_hub_wrapper_fm_config_matches_reference():
+    """`fourm.models.fm.FM(config)` (the class Demo4MSampler / from_pretrained instantiate, fm.py:783-831) builds the reference's
+    state_dict for a 4M-7-style config (untied decoder heads) and a small GELU / bias config (fixture: make_golden_fm_config.py)."""
+    import importlib.util
+    import json
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    try:
+        spec = importlib.util.spec_from_file_location("_mgfc", os.path.join(here, "golden", "make_golden_fm_config.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path.remove(os.path.join(here, "golden"))
+    from fourm.models.fm import FM
+    gold = json.load(open(os.path.join(here, "golden", "fm_config_golden.json")))
+    for tag, cfg in mod.CONFIGS.items():
+        with mod.MGP.no_init():
+            m = FM(cfg)
+        assert mod.MGP.digest(m) == gold[tag], (tag, mod.MGP.digest(m), gold[tag])
