@@ -38,6 +38,12 @@ const char* b200fm_last_error(void);
 int b200fm_abi_version(void);
 int b200fm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin);
 
+/* Runtime options (defaults from the environment variable B200FM_<NAME upper-case>): "pdl" (1: programmatic dependent launch),
+ * "gemm_cta_pairs" (1: cta_group::2 GEMM tiles), "ln_bwd_v2" (0: experimental LayerNorm-backward variant).  Changing an
+ * option affects launches issued afterwards; meant for A/B measurements inside one process.                          */
+int b200fm_set_option(const char* name, int value);
+int b200fm_get_option(const char* name, int* value);
+
 /* ---- dense contractions (tcgen05) ---------------------------------------------------------------------------
  * Replaces every nn.Linear / F.linear on the path: fourm/models/fm_utils.py:155-157,163,178 (qkv, proj),
  * :190-194,200-201,217 (q, kv, proj), :136-144 (GatedMlp fc1/fc3/fc2), :116-125 (Mlp), fourm/models/fm.py:154,679

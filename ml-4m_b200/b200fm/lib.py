@@ -25,6 +25,8 @@ KIND_IMG, KIND_TOK_IMG, KIND_SEQ, KIND_SEQ_EMB = 0, 1, 2, 3
 SIGNATURES = {
     "b200fm_abi_version": [],
     "b200fm_device_info": [c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "b200fm_set_option": [ctypes.c_char_p, c_int],
+    "b200fm_get_option": [ctypes.c_char_p, c_void_p],
     "b200fm_gemm_bf16": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll,
                          c_void_p, c_void_p, c_ll, c_float, c_void_p, c_void_p],
     "b200fm_layernorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p],
@@ -120,3 +122,14 @@ def call(name, *args):
     rc = fn(*args)
     if rc != 0:
         check(rc, name)
+
+
+def set_option(name: str, value: int) -> None:
+    """Runtime option of the kernel library (include/b200fm.h: "pdl", "gemm_cta_pairs", "ln_bwd_v2"); for in-process A/B measurements."""
+    check(load().b200fm_set_option(name.encode(), int(value)), "b200fm_set_option")
+
+
+def get_option(name: str) -> int:
+    v = ctypes.c_int(0)
+    check(load().b200fm_get_option(name.encode(), ctypes.byref(v)), "b200fm_get_option")
+    return v.value

@@ -21,7 +21,9 @@ namespace b200fm {
 B200FM_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 B200FM_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 B200FM_DEVINL void pdl_enter() { pdl_trigger(); pdl_wait(); }
-bool pdl_enabled();      // runtime.cu: env B200FM_PDL (default 1)
+enum { kOptPdl = 0, kOptGemmCtaPairs = 1, kOptLnBwdV2 = 2, kOptCount = 3 };
+int option(int id);      // runtime.cu: value of a runtime option (env default, b200fm_set_option override)
+bool pdl_enabled();      // option "pdl" (env B200FM_PDL, default 1)
 #define B200FM_LAUNCH(...) (void)::b200fm::launch_pdl(__VA_ARGS__)
 
 template <typename... KArgs, typename... Args>

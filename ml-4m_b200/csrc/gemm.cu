@@ -435,14 +435,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
     return 0;
 }
 
-static bool use_cta_pairs() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("B200FM_GEMM_CTA_PAIRS");
-        v = (e == nullptr || e[0] != '0') ? 1 : 0;
-    }
-    return v == 1;
-}
+static bool use_cta_pairs() { return option(kOptGemmCtaPairs) != 0; }
 
 }  // namespace b200fm
 

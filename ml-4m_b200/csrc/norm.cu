@@ -141,6 +141,85 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, c
     }
 }
 
+// EXPERIMENTAL variant (option "ln_bwd_v2", default off, not yet measured on hardware): identical arithmetic, but the dres loads are
+// issued together with x / dy instead of after the two warp reductions, so a row costs one memory round trip instead of two.
+template <int VEC, bool DY_BF16>
+__global__ void __launch_bounds__(kLnWarps * 32)
+layernorm_bwd_v2_kernel(const void* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ dres,
+                     float* __restrict__ dx_out, __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, int rows) {
+    pdl_enter();
+    constexpr int D = VEC * 128;
+    __shared__ float red[kLnWarps][128 + 4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 g[VEC], pg[VEC], pb[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        g[i] = reinterpret_cast<const float4*>(gamma)[i * 32 + lane];
+        pg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int row = blockIdx.x * kLnWarps + warp; row < rows; row += gridDim.x * kLnWarps) {
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+        float4 xh[VEC], dyv[VEC], rv[VEC];
+        float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)       // the residual gradient does not depend on the reductions: fetch it with the first phase
+            rv[i] = dres ? __ldcs(reinterpret_cast<const float4*>(dres + (size_t)row * D) + i * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float4 xv = xr[i * 32 + lane];
+            if constexpr (DY_BF16) {
+                const uint2 u = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy) + (size_t)row * D)[i * 32 + lane];
+                const float2 a = unpack_bf16x2(u.x), c = unpack_bf16x2(u.y);
+                dyv[i] = make_float4(a.x, a.y, c.x, c.y);
+            } else {
+                dyv[i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + (size_t)row * D)[i * 32 + lane];
+            }
+            xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+            const float4 gy = make_float4(dyv[i].x * g[i].x, dyv[i].y * g[i].y, dyv[i].z * g[i].z, dyv[i].w * g[i].w);
+            c1 += (gy.x + gy.y) + (gy.z + gy.w);
+            c2 += (gy.x * xh[i].x + gy.y * xh[i].y) + (gy.z * xh[i].z + gy.w * xh[i].w);
+            pg[i].x += dyv[i].x * xh[i].x; pg[i].y += dyv[i].y * xh[i].y; pg[i].z += dyv[i].z * xh[i].z; pg[i].w += dyv[i].w * xh[i].w;
+            pb[i].x += dyv[i].x; pb[i].y += dyv[i].y; pb[i].z += dyv[i].z; pb[i].w += dyv[i].w;
+        }
+        c1 = warp_sum(c1) * (1.0f / D);
+        c2 = warp_sum(c2) * (1.0f / D);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float4 o;
+            o.x = rstd * (dyv[i].x * g[i].x - c1 - xh[i].x * c2);
+            o.y = rstd * (dyv[i].y * g[i].y - c1 - xh[i].y * c2);
+            o.z = rstd * (dyv[i].z * g[i].z - c1 - xh[i].z * c2);
+            o.w = rstd * (dyv[i].w * g[i].w - c1 - xh[i].w * c2);
+            o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w;
+            reinterpret_cast<float4*>(dx_out + (size_t)row * D)[i * 32 + lane] = o;
+            if (dx_bf16)
+                reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * D)[i * 32 + lane] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+        }
+    }
+    if (dgamma == nullptr && dbeta == nullptr) return;
+    // block reduce the per-warp column partials (128 columns at a time), then one atomic per column per block
+    for (int pass = 0; pass < 2; ++pass) {
+        float* dst = pass == 0 ? dgamma : dbeta;
+        if (dst == nullptr) continue;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            __syncthreads();
+            *reinterpret_cast<float4*>(&red[warp][lane * 4]) = pass == 0 ? pg[i] : pb[i];
+            __syncthreads();
+            if (threadIdx.x < 128) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < kLnWarps; ++w) s += red[w][threadIdx.x];
+                atomicAdd(dst + i * 128 + threadIdx.x, s);
+            }
+        }
+    }
+}
+
 // ---- per-head LayerNorm over head_dim = 64 (qk_norm presets: NormAttention / NormCrossAttention, fm_utils.py:244-245, 290-291)
 // x bf16 [rows, ldx]: head h occupies columns [h*64, h*64+64) (x may be a column slice of a packed qkv buffer);
 // y bf16 [rows, ldy] = bf16(LN_fp32(x) * gamma + beta) -- F.layer_norm under autocast computes in fp32, the following
@@ -261,9 +340,11 @@ extern "C" int b200fm_layernorm_bwd(const void* dy, int dy_is_bf16, const float*
     B200FM_CHECK(D % 128 == 0 && D >= 128 && D <= 2048, "layernorm_bwd: D=%d unsupported", D);
     int grid = ln_grid(rows);
     if (grid > 148 * 2) grid = 148 * 2;       // fewer blocks -> fewer column atomics
+    const bool v2 = option(kOptLnBwdV2) != 0;
 #define LN_BWD(V)                                                                                                          \
     case V:                                                                                                                \
-        if (dy_is_bf16) B200FM_LAUNCH((layernorm_bwd_kernel<V, true>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, dy, x, gamma, mean, rstd, dres, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows); \
+        if (v2 && dy_is_bf16) B200FM_LAUNCH((layernorm_bwd_v2_kernel<V, true>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, dy, x, gamma, mean, rstd, dres, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows); \
+        else if (dy_is_bf16) B200FM_LAUNCH((layernorm_bwd_kernel<V, true>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, dy, x, gamma, mean, rstd, dres, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows); \
         else B200FM_LAUNCH((layernorm_bwd_kernel<V, false>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, dy, x, gamma, mean, rstd, dres, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows);          \
         break;
     switch (D / 128) {

@@ -11,15 +11,26 @@
 
 namespace b200fm {
 
-bool pdl_enabled() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("B200FM_PDL");
-        v = (e && e[0] == '0') ? 0 : 1;
+// ---- runtime options: defaults from the environment (B200FM_<NAME>), changeable in-process through b200fm_set_option so that two
+// variants can be measured back to back in ONE process on ONE box (box-to-box variance of the pool is ~3 %)
+struct OptionSlot { const char* name; const char* env; int def; int value; bool init; };
+static OptionSlot g_options[kOptCount] = {
+    {"pdl", "B200FM_PDL", 1, 1, false},                        // programmatic dependent launch on every kernel
+    {"gemm_cta_pairs", "B200FM_GEMM_CTA_PAIRS", 1, 1, false},  // tcgen05 cta_group::2 GEMM tiles
+    {"ln_bwd_v2", "B200FM_LN_BWD_V2", 0, 0, false},            // EXPERIMENTAL (not yet measured): LayerNorm backward with the dres loads hoisted
+};
+
+int option(int id) {
+    OptionSlot& o = g_options[id];
+    if (!o.init) {
+        const char* e = getenv(o.env);
+        o.value = (e && e[0] != '\0') ? atoi(e) : o.def;
+        o.init = true;
     }
-    return v == 1;
+    return o.value;
 }
 
+bool pdl_enabled() { return option(kOptPdl) != 0; }
 
 static thread_local char g_err[1024] = "";
 
@@ -98,6 +109,29 @@ extern "C" {
 const char* b200fm_last_error(void) { return b200fm::g_err; }
 
 int b200fm_abi_version(void) { return B200FM_ABI_VERSION; }
+
+int b200fm_set_option(const char* name, int value) {
+    B200FM_CHECK(name != nullptr, "set_option: null name");
+    for (int i = 0; i < b200fm::kOptCount; ++i)
+        if (strcmp(b200fm::g_options[i].name, name) == 0) {
+            b200fm::g_options[i].value = value;
+            b200fm::g_options[i].init = true;
+            return 0;
+        }
+    B200FM_CHECK(false, "set_option: unknown option '%s'", name);
+    return 1;
+}
+
+int b200fm_get_option(const char* name, int* value) {
+    B200FM_CHECK(name != nullptr && value != nullptr, "get_option: null pointer");
+    for (int i = 0; i < b200fm::kOptCount; ++i)
+        if (strcmp(b200fm::g_options[i].name, name) == 0) {
+            *value = b200fm::option(i);
+            return 0;
+        }
+    B200FM_CHECK(false, "get_option: unknown option '%s'", name);
+    return 1;
+}
 
 int b200fm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin) {
     cudaDeviceProp p;

@@ -45,3 +45,15 @@ def test_ops_refuse_cpu_tensors(built):
     from b200fm import ops
     with pytest.raises(built.B200FMError):
         ops.vq_argmax(torch.zeros(4, 32), torch.zeros(8, 32))
+
+
+def test_runtime_options_roundtrip(built):
+    """b200fm_set_option / b200fm_get_option (no GPU needed): defaults, override, unknown names are errors with a message."""
+    from b200fm import lib
+    assert lib.get_option("pdl") == 1 and lib.get_option("gemm_cta_pairs") == 1 and lib.get_option("ln_bwd_v2") == 0
+    lib.set_option("pdl", 0)
+    assert lib.get_option("pdl") == 0
+    lib.set_option("pdl", 1)
+    assert lib.get_option("pdl") == 1
+    with pytest.raises(lib.B200FMError, match="unknown option"):
+        lib.set_option("no_such_option", 1)

@@ -106,3 +106,28 @@ def test_vq_scan_full_size_properties():
     assert torch.equal(idx, idx2)
     sub = torch.arange(0, 131072, 257)
     _check_scan(idx.cpu()[sub], V.cosine_scan(z[sub], cb), V.scan_scores(z[sub], cb, True), 1e-6)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("B200FM_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental kernel variants are validated on demand (B200FM_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("rows,D", [(37, 384), (16384, 768), (300, 1024)])
+def test_layernorm_bwd_v2_matches_v1(rows, D):
+    """Option "ln_bwd_v2" (dres loads hoisted ahead of the reductions) must reproduce the default kernel bit for bit on dx."""
+    from b200fm import lib, ops
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(rows, D, generator=g) * 2 + 0.3).cuda()
+    w = (torch.randn(D, generator=g) * 0.1 + 1).cuda()
+    dy = torch.randn(rows, D, generator=g).to(torch.bfloat16).cuda()
+    dres = torch.randn(rows, D, generator=g).cuda()
+    _, mean, rstd = ops.layernorm_fwd(x, w, None, 1e-6)
+    outs = []
+    for v in (0, 1):
+        lib.set_option("ln_bwd_v2", v)
+        try:
+            dgamma = torch.zeros(D, device="cuda")
+            dx, dxb = ops.layernorm_bwd(dy, x, w, mean, rstd, dres=dres, want_bf16=True, dgamma=dgamma)
+            outs.append((dx.clone(), dxb.clone(), dgamma.clone()))
+        finally:
+            lib.set_option("ln_bwd_v2", 0)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    torch.testing.assert_close(outs[0][2], outs[1][2], rtol=1e-4, atol=1e-4 * rows ** 0.5)
