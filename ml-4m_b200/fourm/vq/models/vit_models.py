@@ -7,6 +7,7 @@ tokenizer checkpoints load unchanged.  Patchify is a gather + tcgen05 GEMM (the 
 exactly that), blocks run LayerNorm -> bf16 GEMMs (bias + GELU in the epilogue) -> fused attention (no mask).
 Contractions are bf16 with fp32 accumulation; the reference runs this path in fp32 -- tolerance stated in the tests."""
 import math
+import weakref
 from functools import partial
 from typing import Optional
 
@@ -135,17 +136,19 @@ def _init_vit(module):
 
 
 class _ConvAsLinear:
-    """k = s = P Conv2d weight [O, C, P, P] viewed as a Linear over '(ph pw c)'-ordered patches (cached per version)."""
+    """k = s = P Conv2d weight [O, C, P, P] viewed as a Linear over '(ph pw c)'-ordered patches (cached per parameter version;
+    the entry remembers WHICH parameter it mirrors: id() values and device addresses are recycled when models are re-created)."""
     _cache = {}
 
     @classmethod
     def weight(cls, conv):
-        key = id(conv.weight)
-        ver = (conv.weight._version, conv.weight.data_ptr())
+        p = conv.weight
+        key = id(p)
+        ver = (p._version, p.data_ptr())
         hit = cls._cache.get(key)
-        if hit is None or hit[0] != ver:
-            w = conv.weight.detach().permute(0, 2, 3, 1).reshape(conv.weight.shape[0], -1).float().contiguous()
-            hit = (ver, ops.cast_bf16(w))
+        if hit is None or hit[0] != ver or hit[2]() is not p:
+            w = p.detach().permute(0, 2, 3, 1).reshape(p.shape[0], -1).float().contiguous()
+            hit = (ver, ops.cast_bf16(w), weakref.ref(p))
             cls._cache[key] = hit
         return hit[1]
 
