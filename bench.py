@@ -26,8 +26,21 @@ for _p in (ROOT, os.path.join(ROOT, "ml-4m_b200")):
 import torch  # noqa: E402
 
 MODEL = "fm_base_12e_12d_swiglu_nobias"
-DIMS = dict(D=768, Le=12, Ld=12, heads=12, H=2048)
-VBAR = (16384 + 8192 + 8192 + 4096 + 8192) * 22 / 128 + 30000 * 18 / 128      # token-weighted mean target vocab
+# driver-measurable workloads (BASELINE.json configs[1], [2], [4]; configs[3] = `gen`): per-GPU batch and token budget are the
+# reference configs' (cfgs/default/4m/models/main/4m-{b,l}_mod7_500b.yaml:28)
+WORKLOADS = {
+    "4m-b": dict(model="fm_base_12e_12d_swiglu_nobias", batch=128, tokens=128, D=768, Le=12, Ld=12, H=2048,
+                 name="4M-B mod7 full train step (fwd+bwd+gradient all-reduce+AdamW), BASELINE.json configs[1]"),
+    "4m-l": dict(model="fm_large_24e_24d_swiglu_nobias", batch=64, tokens=256, D=1024, Le=24, Ld=24, H=2730,
+                 name="4M-L mod7 full train step (fwd+bwd+gradient all-reduce+AdamW), 256+256 tokens, BASELINE.json configs[2]"),
+}
+
+
+def vbar(n_tok):
+    """token-weighted mean target vocabulary of the synthetic mod-7 batch."""
+    from b200fm.synthetic import budgets_for
+    _, _, n_img, n_seq = budgets_for(n_tok)
+    return ((16384 + 8192 + 8192 + 4096 + 8192) * n_img + 2 * 30000 * (n_seq - 1)) / n_tok
 
 
 def flops_per_sample_fwd(N, M, D=768, Le=12, Ld=12, H=2048):
@@ -35,7 +48,7 @@ def flops_per_sample_fwd(N, M, D=768, Le=12, Ld=12, H=2048):
     enc = 8 * N * D * D + 4 * N * N * D + 6 * N * D * H
     dec = (8 * M * D * D + 4 * M * M * D) + (4 * M * D * D + 4 * N * D * D + 4 * M * N * D) + 6 * M * D * H
     blocks = Le * enc + Ld * dec
-    extras = 2 * N * D * D + 2 * M * D * VBAR + 2 * 196 * 768 * D
+    extras = 2 * N * D * D + 2 * M * D * vbar(M) + 2 * 196 * 768 * D
     return blocks, blocks + extras
 
 
@@ -99,13 +112,58 @@ def gemm_traffic_per_launch():
         return None
 
 
-def cpu_reference_steps(steps, warmup, sample_B, n_tok, threads=None):
-    """Times fwd+bwd of the oracle restatement of FourM.forward (4M-B mod7, fp32, host threads per cpu_threads())."""
+def reference_tree():
+    """Path of the unmodified apple/ml-4m tree when it is present (authoring container), else None (GPU box)."""
+    root = os.environ.get("ML4M_REFERENCE", "/root/reference")
+    return root if os.path.isdir(os.path.join(root, "fourm", "models")) else None
+
+
+def _import_real_reference():
+    """Make `fourm` resolve to the unmodified tree (drop the overlay from sys.path / sys.modules) and import it with the shims of
+    tests/golden/ref_import.py.  Only the `--impl reference` arm calls this; it never runs in the same process as the B200 arm."""
+    from b200fm.synthetic import budgets_for  # noqa: F401  (pure python; imported before the overlay directory leaves sys.path)
+    pkg = os.path.join(ROOT, "ml-4m_b200")
+    sys.path[:] = [p for p in sys.path if os.path.abspath(p) != pkg]
+    for k in [k for k in sys.modules if k == "fourm" or k.startswith("fourm.")]:
+        del sys.modules[k]
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import ref_import
+    return ref_import.import_reference_models()
+
+
+def cpu_real_reference_steps(steps, warmup, sample_B, n_tok, model_name):
+    """Times fwd+bwd of the UNMODIFIED reference `FourM.forward` (fm.py:640-691) on the host CPU, fp32 -- only where the
+    reference tree exists (it cannot travel to the GPU box); `kind: "reference"`."""
+    import random
+    from b200fm.synthetic import budgets_for
+    fm, fm_utils, MODALITY_INFO = _import_real_reference()
+    from make_golden import build_reference_fourm, clone_batch
+    from oracle import fourm_oracle as O
+    torch.set_num_threads(cpu_threads())
+    torch.manual_seed(0)
+    model = build_reference_fourm(model_name, O.mod7_specs(), MODALITY_INFO)
+    batch = O.synthetic_mod7_batch(sample_B, *budgets_for(n_tok), seed=1234)
+    times = []
+    for it in range(warmup + steps):
+        random.seed(it)
+        t0 = time.perf_counter()
+        loss, _ = model(clone_batch(batch), num_encoder_tokens=n_tok, num_decoder_tokens=n_tok, loss_type="mod")
+        loss.backward()
+        dt = time.perf_counter() - t0
+        model.zero_grad(set_to_none=True)
+        if it >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return sample_B * 2 * n_tok / sec, sec, torch.get_num_threads()
+
+
+def cpu_reference_steps(steps, warmup, sample_B, n_tok, threads=None, model_name=MODEL):
+    """Times fwd+bwd of the oracle restatement of FourM.forward (mod7, fp32, host threads per cpu_threads())."""
     import random
     from oracle import fourm_oracle as O
     torch.set_num_threads(threads or cpu_threads())
     specs = O.mod7_specs()
-    cfg = O.PRESETS[MODEL]
+    cfg = O.PRESETS[model_name]
     g = torch.Generator().manual_seed(0)
     sd = {}
     D = cfg["dim"]
@@ -192,15 +250,25 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_tok = 128
-    B = 8
-    tps, sec, cores = cpu_reference_steps(args.steps, args.warmup, B, n_tok)
+    if args.workload in ("vq-tokenize", "vqvae-train"):
+        return run_vq_reference_arm(args)
+    if args.workload == "gen":
+        return run_gen_reference_arm(args)
+    wl = WORKLOADS[args.workload]
+    n_tok = wl["tokens"]
+    B = 8 if args.workload == "4m-b" else 2
+    if reference_tree() is not None and not os.environ.get("B200FM_CPU_PORT"):
+        tps, sec, cores = cpu_real_reference_steps(args.steps, args.warmup, B, n_tok, wl["model"])
+        kind, what = "reference", "the unmodified reference FourM.forward (fourm/models/fm.py:640-691)"
+    else:
+        tps, sec, cores = cpu_reference_steps(args.steps, args.warmup, B, n_tok, model_name=wl["model"])
+        kind, what = "port", "oracle port of FourM.forward"
     line = dict(metric="tokens_per_sec", value=tps, unit="tokens/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 impl="reference",
-                config=dict(workload="4M-B mod7 train step fwd+bwd (oracle port of FourM.forward on host CPU, fp32)", model=MODEL,
+                config=dict(workload=f"{wl['name'].split(' (')[0]} fwd+bwd ({what} on host CPU, fp32)", model=wl["model"],
                             global_batch=B, seq_len=2 * n_tok, parallelism="cpu"),
-                cpu_baseline=dict(value=tps, unit="tokens/s", cores=cores, kind="port",
+                cpu_baseline=dict(value=tps, unit="tokens/s", cores=cores, kind=kind,
                                   sample=f"fwd+bwd of B={B} samples x {2 * n_tok} tokens per step, fp32, torch CPU {cores} threads of {os.cpu_count()}"),
                 e2e=dict(value=tps, unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
@@ -227,7 +295,10 @@ def run_b200_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     lib.load()
 
-    B, n_tok = args.batch, args.tokens
+    wl = WORKLOADS[args.workload]
+    B = args.batch or wl["batch"]
+    n_tok = args.tokens or wl["tokens"]
+    args.model = args.model or wl["model"]
     torch.manual_seed(0)
     enc, dec, info = build_mod7_embeddings()
     model = create_model(args.model, encoder_embeddings=enc, decoder_embeddings=dec, modality_info=info).to(dev)
@@ -327,17 +398,18 @@ def run_b200_arm(args):
         tokens_per_step = world * B * 2 * n_tok
         tps = tokens_per_step / (ms / args.steps / 1e3)
         tps_e2e = tokens_per_step / (ms_e2e / args.steps / 1e3)
-        blocks, total = flops_per_sample_fwd(n_tok, n_tok)
+        blocks, total = flops_per_sample_fwd(n_tok, n_tok, wl["D"], wl["Le"], wl["Ld"], wl["H"])
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         model_tflops = 3 * total * B * world / (ms / args.steps / 1e3) / 1e12
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            v, sec, cores = cpu_reference_steps(2, 1, 8, n_tok)
+            cb = 8 if args.workload == "4m-b" else 2
+            v, sec, cores = cpu_reference_steps(2, 1, cb, n_tok, model_name=args.model)
             cpu = dict(value=v, unit="tokens/s", cores=cores, kind="port",
-                       sample=f"2 timed fwd+bwd steps (1 warm-up) of B=8 x {2 * n_tok} tokens, oracle port of FourM.forward, fp32, {cores} threads of {os.cpu_count()}")
+                       sample=f"2 timed fwd+bwd steps (1 warm-up) of B={cb} x {2 * n_tok} tokens, oracle port of FourM.forward, fp32, {cores} threads of {os.cpu_count()}")
         line = dict(metric="tokens_per_sec", value=tps, unit="tokens/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-                    config=dict(workload="4M-B mod7 full train step (fwd+bwd+DDP all-reduce+AdamW), BASELINE.json configs[1]",
+                    config=dict(workload=wl["name"],
                                 model=args.model, global_batch=B * world, per_gpu_batch=B, seq_len=2 * n_tok, encoder_tokens=n_tok,
                                 decoder_tokens=n_tok, parallelism=f"dp{world}", params_m=round(n_params / 1e6, 1),
                                 l2_policy="per-step working set (activations+grads > 2 GB) exceeds the 126 MB L2; two alternating input batches"),
@@ -357,19 +429,268 @@ def run_b200_arm(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# VQ tokenizer workloads (BASELINE.json configs[4]: ViT-B @ 256^2, K = 16384, d = 32; per-GPU batch 64 = global 512 on 8 GPUs)
+# ----------------------------------------------------------------------------------------------------------------------
+VQ_KW = dict(enc_type="vit_b_enc", image_size=256, patch_size=16, codebook_size=16384, latent_dim=32, norm_codes=True, post_mlp=True)
+VIT_B_GFLOP_FWD = 48.6            # ViT-B encoder @ 256^2, GFLOP per image forward
+
+
+def _vq_cpu_tokenize(n_img, steps, warmup):
+    """The tokenizer forward on the host CPU: the unmodified reference `VQ.tokenize` (fourm/vq/vqvae.py:318-331) where the
+    tree exists, else the oracle port (oracle/vq_oracle.py)."""
+    torch.set_num_threads(cpu_threads())
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(n_img, 3, 256, 256, generator=g)
+    if reference_tree() is not None and not os.environ.get("B200FM_CPU_PORT"):
+        _import_real_reference()
+        import fourm.vq as rvq
+        torch.manual_seed(0)
+        m = rvq.VQ(sync_codebook=False, **VQ_KW).eval()
+        kind = "reference"
+
+        def run():
+            with torch.no_grad():
+                return m.tokenize(x)
+    else:
+        from oracle import vq_oracle as V
+        import fourm.vq as vq
+        torch.manual_seed(0)
+        sd = {k: v.detach().clone() for k, v in vq.VQ(sync_codebook=False, **VQ_KW).state_dict().items()}
+        kind = "port"
+
+        def run():
+            with torch.no_grad():
+                return V.vq_encode(x, sd, "vit_b_enc", 16, True, True)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        run()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return n_img / sec, sec, torch.get_num_threads(), kind
+
+
+def run_vq_reference_arm(args):
+    if args.workload == "vqvae-train":
+        # the reference's VQVAE training step needs `diffusers`-free imports only (vqvae.py); fwd+bwd on CPU through the real class
+        torch.set_num_threads(cpu_threads())
+        B = 2
+        g = torch.Generator().manual_seed(0)
+        x = torch.randn(B, 3, 256, 256, generator=g)
+        kind = "port"
+        if reference_tree() is not None and not os.environ.get("B200FM_CPU_PORT"):
+            _import_real_reference()
+            import fourm.vq as rvq
+            torch.manual_seed(0)
+            m = rvq.VQVAE(dec_type="vit_b_dec", sync_codebook=False, ema_decay=0.99, **VQ_KW).train()
+            kind = "reference"
+
+            def run():
+                dec, code_loss = m(x)
+                (torch.nn.functional.mse_loss(dec, x) + code_loss.sum()).backward()
+                m.zero_grad(set_to_none=True)
+        else:
+            from oracle import vq_oracle as V
+            import fourm.vq as vq
+            torch.manual_seed(0)
+            kw = dict(VQ_KW, dec_type="vit_b_dec", ema_decay=0.99)
+            sd = {k: v.detach().clone().requires_grad_(v.is_floating_point() and "_codebook" not in k) for k, v in
+                  vq.VQVAE(sync_codebook=False, **kw).state_dict().items()}
+
+            def run():
+                dec, code_loss = V.vqvae_forward_train(x, sd, kw)[:2]
+                (torch.nn.functional.mse_loss(dec, x) + code_loss.sum()).backward()
+                for t in sd.values():
+                    t.grad = None
+        times = []
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            run()
+            if it >= args.warmup:
+                times.append(time.perf_counter() - t0)
+        sec = sum(times) / len(times)
+        val, cores, n_img, what = B / sec, torch.get_num_threads(), B, "VQ-VAE training step fwd+bwd (ViT-B enc + ViT-B dec, K=16384)"
+    else:
+        n_img = 4
+        val, sec, cores, kind = _vq_cpu_tokenize(n_img, args.steps, args.warmup)
+        what = "VQ.tokenize (ViT-B encoder + codebook arg-max, K=16384)"
+    line = dict(metric="images_per_sec", value=val, unit="img/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=sec * 1e3,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=f"{what} 256x256 on host CPU, fp32", global_batch=n_img, parallelism="cpu"),
+                cpu_baseline=dict(value=val, unit="img/s", cores=cores, kind=kind, sample=f"{n_img} images of 256x256 per step, fp32, {cores} threads of {os.cpu_count()}"),
+                e2e=dict(value=val, unit="img/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+def run_vq_arm(args):
+    """`vq-tokenize`: VQ.tokenize on [B,3,256,256] (save_vq_tokens.py:288-303: fp32 images in, int16 tokens out).
+    `vqvae-train`: one VQ-VAE training step (run_training_vqvae.py: encoder + quantizer w/ EMA codebook + ViT-B decoder, MSE, AdamW).
+    Both shard by sample with replicas (vq-tokenize: no collective at all; vqvae-train: DDP + the packed codebook all-reduce)."""
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    import fourm.vq as vq
+    from b200fm import lib, ops
+    from b200fm.optim import FusedAdamW
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (B200 arm) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+    B = args.batch or 64
+    train = args.workload == "vqvae-train"
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(100 + rank)
+    host_x = [torch.randn(B, 3, 256, 256, generator=g).pin_memory() for _ in range(2)]
+    dev_x = [h.to(dev) for h in host_x]
+    if train:
+        model = vq.VQVAE(dec_type="vit_b_dec", sync_codebook=world > 1, ema_decay=0.99, **VQ_KW).to(dev).train()
+        opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, betas=(0.9, 0.99), weight_decay=0.0)
+        net = model
+        if world > 1:
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True, broadcast_buffers=False)
+
+        def step(x):
+            dec, code_loss = net(x)
+            loss = F.mse_loss(dec.float(), x) + code_loss.sum()
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            return loss
+    else:
+        model = vq.VQ(sync_codebook=False, **VQ_KW).to(dev).eval()
+        host_tok = torch.empty(B, 16, 16, dtype=torch.int16).pin_memory()
+
+        def step(x):
+            with torch.no_grad():
+                return model.tokenize(x)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(n, e2e):
+        c0 = lib.CALLS["n"]
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            if e2e:
+                x = host_x[i % 2].to(dev, non_blocking=True)            # 50 MB of fp32 pixels per step from pinned host memory
+                out = step(x)
+                if train:
+                    out.item()
+                else:
+                    host_tok.copy_(out.to(torch.int16), non_blocking=True)   # save_vq_tokens.py:293 stores int16
+                    torch.cuda.current_stream().synchronize()
+            else:
+                out = step(dev_x[i % 2])
+        e1.record()
+        sync()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, lib.CALLS["n"] - c0
+
+    for _ in range(max(args.warmup, 3)):
+        step(dev_x[0])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(args.steps, False)
+    ms_e2e, _ = timed(args.steps, True)
+    clocks = sampler.stop() if rank == 0 else None
+    ops.PROFILE = []
+    step(dev_x[0]); step(dev_x[1])
+    torch.cuda.synchronize()
+    gemm_ms = sum(s.elapsed_time(e) for s, e, _, _ in ops.PROFILE)
+    gemm_flops = sum(f for _, _, f, _ in ops.PROFILE)
+    n_gemm = len(ops.PROFILE)
+    ops.PROFILE = None
+    # the codebook scan alone (fp32-FMA bound, SURVEY.md 8d): n = B*256 latents x K = 16384 x d = 32
+    z = F.normalize(torch.randn(B * 256, 32, device=dev), dim=-1)
+    cbk = F.normalize(torch.randn(16384, 32, device=dev), dim=-1)
+    for _ in range(3):
+        ops.vq_argmax(z, cbk, cosine=True)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); s0.record()
+    for _ in range(10):
+        ops.vq_argmax(z, cbk, cosine=True)
+    s1.record(); torch.cuda.synchronize()
+    scan_ms = s0.elapsed_time(s1) / 10
+    if rank == 0:
+        peaks = measured_peaks()
+        per = ms / args.steps
+        val = world * B / (per / 1e3)
+        val_e2e = world * B / (ms_e2e / args.steps / 1e3)
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        mult = 3 * 2 if train else 1
+        model_tflops = mult * VIT_B_GFLOP_FWD * 1e9 * B / (per / 1e3) / 1e12
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline and not train:
+            v, sec, cores, kind = _vq_cpu_tokenize(2, 1, 1)
+            cpu = dict(value=v, unit="img/s", cores=cores, kind=kind, sample=f"1 timed VQ.tokenize of 2 images 256x256 (1 warm-up), fp32, {cores} threads of {os.cpu_count()}")
+        name = ("VQ-VAE training step (ViT-B enc + dec, K=16384, EMA codebook, MSE, AdamW), BASELINE.json configs[4]" if train else
+                "VQ.tokenize (ViT-B encoder + codebook arg-max K=16384, d=32), 256x256, BASELINE.json configs[4] tokenizer forward")
+        line = dict(metric="images_per_sec", value=val, unit="img/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=per,
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                    config=dict(workload=name, global_batch=B * world, per_gpu_batch=B, image_size=256, tokens_per_image=256, parallelism=f"dp{world}",
+                                l2_policy="two alternating 50 MB input batches; activations exceed the 126 MB L2"),
+                    e2e=dict(value=val_e2e, unit="img/s", h2d_bytes_per_step=host_x[0].numel() * 4, d2h_bytes_per_step=4 if train else B * 256 * 2,
+                             ms_per_step=ms_e2e / args.steps),
+                    gpu_launches=launches, latents_per_sec=val * 256, model_tflops_per_gpu=model_tflops / 1, frac_of_bf16_peak=model_tflops / peaks["bf16"],
+                    roofline=dict(bound="tensor", kernel="gemm_kernel<BN,LAYOUT,EPI> (all tcgen05 GEMM launches of a step)", achieved=achieved, peak=peaks["bf16"],
+                                  unit="TFLOP/s", frac=achieved / peaks["bf16"], traffic=None, peak_source=peaks["src"], launches_per_step=n_gemm // 2,
+                                  gemm_ms_per_step=gemm_ms / 2),
+                    scan=dict(kernel="vq_scan_kernel<32>", bound="fp32 FMA (CUDA cores; HBM traffic is z + idx only)", n=B * 256, K=16384, d=32, ms=scan_ms,
+                              tflops_fp32=2.0 * B * 256 * 16384 * 32 / (scan_ms * 1e-3) / 1e12, algorithmic_gbs=(B * 256 * (32 * 4 + 8) + 16384 * 32 * 4) / (scan_ms * 1e-3) / 1e9),
+                    clocks=clocks)
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_gen_arm(args):
+    from b200fm import genbench
+    genbench.run(args, ClockSampler, measured_peaks, cpu_threads, reference_tree)
+
+
+def run_gen_reference_arm(args):
+    from b200fm import genbench
+    genbench.run_reference(args, cpu_threads, reference_tree)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default=MODEL)
-    ap.add_argument("--batch", type=int, default=128, help="per-GPU batch (cfgs/default/4m/models/main/4m-b_mod7_500b.yaml:28)")
-    ap.add_argument("--tokens", type=int, default=128, help="encoder tokens = decoder tokens per sample")
+    ap.add_argument("--workload", default="4m-b", choices=["4m-b", "4m-l", "vq-tokenize", "vqvae-train", "gen"],
+                    help="4m-b = BASELINE.json configs[1] (the headline metric, default); 4m-l = configs[2]; gen = configs[3] "
+                         "(generation latency); vq-tokenize / vqvae-train = configs[4] (VQ tokenizer forward / training step)")
+    ap.add_argument("--model", default=None)
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the workload's reference config)")
+    ap.add_argument("--tokens", type=int, default=None, help="encoder tokens = decoder tokens per sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload in ("vq-tokenize", "vqvae-train"):
+        run_vq_arm(args)
+    elif args.workload == "gen":
+        run_gen_arm(args)
     else:
         run_b200_arm(args)
 

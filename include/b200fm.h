@@ -167,6 +167,8 @@ typedef struct b200fm_segment {
     int max_length;           /* decoder sequences: positions >= max_length wrap to 0 (decoder_embeddings.py:128) */
     int ids_is_i64;
     int reserved;
+    float* d_pos_emb;         /* backward: [P, D] fp32 gradient of a LEARNABLE positional table (sincos_pos_emb=False), accumulated
+                                 into at row pos_id (NULL for the sincos buffers)                                 */
 } b200fm_segment;
 
 /* Stable partition "first n_keep valid positions, then masked ones, in order" per sample (== argsort(mask+arange*1e-6)[:, :n_keep]).
@@ -184,9 +186,9 @@ int b200fm_embed_rows(const b200fm_segment* segs, int n_seg, int mode, const int
                       const int32_t* pos_id, const uint8_t* pad_mask, const float* mask_token, float* x0, float* emb_out, int B,
                       int n_keep, int D, void* stream);
 /* Backward of embed_rows: dx0 (and demb, optional) fp32 [B, n_keep, D] -> scatter-add into d_token_emb / d_mod_emb / dx_rows of
- * each segment and d_mask_token (decoder image modalities).                                                                 */
+ * each segment and d_mask_token (decoder image modalities); d_pos_emb rows by pos_id when a segment's table is learnable.                                                                 */
 int b200fm_embed_rows_bwd(const b200fm_segment* segs, int n_seg, int mode, const int32_t* src_seg, const int32_t* src_pos,
-                          const uint8_t* pad_mask, const float* dx0, const float* demb, float* d_mask_token, int B, int n_keep,
+                          const int32_t* pos_id, const uint8_t* pad_mask, const float* dx0, const float* demb, float* d_mask_token, int B, int n_keep,
                           int D, void* stream);
 /* Masked-token head index sets (fm.py:589-600 `y[decoder_mod_mask == idx]`): rows_out int32 [n_mods, n_rows] (row-major order,
  * first counts[m] entries valid), counts int32 [n_mods].  mod_ids_dev: device int32 [n_mods].                              */

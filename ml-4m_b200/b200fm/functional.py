@@ -30,6 +30,19 @@ def _root(p):
     return b if b is not None and b.numel() == p.numel() and p.is_contiguous() and b.is_contiguous() else p
 
 
+def _evict(key_id):
+    """weakref callback: the tensor that owned cache entries keyed on `key_id` died -> drop them (re-created models, EMA / eval
+    copies and test suites would otherwise leak their bf16 mirrors, and a recycled id() could alias a dead entry)."""
+    _shadow_views.pop(key_id, None)
+    for k in [k for k in _shadow if (k[0] == key_id if not isinstance(k[0], tuple) else any(e[0] == key_id for e in k))]:
+        _shadow.pop(k, None)
+
+
+def _wref(t):
+    kid = id(t)
+    return weakref.ref(t, lambda _r, kid=kid: _evict(kid))
+
+
 def weight_bf16(*params):
     """bf16 copy of one fp32 weight, or of several concatenated along dim 0 (e.g. [fc1; fc3]), refreshed when any
     source tensor's version counter changes (optimizer steps, load_state_dict).  Rows are zero-padded to a multiple of 8."""
@@ -55,11 +68,16 @@ def weight_bf16(*params):
             ops.cast_bf16(src, view)
             ent = _shadow_views.get(id(root))
             if ent is None or ent[0]() is not root:
-                ent = _shadow_views[id(root)] = (weakref.ref(root), [])
+                ent = _shadow_views[id(root)] = (_wref(root), [])
+            if hit is not None and buf is not hit[1]:
+                # the operand buffer was re-allocated (shape change): forget the mirrors that lived in the old one, or the
+                # fused optimizer would keep refreshing dead memory
+                lo, hi = hit[1].data_ptr(), hit[1].data_ptr() + hit[1].numel() * 2
+                ent[1][:] = [v for v in ent[1] if not lo <= v.data_ptr() < hi]
             if not any(v.data_ptr() == view.data_ptr() for v in ent[1]):
                 ent[1].append(view)
             off += pr
-    _shadow[key] = (ver, buf, tuple(weakref.ref(r) for r in roots))
+    _shadow[key] = (ver, buf, tuple(_wref(r) for r in roots))
     return buf
 
 
@@ -91,7 +109,7 @@ def weight_bf16_padk(param, k_pad):
     with torch.no_grad():
         buf = hit[1] if hit is not None else torch.zeros(param.shape[0], k_pad, device=param.device, dtype=torch.bfloat16)
         buf[:, :param.shape[1]].copy_(param.detach())
-    _shadow[key] = (ver, buf, weakref.ref(param))
+    _shadow[key] = (ver, buf, _wref(param))
     return buf
 
 
@@ -216,7 +234,8 @@ class PatchEmbedFn(torch.autograd.Function):
     """tokens(fp32) = pos + bf16(patches W_lin^T + b): the k = s = P Conv2d patch projection of the ViT tokenizers
     (vq/models/vit_models.py:482-489) as patchify + one GEMM with the positional rows in the epilogue.  conv_weight is the
     module's [O, C, P, P] parameter (state_dict contract); patches are laid out '(ph pw c)', so W_lin = W.permute(0, 2, 3, 1).
-    Backward: dW (TN GEMM on the saved bf16 patches, mapped back to the conv layout), db; images get no gradient."""
+    Backward: dW (TN GEMM on the saved bf16 patches, mapped back to the conv layout), db, and the positional rows' gradient
+    (= dout: a learnable / un-frozen pos_emb reaches it through the caller's reshape); images get no gradient."""
 
     @staticmethod
     def forward(ctx, img, conv_weight, conv_bias, pos_rows, w_lin_bf16, patch):
@@ -224,7 +243,7 @@ class PatchEmbedFn(torch.autograd.Function):
         bias = conv_bias.detach().float() if conv_bias is not None else None
         out = ops.gemm(patches, w_lin_bf16, epilogue=ops.EPI_RESID, bias=bias, resid=pos_rows)
         ctx.save_for_backward(patches)
-        ctx.wshape, ctx.has_bias = conv_weight.shape, conv_bias is not None
+        ctx.wshape, ctx.has_bias, ctx.pshape = conv_weight.shape, conv_bias is not None, pos_rows.shape
         return out
 
     @staticmethod
@@ -237,7 +256,8 @@ class PatchEmbedFn(torch.autograd.Function):
             dw = ops.gemm(d2, patches, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32).view(O, P, P, C).permute(0, 3, 1, 2)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum_bf16(d2)
-        return None, dw, db, None, None, None
+        dpos = dout.reshape(ctx.pshape).float() if ctx.needs_input_grad[3] else None
+        return None, dw, db, dpos, None, None
 
 
 class LinearF32Fn(torch.autograd.Function):
@@ -468,14 +488,16 @@ class HeadGatherFn(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------------------------------
 class EmbedRowsFn(torch.autograd.Function):
     """x0 = x + emb and emb for the kept rows of one side.  `seg_static` holds the non-differentiable part of every
-    segment; the differentiable tensors arrive flat: mask_token, then per segment (token_emb | x_rows, mod_emb)."""
+    segment; the differentiable tensors arrive flat: mask_token, then per segment (token_emb | x_rows, mod_emb, pos_emb).
+    pos_emb gets a gradient only when it is a learnable table (sincos_pos_emb=False: tok_dinov2_global / tok_imagebind_global of
+    the reference's MODALITY_INFO, modality_info.py:280-297); the sincos buffers never require grad."""
 
     @staticmethod
     def forward(ctx, plan, seg_static, D, want_emb, mask_token, *tensors):
         segs = []
         for i, st in enumerate(seg_static):
             d = dict(st)
-            main, mod = tensors[2 * i], tensors[2 * i + 1]
+            main, mod = tensors[3 * i], tensors[3 * i + 1]
             if st["kind"] in (lib.KIND_IMG, lib.KIND_SEQ_EMB):
                 d["x_rows"] = main
             else:
@@ -495,8 +517,8 @@ class EmbedRowsFn(torch.autograd.Function):
         grads, segs = [], []
         for i, st in enumerate(ctx.seg_static):
             d = dict(st)
-            (mshape, _), (eshape, _) = ctx.shapes[2 * i], ctx.shapes[2 * i + 1]
-            need_main, need_mod = ctx.needs_input_grad[5 + 2 * i], ctx.needs_input_grad[5 + 2 * i + 1]
+            (mshape, _), (eshape, _), (pshape, _) = ctx.shapes[3 * i], ctx.shapes[3 * i + 1], ctx.shapes[3 * i + 2]
+            need_main, need_mod, need_pos = ctx.needs_input_grad[5 + 3 * i: 8 + 3 * i]
             gm = None
             if need_main:
                 if st["kind"] in (lib.KIND_IMG, lib.KIND_SEQ_EMB):
@@ -507,7 +529,9 @@ class EmbedRowsFn(torch.autograd.Function):
                     d["d_token_emb"] = gm
             ge = zeros_f32(D, dev) if need_mod else None
             d["d_mod_emb"] = ge
-            grads += [gm, None if ge is None else ge.view(eshape)]
+            gp = torch.zeros(pshape, device=dev, dtype=torch.float32) if need_pos else None
+            d["d_pos_emb"] = gp
+            grads += [gm, None if ge is None else ge.view(eshape), gp]
             segs.append(d)
         dmt = zeros_f32(D, dev) if (ctx.mask_token_shape is not None and ctx.needs_input_grad[4]) else None
         ops.embed_rows_bwd(plan, segs, dx0.contiguous(), None if demb is None else demb.contiguous(), dmt, D)
@@ -644,12 +668,14 @@ class CrossAttnSubLayerFn(torch.autograd.Function):
         dqb = zeros_f32(D, dev) if qnb_grad else None
         dx, dxb = ops.layernorm_bwd(dhq, s2, qnw, qmean, qrstd, dres=d2, want_bf16=has_pend, dgamma=dqg, dbeta=dqb)
         dctx = dcg = dcb = None
-        if ctx.needs_input_grad[2]:
+        # context_norm's own weight / bias train even when the context itself is detached (frozen-encoder fine-tuning,
+        # forward_decoder on a no_grad encoder output): run the dgrad + LayerNorm backward whenever any of the three is wanted
+        if ctx.needs_input_grad[2] or cnw.requires_grad or cnb_grad:
             dhc = ops.gemm(dkv, weight_bf16(kv_w)[:2 * D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
             dcg = zeros_f32(D, dev) if cnw.requires_grad else None
             dcb = zeros_f32(D, dev) if cnb_grad else None
             dctx, _ = ops.layernorm_bwd(dhc, c2, cnw, cmean, crstd, dgamma=dcg, dbeta=dcb)
-            dctx = dctx.view(B, M, D)
+            dctx = dctx.view(B, M, D) if ctx.needs_input_grad[2] else None
         return (dx.view(B, N, D), dxb.view(B, N, D) if has_pend else None, dctx, None, dqg, dqb, dcg, dcb, dq_w, dq_b, dkv_w, dkv_b,
                 dproj_w, dproj_b, None, None, None, None)
 

@@ -15,7 +15,7 @@ class Segment(ctypes.Structure):
     _fields_ = [("mask", c_void_p), ("ids", c_void_p), ("dam", c_void_p), ("token_emb", c_void_p), ("pos_emb", c_void_p),
                 ("mod_emb", c_void_p), ("x_rows", c_void_p), ("d_token_emb", c_void_p), ("d_mod_emb", c_void_p),
                 ("dx_rows", c_void_p), ("padding_idx", c_ll), ("L", c_int), ("kind", c_int), ("mod_id", c_int),
-                ("max_length", c_int), ("ids_is_i64", c_int), ("reserved", c_int)]
+                ("max_length", c_int), ("ids_is_i64", c_int), ("reserved", c_int), ("d_pos_emb", c_void_p)]
 
 
 MAX_SEGMENTS = 24
@@ -52,8 +52,8 @@ SIGNATURES = {
     "b200fm_decoder_attention_mask": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "b200fm_embed_rows": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                           c_int, c_int, c_void_p],
-    "b200fm_embed_rows_bwd": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                              c_int, c_void_p],
+    "b200fm_embed_rows_bwd": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                              c_int, c_int, c_void_p],
     "b200fm_head_rows": [c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
     "b200fm_gather_rows_bf16": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "b200fm_gather_i64": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p],

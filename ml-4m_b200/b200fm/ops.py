@@ -308,7 +308,7 @@ def make_segments(seg_dicts):
     keep = []
     for i, d in enumerate(seg_dicts):
         s = arr[i]
-        for name in ("mask", "ids", "dam", "token_emb", "pos_emb", "mod_emb", "x_rows", "d_token_emb", "d_mod_emb", "dx_rows"):
+        for name in ("mask", "ids", "dam", "token_emb", "pos_emb", "mod_emb", "x_rows", "d_token_emb", "d_mod_emb", "dx_rows", "d_pos_emb"):
             t = d.get(name)
             if t is not None:
                 _need_cuda(t)
@@ -371,7 +371,7 @@ def embed_rows_bwd(plan, seg_dicts, dx0, demb, d_mask_token, D):
     arr, keep = make_segments(seg_dicts)
     assert dx0.is_contiguous() and dx0.dtype == torch.float32 and (demb is None or (demb.is_contiguous() and demb.dtype == torch.float32))
     lib.call("b200fm_embed_rows_bwd", ctypes.addressof(arr), len(seg_dicts), plan.decoder, _ptr(plan.src_seg), _ptr(plan.src_pos),
-             _ptr(plan.pad_mask), _ptr(dx0), _ptr(demb), _ptr(d_mask_token), plan.B, plan.n_keep, D, _stream())
+             _ptr(plan.pos_id), _ptr(plan.pad_mask), _ptr(dx0), _ptr(demb), _ptr(d_mask_token), plan.B, plan.n_keep, D, _stream())
 
 
 def head_rows(mod_mask, mod_ids_dev):

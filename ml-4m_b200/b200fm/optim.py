@@ -56,10 +56,13 @@ class FusedAdamW(torch.optim.Optimizer):
                 loss = closure()
         for gi, group in enumerate(self.param_groups):
             b1, b2 = group["betas"]
-            tensors, extra_casts, step_no, updated = [], [], None, []
+            tensors, extra_casts, step_no, updated, keepalive = [], [], None, [], []
             for p in group["params"]:
                 if p.grad is None:
                     continue
+                if p.dtype != torch.float32:
+                    raise TypeError(f"FusedAdamW updates fp32 master parameters only (got {p.dtype}); the reference keeps fp32 "
+                                    "parameters under autocast (run_training_4m.py:512), use torch.optim.AdamW for anything else")
                 st = self.state[p]
                 if not st:
                     st["step"] = 0
@@ -70,12 +73,14 @@ class FusedAdamW(torch.optim.Optimizer):
                 if step_no is None:
                     step_no = st["step"]
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                if g.dtype != torch.float32:
+                    g = g.float()
                 if g is not p.grad:
-                    st["_g_keepalive"] = g
-                if st["step"] != step_no or g.dtype != torch.float32 or p.dtype != torch.float32:
-                    # stragglers (different step count / dtype): single-tensor kernel
+                    keepalive.append(g)                  # local: must outlive the launch, must not end up in state_dict()
+                if st["step"] != step_no:
+                    # stragglers (a parameter that joined later has a different step count): single-tensor kernel
                     views = BF.shadow_views(p)
-                    ops.adamw_step(p.data, g.float(), st["exp_avg"], st["exp_avg_sq"], group["lr"], b1, b2, group["eps"],
+                    ops.adamw_step(p.data, g, st["exp_avg"], st["exp_avg_sq"], group["lr"], b1, b2, group["eps"],
                                    group["weight_decay"], st["step"], grad_scale, shadow=views[0] if views else None)
                     extra_casts += [(p, v) for v in views[1:]]
                     continue

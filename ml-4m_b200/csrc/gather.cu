@@ -195,20 +195,35 @@ embed_kernel(const SegTable tab, const int32_t* __restrict__ src_seg, const int3
 }
 
 // Backward scatter: token-table rows (vector fp32 atomics; padding_idx rows skipped like nn.Embedding), pixel-patch rows
-// (bf16 copy for the patch-projection wgrad), one warp per kept row.
+// (bf16 copy for the patch-projection wgrad), learnable positional tables (d_pos_emb[pos_id] += dx0 + demb; the sincos
+// buffers of the shipped configs pass NULL), one warp per kept row.
 template <int VEC>
 __global__ void __launch_bounds__(256)
 embed_bwd_scatter_kernel(const SegTable tab, const int32_t* __restrict__ src_seg, const int32_t* __restrict__ src_pos,
-                         const uint8_t* __restrict__ pad_mask, const float* __restrict__ dx0, long long rows, int n_keep) {
+                         const int32_t* __restrict__ pos_id, const uint8_t* __restrict__ pad_mask, const float* __restrict__ dx0,
+                         const float* __restrict__ demb, long long rows, int n_keep) {
     pdl_enter();
     constexpr int D = VEC * 128;
     const int lane = threadIdx.x & 31;
     for (long long row = blockIdx.x * 8ll + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8ll) {
         if (pad_mask[row]) continue;
         const b200fm_segment& sg = tab.seg[src_seg[row]];
-        if (tab.decoder && sg.kind != B200FM_KIND_SEQ) continue;              // mask-token rows: handled by the modality sums
         const int b = (int)(row / n_keep), l = src_pos[row];
         const float4* g = reinterpret_cast<const float4*>(dx0 + row * D);
+        if (sg.d_pos_emb != nullptr && pos_id != nullptr) {
+            const int pid = pos_id[row];
+            if (pid >= 0) {
+                float4* dst = reinterpret_cast<float4*>(sg.d_pos_emb + (long long)pid * D);
+                const float4* ge = demb ? reinterpret_cast<const float4*>(demb + row * D) : nullptr;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    float4 v = tab.sum_mode ? g[i * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ge) { const float4 e = ge[i * 32 + lane]; v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w; }
+                    atomicAdd(dst + i * 32 + lane, v);
+                }
+            }
+        }
+        if (tab.decoder && sg.kind != B200FM_KIND_SEQ) continue;              // mask-token rows: handled by the modality sums
         if (seg_rows_from_gemm(sg)) {
             if (sg.dx_rows == nullptr) continue;
             uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(sg.dx_rows) + ((long long)b * sg.L + l) * D);
@@ -402,7 +417,7 @@ extern "C" int b200fm_embed_rows(const b200fm_segment* segs, int n_seg, int mode
 }
 
 extern "C" int b200fm_embed_rows_bwd(const b200fm_segment* segs, int n_seg, int mode, const int32_t* src_seg, const int32_t* src_pos,
-                                     const uint8_t* pad_mask, const float* dx0, const float* demb, float* d_mask_token, int B, int n_keep,
+                                     const int32_t* pos_id, const uint8_t* pad_mask, const float* dx0, const float* demb, float* d_mask_token, int B, int n_keep,
                                      int D, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (B == 0) return 0;
@@ -412,7 +427,7 @@ extern "C" int b200fm_embed_rows_bwd(const b200fm_segment* segs, int n_seg, int 
     B200FM_CHECK(src_seg && src_pos && pad_mask && dx0, "embed_rows_bwd: null pointer");
     const long long rows = (long long)B * n_keep;
     const int grid = (int)((rows + 7) / 8 < 148 * 8 ? (rows + 7) / 8 : 148 * 8);
-    B200FM_VEC_SWITCH(D, (B200FM_LAUNCH((embed_bwd_scatter_kernel<V>), dim3(grid), dim3(256), 0, stream, 1, t, src_seg, src_pos, pad_mask, dx0, rows, n_keep)));
+    B200FM_VEC_SWITCH(D, (B200FM_LAUNCH((embed_bwd_scatter_kernel<V>), dim3(grid), dim3(256), 0, stream, 1, t, src_seg, src_pos, pos_id, pad_mask, dx0, demb, rows, n_keep)));
     B200FM_CUDA(cudaGetLastError());
     const int splits = (int)(rows / 512 > 0 ? (rows / 512 > 32 ? 32 : rows / 512) : 1);
     B200FM_LAUNCH(embed_bwd_modsum_kernel, dim3(dim3(n_seg, D / 128, splits)), dim3(128), 0, stream, 1, t, src_seg, pad_mask, dx0, demb, d_mask_token, rows, D);

@@ -29,5 +29,5 @@ def materialise(module, d, mask_key, decoder_clamp):
     plan_seg = dict(seg_static)
     mode = ops.MODE_IDENTITY | ops.MODE_NO_SUM
     plan = ops.select_plan([plan_seg], mode, B, L, dev)
-    x, emb = BF.EmbedRowsFn.apply(plan, [seg_static], module.dim_tokens, True, None, main, mod)
+    x, emb = BF.EmbedRowsFn.apply(plan, [seg_static], module.dim_tokens, True, None, main, mod, module.pos_emb)
     return x, emb

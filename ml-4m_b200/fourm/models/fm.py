@@ -188,7 +188,7 @@ class FourM(nn.Module):
                 if "dam" not in st:
                     raise KeyError(f"modality {mod}: 'decoder_attention_mask' missing from mod_dict")
             seg_static.append(st)
-            tensors += [main, mod_emb]
+            tensors += [main, mod_emb, embs[mod].pos_emb]
             B = d['tensor'].shape[0]
         dev = tensors[1].device
         if dev.type != "cuda":

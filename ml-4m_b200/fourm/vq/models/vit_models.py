@@ -148,7 +148,7 @@ class _ConvAsLinear:
         hit = cls._cache.get(key)
         if hit is None or hit[0] != ver or hit[2]() is not p:
             w = p.detach().permute(0, 2, 3, 1).reshape(p.shape[0], -1).float().contiguous()
-            hit = (ver, ops.cast_bf16(w), weakref.ref(p))
+            hit = (ver, ops.cast_bf16(w), weakref.ref(p, lambda _r, key=key: cls._cache.pop(key, None)))   # evicted with its parameter
             cls._cache[key] = hit
         return hit[1]
 
