@@ -98,7 +98,7 @@ def test_segment_struct_layout_matches_header():
     body = text[text.index("typedef struct b200fm_segment {"):text.index("} b200fm_segment;")]
     fields = re.findall(r"\b(\w+);\s*(?:/\*|$)", body, flags=re.M)
     assert fields == [f[0] for f in lib.Segment._fields_]
-    assert ctypes.sizeof(lib.Segment) == 10 * 8 + 8 + 6 * 4
+    assert ctypes.sizeof(lib.Segment) == 10 * 8 + 8 + 6 * 4 + 8
     assert int(re.search(r"#define B200FM_MAX_SEGMENTS (\d+)", text).group(1)) == lib.MAX_SEGMENTS
 
 
@@ -113,7 +113,7 @@ def test_bench_reference_arm_contract_under_torchrun_world2():
     assert len(lines) == 1
     j = json.loads(lines[0])
     assert j["impl"] == "reference" and j["metric"] == "tokens_per_sec" and j["value"] > 0 and j["n_gpus"] == 2
-    assert j["cpu_baseline"]["kind"] == "port" and j["e2e"]["h2d_bytes_per_step"] == 0
+    assert j["cpu_baseline"]["kind"] in ("port", "reference") and j["e2e"]["h2d_bytes_per_step"] == 0
 
 
 def test_device_prefetcher_order_cpu_fallback_refused():
