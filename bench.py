@@ -304,12 +304,21 @@ def run_b200_arm(args):
     model = create_model(args.model, encoder_embeddings=enc, decoder_embeddings=dec, modality_info=info).to(dev)
     n_params = sum(p.numel() for p in model.parameters())
     lr = 1e-4 * B * world / 256                                 # run_training_4m.py:496-503 scaling rule
-    opt = FusedAdamW(param_groups_like_reference(model, 0.05), lr=lr, betas=(0.9, 0.95), eps=1e-8)
-    net = model
+    groups = param_groups_like_reference(model, 0.05)
+    net, sync, comm = model, None, "none"
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False,
-                                                        gradient_as_bucket_view=True, broadcast_buffers=False,
-                                                        bucket_cap_mb=int(os.environ.get("B200FM_DDP_BUCKET_MB", "25")))
+        comm = os.environ.get("B200FM_COMM", "p2p")
+        if comm == "ddp":            # round-1 path, kept for A/B: torch DDP buckets + NCCL all-reduce
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False,
+                                                            gradient_as_bucket_view=True, broadcast_buffers=False,
+                                                            bucket_cap_mb=int(os.environ.get("B200FM_DDP_BUCKET_MB", "25")))
+        else:                        # gradient arena + NVLink peer-memory all-reduce kernel (b200fm.parallel / csrc/comm.cu)
+            from b200fm.parallel import GradSync
+            net = sync = GradSync(model, transport=comm, wait_at_end=False)
+            groups = sync.split_param_groups(groups)
+    opt = FusedAdamW(groups, lr=lr, betas=(0.9, 0.95), eps=1e-8)
+    if sync is not None:
+        opt.pre_group_hook = sync.wait
     import random
     random.seed(rank)
     a, b, c, d = budgets_for(n_tok)
@@ -320,9 +329,16 @@ def run_b200_arm(args):
     def step(batch):
         loss, mod_loss = net(batch, num_encoder_tokens=n_tok, num_decoder_tokens=n_tok, loss_type="mod")
         loss.backward()
-        grads = [p.grad for p in model.parameters() if p.grad is not None]
-        gnorm = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(grads)))       # logged grad norm (native_scaler.py:56-65)
-        opt.step()
+        if sync is None:
+            grads = [p.grad for p in model.parameters() if p.grad is not None]
+            gnorm = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(grads)))   # logged grad norm (native_scaler.py:56-65)
+            opt.step()
+        else:
+            # AdamW of the early chunks runs while the last chunk is still being reduced; the logged norm (no clipping in the
+            # reference config: run_training_4m.py:102 clip_grad None) reads the averaged gradients afterwards
+            opt.step()
+            grads = [p.grad for p in model.parameters() if p.grad is not None]
+            gnorm = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(grads)))
         opt.zero_grad(set_to_none=True)
         return loss, mod_loss, gnorm
 
@@ -373,6 +389,18 @@ def run_b200_arm(args):
     cpu_issue_ms = timed.cpu_ms
     ms_e2e, _, loss_e2e = timed(args.steps, e2e=True)
     clocks = sampler.stop() if rank == 0 else None
+    ms_nocomm, params_equal = None, None
+    if world > 1:
+        # every rank must hold bit-identical parameters after the synchronised steps (checked BEFORE the unsynchronised timing below)
+        if sync is not None:
+            params_equal = sync.params_equal_across_ranks()
+        else:
+            acc = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum().reshape(1)
+            lo, hi = acc.clone(), acc.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            params_equal = bool(torch.equal(lo, hi))
+        with net.no_sync():          # the same steps with the gradient all-reduce switched off: what the communication costs
+            ms_nocomm, _, _ = timed(args.steps, e2e=False)
 
     # roofline of the dominant kernel family (tcgen05 GEMM): CUDA events around every launch during extra steps
     ops.PROFILE = []
@@ -424,8 +452,18 @@ def run_b200_arm(args):
                     clocks=clocks)
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world > 1:
+            line["comm"] = dict(kind=("nccl all-reduce of torch-DDP buckets" if comm == "ddp" else
+                                      f"gradient arena + {sync.transport.name} all-reduce ({sync.n_ctas} CTAs, {len(sync.chunks)} chunks)"),
+                                ms_per_step_without_comm=ms_nocomm / args.steps, exposed_ms_per_step=(ms - ms_nocomm) / args.steps,
+                                stats=None if sync is None else sync.stats)
+            line["ddp_params_equal"] = params_equal
         print(json.dumps(line))
     if world > 1:
+        if sync is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+            sync.close()
         dist.destroy_process_group()
 
 

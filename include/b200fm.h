@@ -39,7 +39,8 @@ int b200fm_abi_version(void);
 int b200fm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin);
 
 /* Runtime options (defaults from the environment variable B200FM_<NAME upper-case>): "pdl" (1: programmatic dependent launch),
- * "gemm_cta_pairs" (1: cta_group::2 GEMM tiles), "ln_bwd_v2" (0: experimental LayerNorm-backward variant).  Changing an
+ * "gemm_cta_pairs" (1: cta_group::2 GEMM tiles), "ln_bwd_v2" (0: experimental LayerNorm-backward variant), "sm_reserve" (0: number
+ * of SMs the persistent GEMM grids leave free, for a concurrent gradient all-reduce kernel).  Changing an
  * option affects launches issued afterwards; meant for A/B measurements inside one process.                          */
 int b200fm_set_option(const char* name, int value);
 int b200fm_get_option(const char* name, int* value);
@@ -220,6 +221,24 @@ int b200fm_vq_ema_stats(const float* z, const long long* idx, long long n, int K
  * embed[k] = embed[k]*decay + (bins[k] == 0 ? l2norm(embed[k]) : l2norm(embed_sum[k] / bins[k])) * (1-decay).             */
 int b200fm_vq_ema_update_cosine(float* embed, float* cluster_size, const float* bins, const float* embed_sum, int K, int d, float decay,
                                 void* stream);
+
+/* ---- data-parallel gradient all-reduce over NVLink peer memory ------------------------------------------------------------
+ * Replaces the NCCL all-reduce torch DDP issues for the reference's train step (run_training_4m.py:512; fp32 gradients, mean).
+ * Every rank allocates one arena with comm_alloc (cudaMalloc, so it can be exported), exports it with comm_ipc_export (64-byte
+ * cudaIpcMemHandle_t), opens the peers' handles with comm_ipc_open.  The first comm_flag_bytes() bytes of each arena are the
+ * flag block; gradients live behind it at IDENTICAL offsets on all ranks.
+ * allreduce_f32: two-shot all-reduce (P2P loads of the caller's 1/world shard from all ranks in rank order, sum, * scale, P2P
+ * stores into all ranks) of data[offset_elems .. offset_elems + n_elems) in ONE launch of n_ctas CTAs, bracketed by per-CTA
+ * cross-rank flag barriers.  peer_data / peer_flags: HOST arrays of `world` device pointers (index = rank; own entry = own
+ * arena).  seq: strictly increasing per call (same value on all ranks).  All ranks must issue the same calls in the same order. */
+int b200fm_comm_flag_bytes(void);
+int b200fm_comm_alloc(long long bytes, void** ptr);
+int b200fm_comm_free(void* ptr);
+int b200fm_comm_ipc_export(const void* ptr, void* handle64);
+int b200fm_comm_ipc_open(const void* handle64, void** ptr);
+int b200fm_comm_ipc_close(void* ptr);
+int b200fm_allreduce_f32(void* const* peer_data, void* const* peer_flags, int rank, int world, long long offset_elems,
+                         long long n_elems, float scale, unsigned int seq, int n_ctas, void* stream);
 
 #ifdef __cplusplus
 }

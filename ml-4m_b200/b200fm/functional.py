@@ -153,6 +153,35 @@ def zeros_f32(n, device):
     return _zero_arena.take(n, device)
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# gradient destinations: with data-parallel training (b200fm.parallel.GradSync) every parameter has a slot in the flat gradient
+# arena that is all-reduced over NVLink; the backward kernels write there directly instead of into a fresh tensor.
+# ----------------------------------------------------------------------------------------------------------------------
+def _claim(param, zeroed=False):
+    """Arena view to write `param`'s gradient into (first producer of the step only), or None."""
+    s = getattr(param, "_b200fm_slot", None)
+    return s.sync.claim(param, zeroed) if s is not None else None
+
+
+def _acc_f32(param, n, device):
+    """Zero-initialised fp32 [n] buffer a kernel ACCUMULATES a small parameter's gradient into (dgamma, dbeta, mod_emb, ...)."""
+    v = _claim(param, zeroed=True)
+    return v.view(-1) if v is not None else zeros_f32(n, device)
+
+
+def _wgrad(dy2, x2, weight, alpha_dev=None):
+    """dW (fp32) = dy^T x, written into the parameter's arena slot when there is one."""
+    return ops.gemm(dy2, x2, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32, out=_claim(weight), alpha_dev=alpha_dev)
+
+
+def _wgrad13(dab, h, w1, w3, H, Hp):
+    """[dW1; dW3] of a SwiGLU block: ONE [2Hp, D] GEMM output, placed over the adjacent fc1 / fc3 arena slots when possible."""
+    s = getattr(w1, "_b200fm_slot", None)
+    out = s.sync.claim_pair(w1, w3, Hp) if s is not None else None
+    dw13 = ops.gemm(dab, h, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32, out=out)
+    return dw13[:H], dw13[Hp:Hp + H]
+
+
 def _as2d(x):
     return x.reshape(-1, x.shape[-1])
 
@@ -171,6 +200,7 @@ class LayerNormFn(torch.autograd.Function):
         y, mean, rstd = ops.layernorm_fwd(x2, weight, bias, eps, out_bf16=out_bf16)
         ctx.save_for_backward(x2, weight, mean, rstd)
         ctx.has_bias = bias is not None and bias.requires_grad
+        ctx.bias_param = bias if ctx.has_bias else None
         ctx.shape = x.shape
         return y.view(x.shape)
 
@@ -179,8 +209,8 @@ class LayerNormFn(torch.autograd.Function):
         x2, weight, mean, rstd = ctx.saved_tensors
         dy2 = _as2d(dy).contiguous()
         D = x2.shape[1]
-        dgamma = zeros_f32(D, x2.device) if weight.requires_grad else None
-        dbeta = zeros_f32(D, x2.device) if ctx.has_bias else None
+        dgamma = _acc_f32(weight, D, x2.device) if weight.requires_grad else None
+        dbeta = _acc_f32(ctx.bias_param, D, x2.device) if ctx.has_bias else None
         dx, _ = ops.layernorm_bwd(dy2, x2, weight, mean, rstd, dgamma=dgamma, dbeta=dbeta)
         return dx.view(ctx.shape), dgamma, dbeta, None, None
 
@@ -205,7 +235,7 @@ def _linear_bwd(ctx, dy2, x2, weight, want_dx=True):
     """dx = dy W (NN), dW = dy^T x (TN, fp32), db = colsum(dy)."""
     wb = weight_bf16(weight)[:weight.shape[0]]
     dx = ops.gemm(dy2, wb, layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16) if want_dx else None
-    dw = ops.gemm(dy2, x2, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if weight.requires_grad else None
+    dw = _wgrad(dy2, x2, weight) if weight.requires_grad else None
     return dx, dw
 
 
@@ -337,8 +367,7 @@ class SwiGLUFn(torch.autograd.Function):
         dx = ops.gemm(dab, w13, layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16) if ctx.needs_input_grad[0] else None
         dw1 = dw3 = db1 = db3 = None
         if w1.requires_grad or w3.requires_grad:
-            dw13 = ops.gemm(dab, x2, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32)      # [2*Hp, D]
-            dw1, dw3 = dw13[:H], dw13[Hp:Hp + H]
+            dw1, dw3 = _wgrad13(dab, x2, w1, w3, H, Hp)
         if ctx.has_bias:
             dbias = ops.colsum_bf16(dab)
             db1, db3 = dbias[:H], dbias[Hp:Hp + H]
@@ -413,6 +442,7 @@ class HeadNormFn(torch.autograd.Function):
         ctx.save_for_backward(x, stats, weight)
         ctx.H = H
         ctx.bias_grad = bias is not None and bias.requires_grad
+        ctx.bias_param = bias if ctx.bias_grad else None
         return y
 
     @staticmethod
@@ -420,8 +450,8 @@ class HeadNormFn(torch.autograd.Function):
         x, stats, weight = ctx.saved_tensors
         if dy.dtype != torch.bfloat16 or dy.stride(1) != 1:
             dy = dy.to(torch.bfloat16).contiguous()
-        dgamma = zeros_f32(64, x.device) if weight.requires_grad else None
-        dbeta = zeros_f32(64, x.device) if ctx.bias_grad else None
+        dgamma = _acc_f32(weight, 64, x.device) if weight.requires_grad else None
+        dbeta = _acc_f32(ctx.bias_param, 64, x.device) if ctx.bias_grad else None
         dx = ops.headnorm_bwd(dy, x, weight, stats, ctx.H, dgamma, dbeta)
         return dx, None, dgamma, dbeta, None
 
@@ -459,7 +489,7 @@ class LinearCrossEntropyFn(torch.autograd.Function):
         coef = (dloss.float() / n).reshape(1).contiguous()             # stays on the device
         wb = weight_bf16(weight)[:weight.shape[0]]
         dh = ops.gemm(dlogits, wb, layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16, alpha_dev=coef) if ctx.needs_input_grad[0] else None
-        dw = ops.gemm(dlogits, h, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32, alpha_dev=coef) if weight.requires_grad else None
+        dw = _wgrad(dlogits, h, weight, alpha_dev=coef) if weight.requires_grad else None
         return dh, dw, None
 
 
@@ -508,6 +538,7 @@ class EmbedRowsFn(torch.autograd.Function):
         ctx.plan, ctx.seg_static, ctx.D = plan, seg_static, D
         ctx.shapes = [(t.shape, t.dtype) for t in tensors]
         ctx.mask_token_shape = None if mask_token is None else mask_token.shape
+        ctx.params, ctx.mask_token_param = tensors, mask_token       # leaf parameters / activations: destinations of their own gradients
         return (x0, emb) if want_emb else (x0, None)
 
     @staticmethod
@@ -520,20 +551,24 @@ class EmbedRowsFn(torch.autograd.Function):
             (mshape, _), (eshape, _), (pshape, _) = ctx.shapes[3 * i], ctx.shapes[3 * i + 1], ctx.shapes[3 * i + 2]
             need_main, need_mod, need_pos = ctx.needs_input_grad[5 + 3 * i: 8 + 3 * i]
             gm = None
+            decoder_side = bool(plan.decoder & ops.MODE_DECODER)
+            if need_main and decoder_side and st["kind"] == lib.KIND_TOK_IMG:
+                need_main = False          # decoder image tokens enter as the mask token (fm.py:322): their table gets no gradient here
             if need_main:
                 if st["kind"] in (lib.KIND_IMG, lib.KIND_SEQ_EMB):
                     gm = torch.zeros(mshape, device=dev, dtype=torch.bfloat16)
                     d["dx_rows"] = gm
                 else:
-                    gm = torch.zeros(mshape, device=dev, dtype=torch.float32)
+                    gm = _claim(ctx.params[3 * i])
+                    gm = gm.zero_() if gm is not None else torch.zeros(mshape, device=dev, dtype=torch.float32)
                     d["d_token_emb"] = gm
-            ge = zeros_f32(D, dev) if need_mod else None
+            ge = _acc_f32(ctx.params[3 * i + 1], D, dev) if need_mod else None
             d["d_mod_emb"] = ge
             gp = torch.zeros(pshape, device=dev, dtype=torch.float32) if need_pos else None
             d["d_pos_emb"] = gp
             grads += [gm, None if ge is None else ge.view(eshape), gp]
             segs.append(d)
-        dmt = zeros_f32(D, dev) if (ctx.mask_token_shape is not None and ctx.needs_input_grad[4]) else None
+        dmt = _acc_f32(ctx.mask_token_param, D, dev) if (ctx.mask_token_shape is not None and ctx.needs_input_grad[4]) else None
         ops.embed_rows_bwd(plan, segs, dx0.contiguous(), None if demb is None else demb.contiguous(), dmt, D)
         return (None, None, None, None, None if dmt is None else dmt.view(ctx.mask_token_shape), *grads)
 
@@ -602,6 +637,7 @@ class SelfAttnSubLayerFn(torch.autograd.Function):
         y = ops.gemm(o, weight_bf16(proj_w), epilogue=ops.EPI_BF16, bias=proj_b, n_out=D)
         ctx.save_for_backward(s2, mean, rstd, h, qkv, o, stats, mask, nw, qkv_w, proj_w)
         ctx.cfg = (B, N, D, heads, scale, qkv_b is not None, proj_b is not None, nb is not None and nb.requires_grad, ypend is not None)
+        ctx.nb = nb
         return s2.view(B, N, D), y.view(B, N, D)
 
     @staticmethod
@@ -610,16 +646,16 @@ class SelfAttnSubLayerFn(torch.autograd.Function):
         B, N, D, heads, scale, has_qb, has_pb, nb_grad, has_pend = ctx.cfg
         d2, db = _stream_grads(g_s, g_y, B * N, D)
         do = ops.gemm(db, weight_bf16(proj_w)[:D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
-        dproj_w = ops.gemm(db, o, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if proj_w.requires_grad else None
+        dproj_w = _wgrad(db, o, proj_w) if proj_w.requires_grad else None
         dproj_b = ops.colsum_bf16(db) if has_pb else None
         dqkv = torch.empty_like(qkv)
         ops.attention_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o, do, stats, B, heads, N, N, mask, scale,
                           dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:])
         dh = ops.gemm(dqkv, weight_bf16(qkv_w)[:3 * D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
-        dqkv_w = ops.gemm(dqkv, h, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if qkv_w.requires_grad else None
+        dqkv_w = _wgrad(dqkv, h, qkv_w) if qkv_w.requires_grad else None
         dqkv_b = ops.colsum_bf16(dqkv) if has_qb else None
-        dgamma = zeros_f32(D, s2.device) if nw.requires_grad else None
-        dbeta = zeros_f32(D, s2.device) if nb_grad else None
+        dgamma = _acc_f32(nw, D, s2.device) if nw.requires_grad else None
+        dbeta = _acc_f32(ctx.nb, D, s2.device) if nb_grad else None
         dx, dxb = ops.layernorm_bwd(dh, s2, nw, mean, rstd, dres=d2, want_bf16=has_pend, dgamma=dgamma, dbeta=dbeta)
         return (dx.view(B, N, D), dxb.view(B, N, D) if has_pend else None, None, dgamma, dbeta, dqkv_w, dqkv_b, dproj_w, dproj_b,
                 None, None, None)
@@ -645,6 +681,7 @@ class CrossAttnSubLayerFn(torch.autograd.Function):
         ctx.save_for_backward(s2, c2, qmean, qrstd, cmean, crstd, hq, hc, q, kv, o, stats, mask, qnw, cnw, q_w, kv_w, proj_w)
         ctx.cfg = (B, N, M, D, heads, scale, q_b is not None, kv_b is not None, proj_b is not None,
                    qnb is not None and qnb.requires_grad, cnb is not None and cnb.requires_grad, ypend is not None)
+        ctx.qnb, ctx.cnb = qnb, cnb
         return s2.view(B, N, D), y.view(B, N, D)
 
     @staticmethod
@@ -654,26 +691,26 @@ class CrossAttnSubLayerFn(torch.autograd.Function):
         dev = s2.device
         d2, db = _stream_grads(g_s, g_y, B * N, D)
         do = ops.gemm(db, weight_bf16(proj_w)[:D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
-        dproj_w = ops.gemm(db, o, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if proj_w.requires_grad else None
+        dproj_w = _wgrad(db, o, proj_w) if proj_w.requires_grad else None
         dproj_b = ops.colsum_bf16(db) if has_pb else None
         dq = torch.empty_like(q)
         dkv = torch.empty_like(kv)
         ops.attention_bwd(q, kv[:, :D], kv[:, D:], o, do, stats, B, heads, N, M, mask, scale, dq, dkv[:, :D], dkv[:, D:])
         dhq = ops.gemm(dq, weight_bf16(q_w)[:D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
-        dq_w = ops.gemm(dq, hq, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if q_w.requires_grad else None
+        dq_w = _wgrad(dq, hq, q_w) if q_w.requires_grad else None
         dq_b = ops.colsum_bf16(dq) if has_qb else None
-        dkv_w = ops.gemm(dkv, hc, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if kv_w.requires_grad else None
+        dkv_w = _wgrad(dkv, hc, kv_w) if kv_w.requires_grad else None
         dkv_b = ops.colsum_bf16(dkv) if has_kvb else None
-        dqg = zeros_f32(D, dev) if qnw.requires_grad else None
-        dqb = zeros_f32(D, dev) if qnb_grad else None
+        dqg = _acc_f32(qnw, D, dev) if qnw.requires_grad else None
+        dqb = _acc_f32(ctx.qnb, D, dev) if qnb_grad else None
         dx, dxb = ops.layernorm_bwd(dhq, s2, qnw, qmean, qrstd, dres=d2, want_bf16=has_pend, dgamma=dqg, dbeta=dqb)
         dctx = dcg = dcb = None
         # context_norm's own weight / bias train even when the context itself is detached (frozen-encoder fine-tuning,
         # forward_decoder on a no_grad encoder output): run the dgrad + LayerNorm backward whenever any of the three is wanted
         if ctx.needs_input_grad[2] or cnw.requires_grad or cnb_grad:
             dhc = ops.gemm(dkv, weight_bf16(kv_w)[:2 * D], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
-            dcg = zeros_f32(D, dev) if cnw.requires_grad else None
-            dcb = zeros_f32(D, dev) if cnb_grad else None
+            dcg = _acc_f32(cnw, D, dev) if cnw.requires_grad else None
+            dcb = _acc_f32(ctx.cnb, D, dev) if cnb_grad else None
             dctx, _ = ops.layernorm_bwd(dhc, c2, cnw, cmean, crstd, dgamma=dcg, dbeta=dcb)
             dctx = dctx.view(B, M, D) if ctx.needs_input_grad[2] else None
         return (dx.view(B, N, D), dxb.view(B, N, D) if has_pend else None, dctx, None, dqg, dqb, dcg, dcb, dq_w, dq_b, dkv_w, dkv_b,
@@ -700,6 +737,7 @@ class GatedMlpSubLayerFn(torch.autograd.Function):
         y = ops.gemm(g, w2b, epilogue=ops.EPI_BF16, bias=b2, n_out=D)
         ctx.save_for_backward(s2, mean, rstd, h, ab, g, nw, w1, w3, w2)
         ctx.cfg = (shape, D, H, Hp, b1 is not None, b2 is not None, nb is not None and nb.requires_grad, ypend is not None)
+        ctx.nb = nb
         return s2.view(shape), y.view(shape)
 
     @staticmethod
@@ -711,21 +749,21 @@ class GatedMlpSubLayerFn(torch.autograd.Function):
         dg = ops.gemm(db, w2b, layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)              # [R, Hp]; padded columns are zero
         dw2 = None
         if w2.requires_grad:
-            dw2 = ops.gemm(db, g, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32)            # [D, Hp]
-            if Hp != H:
-                dw2 = dw2[:, :H]
+            if Hp == H:
+                dw2 = _wgrad(db, g, w2)                                                     # [D, H], into the gradient arena when there is one
+            else:
+                dw2 = ops.gemm(db, g, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32)[:, :H]  # [D, Hp] -> strided view (copied by autograd)
         db2 = ops.colsum_bf16(db) if has_b2 else None
         dab = ops.swiglu_bwd(ab, dg)
         dh = ops.gemm(dab, weight_bf16(w1, w3), layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
         dw1 = dw3 = db1 = db3 = None
         if w1.requires_grad or w3.requires_grad:
-            dw13 = ops.gemm(dab, h, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32)
-            dw1, dw3 = dw13[:H], dw13[Hp:Hp + H]
+            dw1, dw3 = _wgrad13(dab, h, w1, w3, H, Hp)
         if has_b13:
             dbias = ops.colsum_bf16(dab)
             db1, db3 = dbias[:H], dbias[Hp:Hp + H]
-        dgamma = zeros_f32(D, s2.device) if nw.requires_grad else None
-        dbeta = zeros_f32(D, s2.device) if nb_grad else None
+        dgamma = _acc_f32(nw, D, s2.device) if nw.requires_grad else None
+        dbeta = _acc_f32(ctx.nb, D, s2.device) if nb_grad else None
         dx, dxb = ops.layernorm_bwd(dh, s2, nw, mean, rstd, dres=d2, want_bf16=has_pend, dgamma=dgamma, dbeta=dbeta)
         return dx.view(shape), dxb.view(shape) if has_pend else None, dgamma, dbeta, dw1, dw3, dw2, db1, db3, db2, None
 
@@ -744,6 +782,7 @@ class NormLinearResidualFn(torch.autograd.Function):
         out = ops.gemm(h, weight_bf16(w), epilogue=ops.EPI_RESID, bias=b, resid=r2, n_out=w.shape[0])
         ctx.save_for_backward(s2, mean, rstd, h, nw, w)
         ctx.cfg = (x.shape, resid.shape, b is not None, nb is not None and nb.requires_grad, ypend is not None)
+        ctx.nb = nb
         return out.view(resid.shape)
 
     @staticmethod
@@ -756,10 +795,10 @@ class NormLinearResidualFn(torch.autograd.Function):
             d2 = d2.contiguous()
         db = ops.cast_bf16(d2) if d2.dtype == torch.float32 else d2
         dh = ops.gemm(db, weight_bf16(w)[:w.shape[0]], layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)
-        dw = ops.gemm(db, h, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32) if w.requires_grad else None
+        dw = _wgrad(db, h, w) if w.requires_grad else None
         dbias = ops.colsum_bf16(db) if has_b else None
-        dgamma = zeros_f32(D, s2.device) if nw.requires_grad else None
-        dbeta = zeros_f32(D, s2.device) if nb_grad else None
+        dgamma = _acc_f32(nw, D, s2.device) if nw.requires_grad else None
+        dbeta = _acc_f32(ctx.nb, D, s2.device) if nb_grad else None
         dx, dxb = ops.layernorm_bwd(dh, s2, nw, mean, rstd, want_bf16=has_pend, dgamma=dgamma, dbeta=dbeta)
         return dx.view(xshape), dxb.view(xshape) if has_pend else None, dgamma, dbeta, dw, dbias, dout.view(rshape), None
 
@@ -774,6 +813,7 @@ class AddLayerNormFn(torch.autograd.Function):
         s2, h, mean, rstd = ops.add_layernorm_fwd(x2, y2, nw, nb, eps)
         ctx.save_for_backward(s2, mean, rstd, nw)
         ctx.cfg = (x.shape, nb is not None and nb.requires_grad, ypend is not None)
+        ctx.nb = nb
         return h.view(x.shape)
 
     @staticmethod
@@ -784,7 +824,7 @@ class AddLayerNormFn(torch.autograd.Function):
         dh2 = dh.reshape(-1, D)
         if not dh2.is_contiguous():
             dh2 = dh2.contiguous()
-        dgamma = zeros_f32(D, s2.device) if nw.requires_grad else None
-        dbeta = zeros_f32(D, s2.device) if nb_grad else None
+        dgamma = _acc_f32(nw, D, s2.device) if nw.requires_grad else None
+        dbeta = _acc_f32(ctx.nb, D, s2.device) if nb_grad else None
         dx, dxb = ops.layernorm_bwd(dh2, s2, nw, mean, rstd, want_bf16=has_pend, dgamma=dgamma, dbeta=dbeta)
         return dx.view(shape), dxb.view(shape) if has_pend else None, dgamma, dbeta, None

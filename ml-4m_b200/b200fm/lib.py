@@ -67,6 +67,13 @@ SIGNATURES = {
     "b200fm_adamw_chunk_elems": [],
     "b200fm_vq_argmax": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p],
     "b200fm_vq_argmax_host": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p],
+    "b200fm_comm_flag_bytes": [],
+    "b200fm_comm_alloc": [c_ll, c_void_p],
+    "b200fm_comm_free": [c_void_p],
+    "b200fm_comm_ipc_export": [c_void_p, c_void_p],
+    "b200fm_comm_ipc_open": [c_void_p, c_void_p],
+    "b200fm_comm_ipc_close": [c_void_p],
+    "b200fm_allreduce_f32": [c_void_p, c_void_p, c_int, c_int, c_ll, c_ll, c_float, ctypes.c_uint, c_int, c_void_p],
 }
 
 _lib = None

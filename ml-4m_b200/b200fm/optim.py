@@ -15,6 +15,7 @@ class FusedAdamW(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._chunk = None
         self._tables = {}       # group index -> dict(device table, chunk maps, pinned staging ring)
+        self.pre_group_hook = None   # callable(params): e.g. GradSync.wait -- make the stream wait for this group's reduced gradients
 
     def _group_tables(self, gi, tensors):
         """Device-side pointer table + CTA->chunk maps for one param group.  The chunk maps depend on the tensor sizes only
@@ -56,6 +57,8 @@ class FusedAdamW(torch.optim.Optimizer):
                 loss = closure()
         for gi, group in enumerate(self.param_groups):
             b1, b2 = group["betas"]
+            if self.pre_group_hook is not None:
+                self.pre_group_hook(group["params"])
             tensors, extra_casts, step_no, updated, keepalive = [], [], None, [], []
             for p in group["params"]:
                 if p.grad is None:

@@ -357,9 +357,7 @@ static int launch_attn_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const 
         B200FM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = usable_sm_count();
     const int grid = a.num_items < sms ? a.num_items : sms;
     B200FM_LAUNCH(kern, dim3(grid), dim3(kBwdThreads), smem, stream, 1, tq, tdo, tk, tv, a);
     B200FM_CUDA(cudaGetLastError());

@@ -268,9 +268,7 @@ static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const C
         B200FM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = usable_sm_count();
     const int cap = sms * (NKT == 1 ? 2 : 1);
     const int grid = a.num_items < cap ? a.num_items : cap;
     B200FM_LAUNCH(kern, dim3(grid), dim3(192), smem, stream, 1, tq, tk, tv, a);

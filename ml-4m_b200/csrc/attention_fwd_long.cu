@@ -284,9 +284,7 @@ int launch_attention_fwd_long(const CUtensorMap& tq, const CUtensorMap& tk, cons
         B200FM_CUDA(cudaFuncSetAttribute(attention_fwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = usable_sm_count();
     const int grid = a.num_items < sms ? a.num_items : sms;
     B200FM_LAUNCH(attention_fwd_long_kernel, dim3(grid), dim3(192), smem, stream, 1, tq, tk, tv, a);
     B200FM_CUDA(cudaGetLastError());

@@ -403,16 +403,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------------------
 // host launcher
 // ------------------------------------------------------------------------------------------------------------
-static int g_sm_count = 0;
-static int sm_count() {
-    if (g_sm_count == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sm_count <= 0) g_sm_count = 148;
-    }
-    return g_sm_count;
-}
+static int sm_count() { return usable_sm_count(); }
 
 template <int BN, int LAYOUT, int EPI, bool CTA2>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t stream) {

@@ -18,6 +18,7 @@ static OptionSlot g_options[kOptCount] = {
     {"pdl", "B200FM_PDL", 1, 1, false},                        // programmatic dependent launch on every kernel
     {"gemm_cta_pairs", "B200FM_GEMM_CTA_PAIRS", 1, 1, false},  // tcgen05 cta_group::2 GEMM tiles
     {"ln_bwd_v2", "B200FM_LN_BWD_V2", 0, 0, false},            // EXPERIMENTAL (not yet measured): LayerNorm backward with the dres loads hoisted
+    {"sm_reserve", "B200FM_SM_RESERVE", 0, 0, false},          // SMs the persistent GEMM grids leave free (concurrent all-reduce kernel)
 };
 
 int option(int id) {
@@ -31,6 +32,20 @@ int option(int id) {
 }
 
 bool pdl_enabled() { return option(kOptPdl) != 0; }
+
+int usable_sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    // "sm_reserve": SMs left to a concurrently running gradient all-reduce kernel (comm.cu); even, so CTA-pair grids stay whole
+    const int reserve = option(kOptSmReserve);
+    const int n = sms - (reserve > 0 ? ((reserve + 1) & ~1) : 0);
+    return n >= 16 ? n : 16;
+}
 
 static thread_local char g_err[1024] = "";
 

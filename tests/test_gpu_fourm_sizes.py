@@ -6,9 +6,10 @@ Tolerance rule: the yardstick is the fp64 run; the allowed error
 when it runs under bf16 autocast (what `run_training_4m.py --dtype bfloat16` does), measured per quantity in the golden file:
    loss:        3 x |ref_bf16 - ref_fp64|           (4M-B: 3 x 8.0e-5, 4M-L: 3 x 7.0e-5)
    mod losses:  3 x max_m |ref_bf16[m] - ref_fp64[m]|
-   grad norms:  per tensor 3 x max(own reference error, the p90 reference error over all tensors)
-   grad slices: 3 x the reference's worst relative slice error is not stored, so slices use 3 x the p90 norm error, relative
-                to the slice's max magnitude, plus the bf16 unit round-off (2^-8) of one product.
+   grad norms:  every tensor within 3 x the reference's WORST per-tensor relative error (4M-B: 3 x 1.6e-3, 4M-L: 3 x 3.8e-3), and the
+                median / p90 of our per-tensor errors within 3 x the reference's median / p90 (the distribution, not only its tail)
+   grad slices: the reference's slice errors are not stored, so slices use 3 x the worst norm error, relative to the slice's max
+                magnitude, plus the bf16 unit round-off (2^-8) of one product.
 """
 import random
 
@@ -57,27 +58,29 @@ def test_loss_logits_and_gradients_at_benchmarked_size(tag):
     err_mod = max(abs(float(mod_loss[m]) - v) for m, v in r64["mod_loss"].items())
 
     ref_rel = {k: abs(r16["grad_norm"][k] - v) / max(v, 1e-30) for k, v in r64["grad_norm"].items()}
-    srt = sorted(ref_rel.values())
-    p90 = srt[int(len(srt) * 0.9)]
     grads = {k: p.grad for k, p in model.named_parameters()}
-    worst, worst_k, n_bad = 0.0, None, []
+    our_rel = {}
     for k, v in r64["grad_norm"].items():
-        g = grads[k]
-        assert g is not None, k
-        rel = abs(float(g.double().norm()) - v) / max(v, 1e-30)
-        if rel / max(ref_rel[k], p90) > worst:
-            worst, worst_k = rel / max(ref_rel[k], p90), k
-        if rel > 3 * max(ref_rel[k], p90):
-            n_bad.append((k, rel, ref_rel[k]))
-    print(f"[{tag}] loss err {err_loss:.2e} (tol {tol_loss:.2e}; reference bf16 {tol_loss / 3:.2e}); mod-loss err {err_mod:.2e} "
-          f"(tol {tol_mod:.2e}); grad-norm worst = {worst:.2f} x reference bf16 error at {worst_k} (p90 ref {p90:.2e})")
+        assert grads[k] is not None, k
+        our_rel[k] = abs(float(grads[k].double().norm()) - v) / max(v, 1e-30)
+
+    def q(d, f):
+        srt = sorted(d.values())
+        return srt[min(len(srt) - 1, int(len(srt) * f))]
+    ref_med, ref_p90, ref_max = q(ref_rel, 0.5), q(ref_rel, 0.9), max(ref_rel.values())
+    our_med, our_p90, our_max = q(our_rel, 0.5), q(our_rel, 0.9), max(our_rel.values())
+    worst_k = max(our_rel, key=our_rel.get)
+    print(f"[{tag}] loss err {err_loss:.2e} (tol {tol_loss:.2e} = 3 x reference bf16); mod-loss err {err_mod:.2e} (tol {tol_mod:.2e}); "
+          f"grad-norm rel err median/p90/max: ours {our_med:.2e}/{our_p90:.2e}/{our_max:.2e} ({worst_k}) vs reference bf16 "
+          f"{ref_med:.2e}/{ref_p90:.2e}/{ref_max:.2e}")
     assert err_loss <= tol_loss
     assert err_mod <= tol_mod
-    assert not n_bad, n_bad[:5]
+    assert our_max <= 3 * ref_max, (worst_k, our_max, ref_max)
+    assert our_med <= 3 * ref_med and our_p90 <= 3 * ref_p90
     for k, sl in r64["grad_slices"].items():
         got = grads[k].flatten()[:256].double().cpu()
         scale = float(sl.abs().max()) + 1e-300
-        assert float((got - sl).abs().max()) <= (3 * p90 + 2 ** -8) * scale, k
+        assert float((got - sl).abs().max()) <= (3 * ref_max + 2 ** -8) * scale, k
 
     random.seed(gold["py_seed"])
     with torch.no_grad():
