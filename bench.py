@@ -305,7 +305,7 @@ def run_b200_arm(args):
     n_params = sum(p.numel() for p in model.parameters())
     lr = 1e-4 * B * world / 256                                 # run_training_4m.py:496-503 scaling rule
     groups = param_groups_like_reference(model, 0.05)
-    net, sync, comm = model, None, "none"
+    net, gsync, comm = model, None, "none"
     if world > 1:
         comm = os.environ.get("B200FM_COMM", "p2p")
         if comm == "ddp":            # round-1 path, kept for A/B: torch DDP buckets + NCCL all-reduce
@@ -314,11 +314,11 @@ def run_b200_arm(args):
                                                             bucket_cap_mb=int(os.environ.get("B200FM_DDP_BUCKET_MB", "25")))
         else:                        # gradient arena + NVLink peer-memory all-reduce kernel (b200fm.parallel / csrc/comm.cu)
             from b200fm.parallel import GradSync
-            net = sync = GradSync(model, transport=comm, wait_at_end=False)
-            groups = sync.split_param_groups(groups)
+            net = gsync = GradSync(model, transport=comm, wait_at_end=False)
+            groups = gsync.split_param_groups(groups)
     opt = FusedAdamW(groups, lr=lr, betas=(0.9, 0.95), eps=1e-8)
-    if sync is not None:
-        opt.pre_group_hook = sync.wait
+    if gsync is not None:
+        opt.pre_group_hook = gsync.wait
     import random
     random.seed(rank)
     a, b, c, d = budgets_for(n_tok)
@@ -329,7 +329,7 @@ def run_b200_arm(args):
     def step(batch):
         loss, mod_loss = net(batch, num_encoder_tokens=n_tok, num_decoder_tokens=n_tok, loss_type="mod")
         loss.backward()
-        if sync is None:
+        if gsync is None:
             grads = [p.grad for p in model.parameters() if p.grad is not None]
             gnorm = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(grads)))   # logged grad norm (native_scaler.py:56-65)
             opt.step()
@@ -392,8 +392,8 @@ def run_b200_arm(args):
     ms_nocomm, params_equal = None, None
     if world > 1:
         # every rank must hold bit-identical parameters after the synchronised steps (checked BEFORE the unsynchronised timing below)
-        if sync is not None:
-            params_equal = sync.params_equal_across_ranks()
+        if gsync is not None:
+            params_equal = gsync.params_equal_across_ranks()
         else:
             acc = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum().reshape(1)
             lo, hi = acc.clone(), acc.clone()
@@ -454,16 +454,16 @@ def run_b200_arm(args):
             line["cpu_baseline"] = cpu
         if world > 1:
             line["comm"] = dict(kind=("nccl all-reduce of torch-DDP buckets" if comm == "ddp" else
-                                      f"gradient arena + {sync.transport.name} all-reduce ({sync.n_ctas} CTAs, {len(sync.chunks)} chunks)"),
+                                      f"gradient arena + {gsync.transport.name} all-reduce ({gsync.n_ctas} CTAs, {len(gsync.chunks)} chunks)"),
                                 ms_per_step_without_comm=ms_nocomm / args.steps, exposed_ms_per_step=(ms - ms_nocomm) / args.steps,
-                                stats=None if sync is None else sync.stats)
+                                stats=None if gsync is None else gsync.stats)
             line["ddp_params_equal"] = params_equal
         print(json.dumps(line))
     if world > 1:
-        if sync is not None:
+        if gsync is not None:
             torch.cuda.synchronize()
             dist.barrier()
-            sync.close()
+            gsync.close()
         dist.destroy_process_group()
 
 

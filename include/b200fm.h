@@ -57,6 +57,14 @@ int b200fm_gemm_bf16(int layout, int epilogue, int M, int N, int K, const void* 
                      long long ldb, void* out0, long long ld0, void* out1, long long ld1, const float* bias,
                      const float* resid, long long ldr, float alpha, const float* alpha_dev, void* stream);
 
+/* Same with a DEVICE-side problem size (the masked-token head under a captured CUDA graph: per-modality row counts never visit the
+ * host).  dyn_mode 1 (NT / NN): the number of output rows is min(*dyn_dev, M); dyn_mode 2 (TN, EPI_F32): the contraction length is
+ * min(*dyn_dev, K) -- operand rows in [*dyn_dev, roundup(*dyn_dev, 64)) must be zero in one operand and finite in the other.
+ * Grid, tensor maps and the split-K plan are sized for the bounds M / K; dyn_dev == NULL behaves like b200fm_gemm_bf16.        */
+int b200fm_gemm_bf16_dyn(int layout, int epilogue, int M, int N, int K, const void* A, long long lda, const void* B, long long ldb,
+                         void* out0, long long ld0, void* out1, long long ld1, const float* bias, const float* resid, long long ldr,
+                         float alpha, const float* alpha_dev, const int* dyn_dev, int dyn_mode, void* stream);
+
 /* ---- LayerNorm (fourm/models/fm_utils.py:93-108; F.layer_norm, fp32 statistics) -----------------------------
  * x fp32 [rows, D] -> y (bf16 if y_is_bf16 else fp32) [rows, D]; mean/rstd fp32 [rows] saved for backward (may be NULL). */
 int b200fm_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_is_bf16, float* mean,
@@ -108,6 +116,11 @@ int b200fm_act_bwd(int act, const void* pre, const void* dact, void* dpre, long 
  * dlogits (optional) bf16 [n,V] = softmax - onehot, UNSCALED (fold 1/n and the upstream grad in via gemm alpha_dev).    */
 int b200fm_cross_entropy(const float* logits, long long ld, const int64_t* targets, float* loss_rows, void* dlogits,
                          long long ldd, long long n, int V, void* stream);
+/* cross_entropy with a device-side row count: rows >= *n_dev (< n_max) get loss 0; their dlogits rows are zeroed up to the next
+ * multiple of 64.  masked_mean: mean_out = sum(x[:n]) / max(n, 1) (0 for n == 0: fm.py:593-595), inv_n_out = 1 / max(n, 1).  */
+int b200fm_cross_entropy_dyn(const float* logits, long long ld, const int64_t* targets, float* loss_rows, void* dlogits,
+                             long long ldd, long long n_max, int V, const int* n_dev, void* stream);
+int b200fm_masked_mean(const float* x, const int* n_dev, long long n_max, float* mean_out, float* inv_n_out, void* stream);
 /* colsum_bf16: out[c] += sum_r x[r,c] (bias gradients of nn.Linear layers with bias).                                   */
 int b200fm_colsum_bf16(const void* x, long long ld, float* out, long long R, int N, void* stream);
 /* cast_f32_bf16: bf16 shadow of fp32 master weights / activations (what autocast does per call in the reference).       */
@@ -134,6 +147,11 @@ int b200fm_adamw_multi(const b200fm_adamw_tensor* table_dev, const int* chunk_te
                        int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                        void* stream);
 int b200fm_adamw_chunk_elems(void);
+/* As adamw_multi with the per-step scalars in DEVICE memory, hyper_dev = {lr, 1 - beta1^t, sqrt(1 - beta2^t)}: a captured CUDA graph
+ * replays the same launch while the host refreshes the three floats (learning-rate schedule, bias correction) before each replay. */
+int b200fm_adamw_multi_dev(const b200fm_adamw_tensor* table_dev, const int* chunk_tensor_dev, const long long* chunk_offset_dev,
+                           int n_chunks, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                           const float* hyper_dev, void* stream);
 
 /* ---- modality-masked token selection + embedding gather / scatter ------------------------------------------------
  * Replaces cat_{encoder,decoder}_tensors + forward_mask_{encoder,decoder} + adapt_decoder_attention_mask
@@ -179,6 +197,12 @@ typedef struct b200fm_segment {
 int b200fm_select_plan(const b200fm_segment* segs, int n_seg, int mode, int B, int n_keep, int32_t* src_seg, int32_t* src_pos,
                        int32_t* pos_id, uint8_t* pad_mask, int16_t* mod_mask, int16_t* mod_raw, int64_t* target_ids,
                        int32_t* dam_out, void* stream);
+/* As select_plan with the concatenation order as DEVICE data: segs[] is given in a fixed (canonical) order and order_dev[i] names the
+ * segment that comes i-th (the Python-random decoder shuffle of fm.py:306); src_seg stores indices into segs[].  order_dev NULL ==
+ * select_plan.  Lets a captured CUDA graph replay the step with a fresh shuffle.                                                   */
+int b200fm_select_plan_ordered(const b200fm_segment* segs, int n_seg, int mode, int B, int n_keep, int32_t* src_seg, int32_t* src_pos,
+                               int32_t* pos_id, uint8_t* pad_mask, int16_t* mod_mask, int16_t* mod_raw, int64_t* target_ids,
+                               int32_t* dam_out, const int32_t* order_dev, void* stream);
 /* mask_out uint8 [B, M, M], 1 = masked: (j >= cumsum(dam)[i]) | (mod_raw[i] != mod_raw[j])  (or triu(1) if causal).          */
 int b200fm_decoder_attention_mask(const int32_t* dam, const int16_t* mod_raw, uint8_t* mask_out, int B, int M, int causal, int sep,
                                   void* stream);
@@ -197,6 +221,10 @@ int b200fm_head_rows(const int16_t* mod_mask, long long n_rows, const int* mod_i
                      int32_t* counts, void* stream);
 int b200fm_gather_rows_bf16(const void* src, const int32_t* rows, void* out, long long n, int D, void* stream);
 int b200fm_gather_i64(const int64_t* src, const int32_t* rows, int64_t* out, long long n, void* stream);
+/* Device-side counts (n = min(*n_dev, n)): gather_rows zero-fills output rows [n, roundup(n, 128)).                          */
+int b200fm_gather_rows_bf16_dyn(const void* src, const int32_t* rows, void* out, long long n, int D, const int* n_dev, void* stream);
+int b200fm_gather_i64_dyn(const int64_t* src, const int32_t* rows, int64_t* out, long long n, const int* n_dev, void* stream);
+int b200fm_scatter_rows_bf16_dyn(const void* src, const int32_t* rows, void* dst, long long n, int D, const int* n_dev, void* stream);
 /* dst bf16 [*, D] row rows[i] = src bf16 [n, D] row i (backward of gather_rows_bf16; distinct destination rows).           */
 int b200fm_scatter_rows_bf16(const void* src, const int32_t* rows, void* dst, long long n, int D, void* stream);
 /* dst fp32 [*, D] rows[i] += src bf16 [n, D] row i (distinct destination rows).                                             */
@@ -239,6 +267,10 @@ int b200fm_comm_ipc_open(const void* handle64, void** ptr);
 int b200fm_comm_ipc_close(void* ptr);
 int b200fm_allreduce_f32(void* const* peer_data, void* const* peer_flags, int rank, int world, long long offset_elems,
                          long long n_elems, float scale, unsigned int seq, int n_ctas, void* stream);
+/* As above with seq + *seq_base_dev as the sequence number (seq_base_dev: device uint32 the caller advances once per step), so the
+ * launch can be captured in a CUDA graph and replayed.                                                                         */
+int b200fm_allreduce_f32_seq(void* const* peer_data, void* const* peer_flags, int rank, int world, long long offset_elems,
+                             long long n_elems, float scale, unsigned int seq, const unsigned int* seq_base_dev, int n_ctas, void* stream);
 
 #ifdef __cplusplus
 }

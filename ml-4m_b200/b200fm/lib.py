@@ -67,6 +67,17 @@ SIGNATURES = {
     "b200fm_adamw_chunk_elems": [],
     "b200fm_vq_argmax": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p],
     "b200fm_vq_argmax_host": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p],
+    "b200fm_gemm_bf16_dyn": [c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll,
+                             c_void_p, c_void_p, c_ll, c_float, c_void_p, c_void_p, c_int, c_void_p],
+    "b200fm_cross_entropy_dyn": [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p],
+    "b200fm_masked_mean": [c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p],
+    "b200fm_adamw_multi_dev": [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p],
+    "b200fm_select_plan_ordered": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p],
+    "b200fm_gather_rows_bf16_dyn": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p],
+    "b200fm_gather_i64_dyn": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p],
+    "b200fm_scatter_rows_bf16_dyn": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p],
+    "b200fm_allreduce_f32_seq": [c_void_p, c_void_p, c_int, c_int, c_ll, c_ll, c_float, ctypes.c_uint, c_void_p, c_int, c_void_p],
     "b200fm_comm_flag_bytes": [],
     "b200fm_comm_alloc": [c_ll, c_void_p],
     "b200fm_comm_free": [c_void_p],

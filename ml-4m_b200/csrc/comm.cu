@@ -64,7 +64,9 @@ B200FM_DEVINL void cta_barrier_all_ranks(const CommPeers& pr, int rank, int worl
 
 template <int W>
 __global__ void __launch_bounds__(kCommThreads, 1)
-allreduce_f32_kernel(const CommPeers pr, int rank, long long off, long long n4, float scale, uint32_t seq) {
+allreduce_f32_kernel(const CommPeers pr, int rank, long long off, long long n4, float scale, uint32_t seq, const uint32_t* seq_base_dev) {
+    // CUDA-graph replays: the sequence number must differ per replay, so its step-dependent part is read from device memory
+    if (seq_base_dev != nullptr) seq += *reinterpret_cast<const volatile uint32_t*>(seq_base_dev);
     cta_barrier_all_ranks(pr, rank, W, 0, seq);
     // my shard of the chunk, in float4 units
     const long long per = (n4 + W - 1) / W;
@@ -145,6 +147,12 @@ extern "C" int b200fm_comm_ipc_close(void* ptr) {
 
 extern "C" int b200fm_allreduce_f32(void* const* peer_data, void* const* peer_flags, int rank, int world, long long offset_elems,
                                     long long n_elems, float scale, unsigned int seq, int n_ctas, void* stream_) {
+    return b200fm_allreduce_f32_seq(peer_data, peer_flags, rank, world, offset_elems, n_elems, scale, seq, nullptr, n_ctas, stream_);
+}
+
+extern "C" int b200fm_allreduce_f32_seq(void* const* peer_data, void* const* peer_flags, int rank, int world, long long offset_elems,
+                                        long long n_elems, float scale, unsigned int seq, const unsigned int* seq_base_dev, int n_ctas,
+                                        void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     B200FM_CHECK(peer_data && peer_flags, "allreduce_f32: null pointer table");
     B200FM_CHECK(world >= 2 && world <= kCommMaxWorld && rank >= 0 && rank < world, "allreduce_f32: world=%d rank=%d (2..%d ranks)", world, rank, kCommMaxWorld);
@@ -159,7 +167,7 @@ extern "C" int b200fm_allreduce_f32(void* const* peer_data, void* const* peer_fl
     const long long n4 = n_elems / 4;
     // plain launch (no programmatic dependent launch): the kernel must not start before the producers of the chunk have finished
 #define B200FM_AR_CASE(W_)                                                                                                   \
-    case W_: allreduce_f32_kernel<W_><<<n_ctas, kCommThreads, 0, stream>>>(pr, rank, offset_elems, n4, scale, seq); break;
+    case W_: allreduce_f32_kernel<W_><<<n_ctas, kCommThreads, 0, stream>>>(pr, rank, offset_elems, n4, scale, seq, seq_base_dev); break;
     switch (world) {
         B200FM_AR_CASE(2) B200FM_AR_CASE(3) B200FM_AR_CASE(4) B200FM_AR_CASE(5) B200FM_AR_CASE(6) B200FM_AR_CASE(7) B200FM_AR_CASE(8)
         default: B200FM_CHECK(false, "allreduce_f32: unsupported world size %d", world);

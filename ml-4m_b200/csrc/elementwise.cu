@@ -86,11 +86,26 @@ __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv
 // (unscaled: the 1/n mean factor and the upstream gradient are folded into the following GEMMs via alpha_dev).
 __global__ void __launch_bounds__(256)
 cross_entropy_kernel(const float* __restrict__ logits, long long ld, const int64_t* __restrict__ targets,
-                     float* __restrict__ loss_rows, __nv_bfloat16* __restrict__ dlogits, long long ldd, int V) {
+                     float* __restrict__ loss_rows, __nv_bfloat16* __restrict__ dlogits, long long ldd, int V, const int* __restrict__ n_dev) {
     pdl_enter();
     __shared__ float red[8];
     __shared__ float bc;
     const long long row = blockIdx.x;
+    if (n_dev != nullptr) {
+        // device-side row count (graph-captured head): rows >= n carry no sample.  Their loss is 0 and, up to the next multiple
+        // of 64 (the K block of the weight-gradient GEMM that contracts over rows), their gradient rows are ZERO.
+        const long long n = max(0, __ldg(n_dev));
+        if (row >= n) {
+            if (row < ((n + 63) & ~63ll)) {
+                if (threadIdx.x == 0) loss_rows[row] = 0.f;
+                if (dlogits != nullptr)
+                    for (int j = threadIdx.x * 2; j < V; j += 512) {
+                        if (j + 1 < V) *reinterpret_cast<uint32_t*>(dlogits + row * ldd + j) = 0u; else dlogits[row * ldd + j] = __float2bfloat16_rn(0.f);
+                    }
+            } else if (threadIdx.x == 0) loss_rows[row] = 0.f;
+            return;
+        }
+    }
     const float* l = logits + row * ld;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float m = -INFINITY;
@@ -205,8 +220,11 @@ constexpr int kMtChunk = 8192;      // elements per CTA (256 threads x 8 float4)
 __global__ void __launch_bounds__(256)
 adamw_multi_kernel(const b200fm_adamw_tensor* __restrict__ table, const int* __restrict__ chunk_tensor,
                    const long long* __restrict__ chunk_offset, float lr, float beta1, float beta2, float eps, float wd, float bc1,
-                   float bc2_sqrt, float grad_scale) {
+                   float bc2_sqrt, float grad_scale, const float* __restrict__ hyper_dev) {
     pdl_enter();
+    if (hyper_dev != nullptr) {      // captured in a CUDA graph: the per-step scalars live in device memory {lr, 1 - b1^t, sqrt(1 - b2^t)}
+        lr = __ldg(hyper_dev); bc1 = __ldg(hyper_dev + 1); bc2_sqrt = __ldg(hyper_dev + 2);
+    }
     const b200fm_adamw_tensor t = table[chunk_tensor[blockIdx.x]];
     const long long off = chunk_offset[blockIdx.x];
     const long long end = off + kMtChunk < t.n ? off + kMtChunk : t.n;
@@ -263,7 +281,19 @@ extern "C" int b200fm_adamw_multi(const b200fm_adamw_tensor* table_dev, const in
     const float bc1 = 1.0f - powf(beta1, (float)step);
     const float bc2s = sqrtf(1.0f - powf(beta2, (float)step));
     B200FM_LAUNCH(adamw_multi_kernel, dim3(n_chunks), dim3(256), 0, stream, 1, table_dev, chunk_tensor_dev, chunk_offset_dev, lr, beta1, beta2, eps, weight_decay, bc1,
-                                                   bc2s, grad_scale);
+                                                   bc2s, grad_scale, static_cast<const float*>(nullptr));
+    B200FM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200fm_adamw_multi_dev(const b200fm_adamw_tensor* table_dev, const int* chunk_tensor_dev, const long long* chunk_offset_dev,
+                                      int n_chunks, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                                      const float* hyper_dev, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (n_chunks == 0) return 0;
+    B200FM_CHECK(table_dev && chunk_tensor_dev && chunk_offset_dev && hyper_dev, "adamw_multi_dev: null pointer");
+    B200FM_LAUNCH(adamw_multi_kernel, dim3(n_chunks), dim3(256), 0, stream, 1, table_dev, chunk_tensor_dev, chunk_offset_dev, 0.f, beta1, beta2, eps, weight_decay, 1.f,
+                                                   1.f, grad_scale, hyper_dev);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -302,7 +332,48 @@ extern "C" int b200fm_cross_entropy(const float* logits, long long ld, const int
     if (n == 0) return 0;
     B200FM_CHECK(logits && targets && loss_rows, "cross_entropy: null pointer");
     B200FM_CHECK(V > 0 && (dlogits == nullptr || ldd % 2 == 0), "cross_entropy: bad V / dlogits stride");
-    B200FM_LAUNCH(cross_entropy_kernel, dim3((unsigned)n), dim3(256), 0, stream, 1, logits, ld, targets, loss_rows, reinterpret_cast<__nv_bfloat16*>(dlogits), ldd, V);
+    B200FM_LAUNCH(cross_entropy_kernel, dim3((unsigned)n), dim3(256), 0, stream, 1, logits, ld, targets, loss_rows, reinterpret_cast<__nv_bfloat16*>(dlogits), ldd, V,
+                  static_cast<const int*>(nullptr));
+    B200FM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200fm_cross_entropy_dyn(const float* logits, long long ld, const int64_t* targets, float* loss_rows, void* dlogits,
+                                        long long ldd, long long n_max, int V, const int* n_dev, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (n_max == 0) return 0;
+    B200FM_CHECK(logits && targets && loss_rows && n_dev, "cross_entropy_dyn: null pointer");
+    B200FM_CHECK(V > 0 && (dlogits == nullptr || ldd % 2 == 0), "cross_entropy_dyn: bad V / dlogits stride");
+    B200FM_LAUNCH(cross_entropy_kernel, dim3((unsigned)n_max), dim3(256), 0, stream, 1, logits, ld, targets, loss_rows, reinterpret_cast<__nv_bfloat16*>(dlogits), ldd, V, n_dev);
+    B200FM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// mean of the first *n_dev entries of x (0 when n == 0, like the reference's `torch.zeros(1)` term for an empty modality, fm.py:593-595);
+// inv_n_out (optional) = 1 / max(n, 1): the factor the backward GEMMs fold in through alpha_dev.  Single CTA, deterministic order.
+__global__ void __launch_bounds__(1024)
+masked_mean_kernel(const float* __restrict__ x, const int* __restrict__ n_dev, long long n_max, float* __restrict__ mean_out, float* __restrict__ inv_n_out) {
+    pdl_enter();
+    __shared__ float red[32];
+    const long long n = min((long long)max(0, __ldg(n_dev)), n_max);
+    float s = 0.f;
+    for (long long i = threadIdx.x; i < n; i += 1024) s += x[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 32; ++w) t += red[w];
+        const float inv = 1.0f / (float)(n > 0 ? n : 1);
+        *mean_out = t * inv;
+        if (inv_n_out) *inv_n_out = inv;
+    }
+}
+
+extern "C" int b200fm_masked_mean(const float* x, const int* n_dev, long long n_max, float* mean_out, float* inv_n_out, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    B200FM_CHECK(x && n_dev && mean_out, "masked_mean: null pointer");
+    B200FM_LAUNCH(masked_mean_kernel, dim3(1), dim3(1024), 0, stream, 1, x, n_dev, n_max, mean_out, inv_n_out);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }

@@ -38,18 +38,34 @@ B200FM_DEVINL bool seg_masked(const b200fm_segment& s, int decoder, int b, int l
 __global__ void __launch_bounds__(1024)
 plan_kernel(const SegTable tab, int n_keep, int32_t* __restrict__ src_seg, int32_t* __restrict__ src_pos, int32_t* __restrict__ pos_id,
             uint8_t* __restrict__ pad_mask, int16_t* __restrict__ mod_mask, int16_t* __restrict__ mod_raw,
-            int64_t* __restrict__ target_ids, int32_t* __restrict__ dam_out) {
+            int64_t* __restrict__ target_ids, int32_t* __restrict__ dam_out, const int32_t* __restrict__ order_dev) {
     pdl_enter();
     __shared__ int warp_tot[32];
     __shared__ int carry_s;
+    // concatenation order: tab.seg[] as given, or -- order_dev != NULL -- tab.seg[order_dev[i]] is the i-th segment (the Python-random
+    // decoder shuffle of fm.py:306 as DATA, so a captured CUDA graph can replay with a new order); src_seg always stores the index
+    // into tab.seg[] so that the embedding kernels need no order.
+    __shared__ int ord_s[B200FM_MAX_SEGMENTS];
+    __shared__ int off_s[B200FM_MAX_SEGMENTS + 1];
+    if (threadIdx.x == 0) {
+        int off = 0;
+        for (int i = 0; i < tab.n_seg; ++i) {
+            const int sidx = order_dev ? order_dev[i] : i;
+            ord_s[i] = sidx;
+            off_s[i] = off;
+            off += seg_len(tab.seg[sidx], tab.decoder);
+        }
+        for (int i = tab.n_seg; i <= B200FM_MAX_SEGMENTS; ++i) off_s[i] = off;
+    }
+    __syncthreads();
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int total = tab.offset[tab.n_seg];
+    const int total = off_s[tab.n_seg];
     // pass A: number of valid positions in the whole row (needed to place the masked ones behind them)
     int cnt = 0;
     for (int p = tid; p < total; p += 1024) {
         int s = 0;
-        while (p >= tab.offset[s + 1]) ++s;
-        cnt += seg_masked(tab.seg[s], tab.decoder, b, p - tab.offset[s]) ? 0 : 1;
+        while (p >= off_s[s + 1]) ++s;
+        cnt += seg_masked(tab.seg[ord_s[s]], tab.decoder, b, p - off_s[s]) ? 0 : 1;
     }
     cnt = (int)warp_sum((float)cnt);   // counts <= 2^24: exact in fp32
     if (lane == 0) warp_tot[warp] = cnt;
@@ -64,8 +80,9 @@ plan_kernel(const SegTable tab, int n_keep, int32_t* __restrict__ src_seg, int32
         const int p = base + tid;
         int s = 0, l = 0, valid = 0;
         if (p < total) {
-            while (p >= tab.offset[s + 1]) ++s;
-            l = p - tab.offset[s];
+            while (p >= off_s[s + 1]) ++s;
+            l = p - off_s[s];
+            s = ord_s[s];
             valid = seg_masked(tab.seg[s], tab.decoder, b, l) ? 0 : 1;
         }
         int incl = valid;
@@ -298,17 +315,23 @@ head_rows_kernel(const int16_t* __restrict__ mod_mask, long long n_rows, const i
 }
 
 // out[i] = src[rows[i]] : row gather used to feed the per-modality logits GEMMs (bf16 rows) and their targets (int64).
+// n_dev != NULL: the row count lives on the device (n = min(*n_dev, n)); output rows [n, roundup(n, 128)) are ZERO-filled because a
+// following weight-gradient GEMM contracts over whole 64-row blocks.
 __global__ void gather_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ rows, __nv_bfloat16* __restrict__ out,
-                                        long long n, int D8) {
+                                        long long n, int D8, const int* __restrict__ n_dev) {
     pdl_enter();
-    const long long total = n * D8;
+    long long fill = n;
+    if (n_dev != nullptr) { const long long d = max(0, __ldg(n_dev)); fill = min((d + 127) & ~127ll, n); n = min(d, n); }
+    const long long total = fill * D8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / D8; const int c = (int)(i % D8);
-        reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(src)[(long long)rows[r] * D8 + c];
+        reinterpret_cast<uint4*>(out)[i] = r < n ? reinterpret_cast<const uint4*>(src)[(long long)rows[r] * D8 + c] : make_uint4(0u, 0u, 0u, 0u);
     }
 }
-__global__ void gather_i64_kernel(const int64_t* __restrict__ src, const int32_t* __restrict__ rows, int64_t* __restrict__ out, long long n) {
+__global__ void gather_i64_kernel(const int64_t* __restrict__ src, const int32_t* __restrict__ rows, int64_t* __restrict__ out, long long n,
+                                  const int* __restrict__ n_dev) {
     pdl_enter();
+    if (n_dev != nullptr) n = min((long long)max(0, __ldg(n_dev)), n);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = src[rows[i]];
 }
 // dst[rows[i]] += src[i] (fp32 accumulate of bf16 rows; each destination row is hit by at most one source row per call)
@@ -329,8 +352,9 @@ __global__ void scatter_add_rows_kernel(const __nv_bfloat16* __restrict__ src, c
 
 // dst[rows[i]] = src[i] for bf16 rows (destination rows are distinct)
 __global__ void scatter_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ rows, __nv_bfloat16* __restrict__ dst,
-                                         long long n, int D8) {
+                                         long long n, int D8, const int* __restrict__ n_dev) {
     pdl_enter();
+    if (n_dev != nullptr) n = min((long long)max(0, __ldg(n_dev)), n);
     const long long total = n * D8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / D8; const int c = (int)(i % D8);
@@ -361,6 +385,13 @@ using namespace b200fm;
 extern "C" int b200fm_select_plan(const b200fm_segment* segs, int n_seg, int mode, int B, int n_keep, int32_t* src_seg,
                                   int32_t* src_pos, int32_t* pos_id, uint8_t* pad_mask, int16_t* mod_mask, int16_t* mod_raw,
                                   int64_t* target_ids, int32_t* dam_out, void* stream_) {
+    return b200fm_select_plan_ordered(segs, n_seg, mode, B, n_keep, src_seg, src_pos, pos_id, pad_mask, mod_mask, mod_raw, target_ids, dam_out,
+                                      nullptr, stream_);
+}
+
+extern "C" int b200fm_select_plan_ordered(const b200fm_segment* segs, int n_seg, int mode, int B, int n_keep, int32_t* src_seg,
+                                          int32_t* src_pos, int32_t* pos_id, uint8_t* pad_mask, int16_t* mod_mask, int16_t* mod_raw,
+                                          int64_t* target_ids, int32_t* dam_out, const int32_t* order_dev, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (B == 0) return 0;
     SegTable t;
@@ -372,7 +403,7 @@ extern "C" int b200fm_select_plan(const b200fm_segment* segs, int n_seg, int mod
         B200FM_CHECK(target_ids && dam_out, "select_plan: decoder side needs target_ids and dam outputs");
         for (int i = 0; i < n_seg; ++i) B200FM_CHECK(segs[i].ids && segs[i].dam, "select_plan: decoder segment %d needs ids and dam", i);
     }
-    B200FM_LAUNCH(plan_kernel, dim3(B), dim3(1024), 0, stream, 1, t, n_keep, src_seg, src_pos, pos_id, pad_mask, mod_mask, mod_raw, target_ids, dam_out);
+    B200FM_LAUNCH(plan_kernel, dim3(B), dim3(1024), 0, stream, 1, t, n_keep, src_seg, src_pos, pos_id, pad_mask, mod_mask, mod_raw, target_ids, dam_out, order_dev);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -446,21 +477,27 @@ extern "C" int b200fm_head_rows(const int16_t* mod_mask, long long n_rows, const
 }
 
 extern "C" int b200fm_gather_rows_bf16(const void* src, const int32_t* rows, void* out, long long n, int D, void* stream_) {
+    return b200fm_gather_rows_bf16_dyn(src, rows, out, n, D, nullptr, stream_);
+}
+extern "C" int b200fm_gather_rows_bf16_dyn(const void* src, const int32_t* rows, void* out, long long n, int D, const int* n_dev, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (n == 0) return 0;
     B200FM_CHECK(src && rows && out && D % 8 == 0, "gather_rows_bf16: bad arguments");
     const long long total = n * (D / 8);
     const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-    B200FM_LAUNCH(gather_rows_bf16_kernel, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(src), rows, reinterpret_cast<__nv_bfloat16*>(out), n, D / 8);
+    B200FM_LAUNCH(gather_rows_bf16_kernel, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(src), rows, reinterpret_cast<__nv_bfloat16*>(out), n, D / 8, n_dev);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
 
 extern "C" int b200fm_gather_i64(const int64_t* src, const int32_t* rows, int64_t* out, long long n, void* stream_) {
+    return b200fm_gather_i64_dyn(src, rows, out, n, nullptr, stream_);
+}
+extern "C" int b200fm_gather_i64_dyn(const int64_t* src, const int32_t* rows, int64_t* out, long long n, const int* n_dev, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (n == 0) return 0;
     B200FM_CHECK(src && rows && out, "gather_i64: null pointer");
-    B200FM_LAUNCH(gather_i64_kernel, dim3((int)((n + 255) / 256)), dim3(256), 0, stream, 1, src, rows, out, n);
+    B200FM_LAUNCH(gather_i64_kernel, dim3((int)((n + 255) / 256)), dim3(256), 0, stream, 1, src, rows, out, n, n_dev);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -477,12 +514,15 @@ extern "C" int b200fm_scatter_add_rows(const void* src_bf16, const int32_t* rows
 }
 
 extern "C" int b200fm_scatter_rows_bf16(const void* src, const int32_t* rows, void* dst, long long n, int D, void* stream_) {
+    return b200fm_scatter_rows_bf16_dyn(src, rows, dst, n, D, nullptr, stream_);
+}
+extern "C" int b200fm_scatter_rows_bf16_dyn(const void* src, const int32_t* rows, void* dst, long long n, int D, const int* n_dev, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (n == 0) return 0;
     B200FM_CHECK(src && rows && dst && D % 8 == 0, "scatter_rows_bf16: bad arguments");
     const long long total = n * (D / 8);
     const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-    B200FM_LAUNCH(scatter_rows_bf16_kernel, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(src), rows, reinterpret_cast<__nv_bfloat16*>(dst), n, D / 8);
+    B200FM_LAUNCH(scatter_rows_bf16_kernel, dim3(grid), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(src), rows, reinterpret_cast<__nv_bfloat16*>(dst), n, D / 8, n_dev);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }

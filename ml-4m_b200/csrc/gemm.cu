@@ -44,6 +44,11 @@ struct GemmArgs {
     int act;             // EPI_GELU family: 0 = GELU(erf), 1 = tanh
     int k_splits;        // EPI_F32 only: > 1 -> each work item covers a K slice and accumulates with fp32 atomics (out pre-zeroed)
     int kb_per_split;
+    // device-side problem size (CUDA-graph friendly masked-token head: the per-modality row counts never visit the host):
+    // dyn_mode 1: the number of output rows M is *dyn_dev (<= M), dyn_mode 2 (LAYOUT_TN): the contraction length K is *dyn_dev (<= K).
+    // The launch (grid, tensor maps, split-K plan) is sized for the upper bounds; tiles / K blocks beyond the device value are skipped.
+    const int* dyn_dev;
+    int dyn_mode;
 };
 
 // CTA2: a CTA pair (cluster of 2, one TPC) computes a 256 x BN tile with tcgen05.mma.cta_group::2 -- each CTA stages its own
@@ -126,10 +131,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_m_units = (args.num_m_blocks + cta_stride - 1) / cta_stride;      // CTA2: pairs of 128-row blocks
-    const int num_mn = num_m_units * args.num_n_blocks;
-    const int num_tiles = num_mn * args.k_splits;               // work items: (k slice, m unit, n block), n fastest
-    const int num_kb_total = (args.K + kBK - 1) / kBK;
 
     if (warp == kEpiWarps) {
         if (lane == 0) {
@@ -148,6 +149,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     pdl_trigger();      // TMEM is held: a dependent grid can no longer starve this one of columns
     pdl_wait();         // everything below touches global memory
     const uint32_t tmem_base = *tmem_slot;
+    int M_ = args.M, K_ = args.K, num_m_blocks = args.num_m_blocks;
+    if (args.dyn_dev != nullptr) {
+        const int d = max(0, __ldg(args.dyn_dev));
+        if (args.dyn_mode == 1) { M_ = min(d, args.M); num_m_blocks = (M_ + kBM - 1) / kBM; }
+        else K_ = min(d, args.K);
+    }
+    const int num_m_units = (num_m_blocks + cta_stride - 1) / cta_stride;           // CTA2: pairs of 128-row blocks
+    const int num_mn = num_m_units * args.num_n_blocks;
+    const int num_tiles = num_mn * args.k_splits;               // work items: (k slice, m unit, n block), n fastest
+    const int num_kb_total = (K_ + kBK - 1) / kBK;
 
     if (warp == kEpiWarps) {
         // ------------------------------ TMA producer ------------------------------
@@ -260,7 +271,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const int n_blk = mn % args.num_n_blocks;
             const int row_base = m_blk * kBM + quarter * 32;            // first of this warp's 32 rows
             const int row = row_base + lane;
-            const bool row_ok = row < args.M;
+            const bool row_ok = row < M_;
+            // a K slice that lies entirely beyond the (device-side) contraction length: no MMA ran, the accumulator is undefined
+            const bool empty_acc = (tile / num_mn) * args.kb_per_split >= num_kb_total;
             const uint32_t t_acc = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
             float* stg_f = reinterpret_cast<float*>(smem + kStages * SM::kStageBytes + SM::kBarBytes) + warp * (SM::kEpiStageBytes / 4);
             uint32_t* stg_u = reinterpret_cast<uint32_t*>(stg_f);
@@ -295,9 +308,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                         const float2 ar = unpack_bf16x2(pa[j]), br = unpack_bf16x2(pb[j]);
                         pg[j] = pack_bf16x2(bf16_round(silu_f(ar.x)) * br.x, bf16_round(silu_f(ar.y)) * br.y);
                     }
-                    stage_store_bf16(stg_u, lane, pa, ab, args.ld0, row_base, n, args.M, args.N, vec_ok);
-                    stage_store_bf16(stg_u, lane, pb, ab + args.n_half, args.ld0, row_base, n, args.M, args.N, vec_ok);
-                    stage_store_bf16(stg_u, lane, pg, gg, args.ld1, row_base, n, args.M, args.N, vec_ok);
+                    stage_store_bf16(stg_u, lane, pa, ab, args.ld0, row_base, n, M_, args.N, vec_ok);
+                    stage_store_bf16(stg_u, lane, pb, ab + args.n_half, args.ld0, row_base, n, M_, args.N, vec_ok);
+                    stage_store_bf16(stg_u, lane, pg, gg, args.ld1, row_base, n, M_, args.N, vec_ok);
                 }
             } else {
                 const int n0 = n_blk * BN;
@@ -311,6 +324,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     tmem_ld_wait();
                     const int n = n0 + c * 32;
                     if (n >= args.N) continue;                   // warp-uniform
+                    if (empty_acc) {                             // warp-uniform; only reachable with a device-side K (dyn_mode 2)
+                        if (args.k_splits > 1) continue;         // nothing to add
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = 0u;  // K == 0: the product is exactly zero
+                    }
                     if constexpr (EPI == B200FM_EPI_BF16 || EPI == B200FM_EPI_GELU) {
                         uint32_t p[16];
 #pragma unroll
@@ -324,7 +342,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                             p[j] = pack_bf16x2(v0, v1);
                         }
                         const bool vec0 = (args.ld0 & 7) == 0;
-                        stage_store_bf16(stg_u, lane, p, reinterpret_cast<__nv_bfloat16*>(args.out0), args.ld0, row_base, n, args.M, args.N, vec0);
+                        stage_store_bf16(stg_u, lane, p, reinterpret_cast<__nv_bfloat16*>(args.out0), args.ld0, row_base, n, M_, args.N, vec0);
                         if constexpr (EPI == B200FM_EPI_GELU) {
                             uint32_t g[16];
 #pragma unroll
@@ -332,7 +350,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                                 const float2 pr = unpack_bf16x2(p[j]);       // activation sees the bf16-rounded pre-activation
                                 g[j] = args.act == 0 ? pack_bf16x2(gelu_erf(pr.x), gelu_erf(pr.y)) : pack_bf16x2(tanhf(pr.x), tanhf(pr.y));
                             }
-                            stage_store_bf16(stg_u, lane, g, reinterpret_cast<__nv_bfloat16*>(args.out1), args.ld1, row_base, n, args.M, args.N, (args.ld1 & 7) == 0);
+                            stage_store_bf16(stg_u, lane, g, reinterpret_cast<__nv_bfloat16*>(args.out1), args.ld1, row_base, n, M_, args.N, (args.ld1 & 7) == 0);
                         }
                     } else {
                         // fp32 outputs: transpose through smem, then each lane owns 4 consecutive columns of 8 rows
@@ -353,7 +371,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                             const int grow = row_base + rl;
                             float4 a = *reinterpret_cast<const float4*>(stg_f + rl * 36 + c4);
                             a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
-                            if (grow >= args.M || gcol >= args.N) continue;
+                            if (grow >= M_ || gcol >= args.N) continue;
                             float* o0 = reinterpret_cast<float*>(args.out0) + static_cast<long long>(grow) * args.ld0 + gcol;
                             if constexpr (EPI == B200FM_EPI_F32) {
                                 a.x *= alpha; a.y *= alpha; a.z *= alpha; a.w *= alpha;
@@ -435,7 +453,17 @@ using namespace b200fm;
 extern "C" int b200fm_gemm_bf16(int layout, int epilogue, int M, int N, int K, const void* A, long long lda, const void* B,
                                 long long ldb, void* out0, long long ld0, void* out1, long long ld1, const float* bias,
                                 const float* resid, long long ldr, float alpha, const float* alpha_dev, void* stream_) {
+    return b200fm_gemm_bf16_dyn(layout, epilogue, M, N, K, A, lda, B, ldb, out0, ld0, out1, ld1, bias, resid, ldr, alpha, alpha_dev, nullptr, 0,
+                                stream_);
+}
+
+extern "C" int b200fm_gemm_bf16_dyn(int layout, int epilogue, int M, int N, int K, const void* A, long long lda, const void* B,
+                                    long long ldb, void* out0, long long ld0, void* out1, long long ld1, const float* bias,
+                                    const float* resid, long long ldr, float alpha, const float* alpha_dev, const int* dyn_dev,
+                                    int dyn_mode, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    B200FM_CHECK(dyn_dev == nullptr || (dyn_mode == 1 && layout != LAYOUT_TN) || (dyn_mode == 2 && layout == LAYOUT_TN && epilogue == B200FM_EPI_F32),
+                 "gemm: dyn_mode %d does not fit layout %d / epilogue %d (1: rows of NT/NN, 2: contraction length of TN + EPI_F32)", dyn_mode, layout, epilogue);
     B200FM_CHECK(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
     B200FM_CHECK(layout >= 0 && layout <= 2, "gemm: bad layout %d", layout);
     B200FM_CHECK(epilogue >= 0 && epilogue <= 5, "gemm: bad epilogue %d", epilogue);
@@ -454,6 +482,7 @@ extern "C" int b200fm_gemm_bf16(int layout, int epilogue, int M, int N, int K, c
     a.M = M; a.N = N; a.K = K;
     a.out0 = out0; a.ld0 = ld0; a.out1 = out1; a.ld1 = ld1; a.bias = bias; a.resid = resid; a.ldr = ldr;
     a.n_half = N; a.alpha = alpha; a.alpha_dev = alpha_dev; a.act = act;
+    a.dyn_dev = dyn_dev; a.dyn_mode = dyn_dev ? dyn_mode : 0;
     a.num_m_blocks = (M + kBM - 1) / kBM;
 
     // tile width: 256 when there is enough N to fill it and enough tiles to fill the machine, else 128
