@@ -316,9 +316,15 @@ def run_b200_arm(args):
             from b200fm.parallel import GradSync
             net = gsync = GradSync(model, transport=comm, wait_at_end=False)
             groups = gsync.split_param_groups(groups)
-    opt = FusedAdamW(groups, lr=lr, betas=(0.9, 0.95), eps=1e-8)
+    # whole-step CUDA graph (b200fm.graph): the step is captured once and replayed; B200FM_GRAPH=0 issues every launch from Python
+    use_graph = os.environ.get("B200FM_GRAPH", "1") != "0" and comm != "ddp"
+    opt = FusedAdamW(groups, lr=lr, betas=(0.9, 0.95), eps=1e-8, capturable=use_graph)
     if gsync is not None:
         opt.pre_group_hook = gsync.wait
+    gstep = None
+    if use_graph:
+        from b200fm.graph import GraphedTrainStep
+        gstep = GraphedTrainStep(net, opt, n_tok, n_tok, loss_type="mod")
     import random
     random.seed(rank)
     a, b, c, d = budgets_for(n_tok)
@@ -327,6 +333,11 @@ def run_b200_arm(args):
     h2d = batch_bytes(host_batches[0])
 
     def step(batch):
+        return gstep(batch) if gstep is not None else eager_step(batch)
+
+    def eager_step(batch):
+        if opt.capturable:
+            opt.prepare_step()
         loss, mod_loss = net(batch, num_encoder_tokens=n_tok, num_decoder_tokens=n_tok, loss_type="mod")
         loss.backward()
         if gsync is None:
@@ -348,7 +359,7 @@ def run_b200_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(n_steps, e2e):
+    def timed(n_steps, e2e, step=step):
         calls0 = lib.CALLS["n"]
         sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -371,14 +382,17 @@ def run_b200_arm(args):
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, lib.CALLS["n"] - calls0, (last if last is not None else float(loss.item()))
+        n_calls = lib.CALLS["n"] - calls0
+        if gstep is not None and gstep.graph is not None:
+            n_calls += gstep.kernel_calls_per_step * n_steps        # launches replayed from the captured graph
+        return ms, n_calls, (last if last is not None else float(loss.item()))
 
     for _ in range(max(args.warmup, 3)):
         step(dev_batches[0])
     if os.environ.get("B200FM_NCU_ONE_STEP"):      # ncu --profile-from-start off: exactly one steady-state step is profiled
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        step(dev_batches[1])
+        eager_step(dev_batches[1])
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
@@ -400,11 +414,17 @@ def run_b200_arm(args):
             dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
             params_equal = bool(torch.equal(lo, hi))
         with net.no_sync():          # the same steps with the gradient all-reduce switched off: what the communication costs
-            ms_nocomm, _, _ = timed(args.steps, e2e=False)
+            step_nc = eager_step
+            if use_graph:            # (a second capture; the first graph is not replayed again after this point)
+                g2 = GraphedTrainStep(net, opt, n_tok, n_tok, loss_type="mod", eager_steps=0)
+                g2.eager_left = 0
+                step_nc = g2
+                step_nc(dev_batches[0])
+            ms_nocomm, _, _ = timed(args.steps, e2e=False, step=step_nc)
 
     # roofline of the dominant kernel family (tcgen05 GEMM): CUDA events around every launch during extra steps
     ops.PROFILE = []
-    step(dev_batches[0]); step(dev_batches[1])
+    eager_step(dev_batches[0]); eager_step(dev_batches[1])          # per-launch CUDA events need the launches issued from Python
     torch.cuda.synchronize()
     gemm_ms = sum(s.elapsed_time(e) for s, e, _, _ in ops.PROFILE)
     gemm_flops = sum(f for _, _, f, _ in ops.PROFILE)
@@ -443,6 +463,7 @@ def run_b200_arm(args):
                                 l2_policy="per-step working set (activations+grads > 2 GB) exceeds the 126 MB L2; two alternating input batches"),
                     e2e=dict(value=tps_e2e, unit="tokens/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
                     gpu_launches=launches, loss=loss_val, host_issue_ms_per_step=cpu_issue_ms,
+                    launch_mode=("cuda-graph replay of the whole step (b200fm.graph.GraphedTrainStep)" if use_graph else "python-issued launches"),
                     model_tflops_per_gpu=model_tflops / world,
                     frac_of_bf16_peak=model_tflops / world / peaks["bf16"],
                     roofline=dict(bound="tensor", kernel="gemm_kernel<BN,LAYOUT,EPI> (all tcgen05 GEMM launches of a step)", achieved=achieved,

@@ -153,6 +153,13 @@ def zeros_f32(n, device):
     return _zero_arena.take(n, device)
 
 
+def reset_zero_arena():
+    """Forget the current pre-zeroed chunks.  Called around CUDA-graph capture: the first request INSIDE the capture then allocates
+    (and memsets) a chunk as part of the graph, so every replay starts from zeros; after the capture eager code must not hand out
+    slices of the graph's chunk."""
+    _zero_arena._chunks.clear()
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # gradient destinations: with data-parallel training (b200fm.parallel.GradSync) every parameter has a slot in the flat gradient
 # arena that is all-reduced over NVLink; the backward kernels write there directly instead of into a fresh tensor.
@@ -491,6 +498,54 @@ class LinearCrossEntropyFn(torch.autograd.Function):
         dh = ops.gemm(dlogits, wb, layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16, alpha_dev=coef) if ctx.needs_input_grad[0] else None
         dw = _wgrad(dlogits, h, weight, alpha_dev=coef) if weight.requires_grad else None
         return dh, dw, None
+
+
+class LinearCrossEntropyStaticFn(torch.autograd.Function):
+    """As LinearCrossEntropyFn with a DEVICE-side row count: h bf16 [R, D] holds the modality's rows first (zero rows behind them),
+    targets int64 [R], n_dev int32 [1].  Every launch has a host-independent shape, so the head can be captured in a CUDA graph and
+    costs no host synchronisation; tiles / rows beyond the count are skipped on the device.  Empty modality -> loss 0 (fm.py:593-595)."""
+
+    @staticmethod
+    def forward(ctx, h, weight, targets, n_dev):
+        wb = weight_bf16(weight)
+        logits = ops.gemm(h, wb, epilogue=ops.EPI_F32, n_out=weight.shape[0], dyn=n_dev)
+        loss_rows, dlogits = ops.cross_entropy_dyn(logits, targets, n_dev, want_grad=True)
+        del logits
+        loss, inv_n = ops.masked_mean(loss_rows, n_dev)
+        ctx.save_for_backward(h, weight, dlogits, n_dev, inv_n)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        h, weight, dlogits, n_dev, inv_n = ctx.saved_tensors
+        coef = (dloss.float() * inv_n).reshape(1).contiguous()
+        wb = weight_bf16(weight)[:weight.shape[0]]
+        dh = ops.gemm(dlogits, wb, layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16, alpha_dev=coef, dyn=n_dev) if ctx.needs_input_grad[0] else None
+        dw = None
+        if weight.requires_grad:
+            dw = ops.gemm(dlogits, h, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32, out=_claim(weight), alpha_dev=coef, dyn=n_dev)
+        return dh, dw, None, None
+
+
+class HeadGatherStaticFn(torch.autograd.Function):
+    """HeadGatherFn with device-side counts: every part is a full-height [R, D] buffer whose first counts[i] rows are the
+    modality's rows (rows up to the next multiple of 128 are zero)."""
+
+    @staticmethod
+    def forward(ctx, src, rows, counts_dev):
+        ctx.save_for_backward(rows, counts_dev)
+        ctx.shape = src.shape
+        R = src.shape[0]
+        return tuple(ops.gather_rows_bf16(src, rows[i], R, counts_dev[i:i + 1]) for i in range(rows.shape[0]))
+
+    @staticmethod
+    def backward(ctx, *douts):
+        rows, counts_dev = ctx.saved_tensors
+        d = torch.zeros(ctx.shape, device=rows.device, dtype=torch.bfloat16)
+        for i, g in enumerate(douts):
+            if g is not None:
+                ops.scatter_rows_bf16(g.contiguous(), rows[i], d, ctx.shape[0], counts_dev[i:i + 1])
+        return d, None, None
 
 
 class HeadGatherFn(torch.autograd.Function):

@@ -1,0 +1,125 @@
+"""Whole-step CUDA graph for the 4M train step (forward + backward + gradient all-reduce + AdamW).
+
+Why: one 4M-B step is ~830 kernel launches issued from Python (~20-30 ms of host time on the pool's hosts, ~100 ms for 4M-L's
+48 blocks) against ~33 ms of GPU time -- the host, not the kernels, is what the step waits for.  The reference answers launch
+overhead with `torch.compile`; here the step is captured ONCE with CUDA stream capture and replayed with one `cudaGraphLaunch`.
+
+What makes the step replayable (everything that used to depend on the host is data now):
+  * the Python-`random` shuffle of the decoder modalities (reference fm.py:306) is drawn on the host exactly like the reference does
+    and uploaded as a device permutation (`b200fm_select_plan_ordered`);
+  * the masked-token head works with device-side per-modality row counts (`FourM.static_head`, `b200fm_gemm_bf16_dyn`);
+  * AdamW reads lr / bias corrections from device memory (`FusedAdamW(capturable=True)`), so schedules keep working;
+  * the gradient all-reduce kernels take their sequence numbers from a device counter (b200fm.parallel.GradSync);
+  * the batch is copied into static input buffers (host->device directly when the caller hands over pinned CPU tensors).
+
+Usage (replaces the body of the reference's train loop, run_training_4m.py:712-745):
+
+    step = GraphedTrainStep(model_or_GradSync, optimizer, num_encoder_tokens=128, num_decoder_tokens=128)
+    for batch in loader:
+        for g in optimizer.param_groups: g["lr"] = schedule(it)
+        loss, mod_loss, grad_norm = step(batch)          # device tensors, valid until the next call
+"""
+import random
+
+import torch
+
+from . import functional as BF
+from . import lib
+
+
+class GraphedTrainStep:
+    def __init__(self, net, optimizer, num_encoder_tokens, num_decoder_tokens, loss_type="mod", eager_steps=2, grad_norm=True):
+        self.net = net
+        self.model = net.module if hasattr(net, "module") else net
+        self.opt = optimizer
+        if not getattr(optimizer, "capturable", False):
+            raise ValueError("GraphedTrainStep needs FusedAdamW(capturable=True): the step count / learning rate must live on the device")
+        self.N, self.M, self.loss_type = num_encoder_tokens, num_decoder_tokens, loss_type
+        self.eager_left = max(1, eager_steps)       # first calls run eagerly (allocator / caches / GradSync warm up), then capture
+        self.want_norm = grad_norm
+        self.graph = None
+        self.static_in = None
+        self.static_out = None
+        self.order_dev = None
+        self.dec_mods = None
+        self.model.static_head = True
+        self.replays = 0
+        self.kernel_calls_per_step = 0
+
+    # ------------------------------------------------------------------ pieces
+    def _params(self):
+        return [p for g in self.opt.param_groups for p in g["params"]]
+
+    def _step_body(self, batch):
+        loss, mod_loss = self.net(batch, num_encoder_tokens=self.N, num_decoder_tokens=self.M, loss_type=self.loss_type)
+        loss.backward()
+        self.opt.step()
+        gnorm = None
+        if self.want_norm:           # the logged gradient norm (native_scaler.py:56-65), read after the averaged gradients are final
+            grads = [p.grad for p in self._params() if p.grad is not None]
+            gnorm = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(grads)))
+        self.opt.zero_grad(set_to_none=True)
+        return loss.detach(), {k: v.detach() for k, v in mod_loss.items()}, gnorm
+
+    def _draw_order(self, batch):
+        """The reference's per-step shuffle (fm.py:306): one random.sample over the decoder modalities present in the batch."""
+        dec_mods = [m for m in batch if m in self.model.decoder_embeddings]
+        order = random.sample(dec_mods, len(dec_mods))
+        return dec_mods, [dec_mods.index(m) for m in order]
+
+    def _copy_in(self, batch):
+        for m, d in batch.items():
+            sd = self.static_in[m]
+            for k, v in d.items():
+                sd[k].copy_(v, non_blocking=True)
+
+    # ------------------------------------------------------------------ call
+    def __call__(self, batch):
+        dev = next(self.model.parameters()).device
+        dec_mods, perm = self._draw_order(batch)
+        self.opt.prepare_step()
+        if self.graph is None and self.eager_left > 0:
+            # eager step on the caller's batch with the same code path (device-side order, static head)
+            self.eager_left -= 1
+            self.model._decoder_order_dev = torch.tensor(perm, dtype=torch.int32, device=dev)
+            try:
+                dbatch = {m: {k: v.to(dev, non_blocking=True) for k, v in d.items()} for m, d in batch.items()}
+                return self._step_body(dbatch)
+            finally:
+                self.model._decoder_order_dev = None
+        if self.graph is None:
+            self._capture(batch, dec_mods, dev)
+        if dec_mods != self.dec_mods:
+            raise ValueError(f"GraphedTrainStep was captured for the modalities {self.dec_mods}; this batch has {dec_mods}")
+        self._copy_in(batch)
+        self.order_dev.copy_(torch.tensor(perm, dtype=torch.int32), non_blocking=True)
+        self.graph.replay()
+        self.replays += 1
+        return self.static_out
+
+    def _capture(self, batch, dec_mods, dev):
+        self.dec_mods = dec_mods
+        self.static_in = {m: {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in d.items()} for m, d in batch.items()}
+        self.order_dev = torch.zeros(len(dec_mods), dtype=torch.int32, device=dev)
+        self.model._decoder_order_dev = self.order_dev
+        torch.cuda.synchronize(dev)
+        BF.reset_zero_arena()
+        self.opt.zero_grad(set_to_none=True)
+        g = torch.cuda.CUDAGraph()
+        calls0 = lib.CALLS["n"]
+        try:
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                out = self._step_body(self.static_in)
+        finally:
+            BF.reset_zero_arena()
+            lib.set_option("sm_reserve", 0)
+            self.model._decoder_order_dev = None     # eager calls of the model (evaluation) draw their own shuffle again
+        self.kernel_calls_per_step = lib.CALLS["n"] - calls0      # C-ABI kernel launches baked into one replay
+        self.graph, self.static_out = g, out
+
+    def release(self):
+        """Drop the graph (and its private memory pool); later calls run eagerly again until re-captured."""
+        self.graph = None
+        self.static_in = self.static_out = None
+        self.model._decoder_order_dev = None
+        self.eager_left = 1

@@ -36,9 +36,10 @@ def _rowmajor2d(t, name):
 
 
 def gemm(a, b, layout=LAYOUT_NT, epilogue=EPI_BF16, out=None, out1=None, bias=None, resid=None, alpha=1.0, alpha_dev=None,
-         n_out=None):
+         n_out=None, dyn=None):
     """C = op(A, B) with a fused epilogue; see include/b200fm.h.  a, b bf16 2-D (row stride free, inner stride 1).
-    Returns out (and out1 for SWIGLU / GELU / TANH).  (Hot wrapper: argument validation lives in the C entry point.)"""
+    Returns out (and out1 for SWIGLU / GELU / TANH).  (Hot wrapper: argument validation lives in the C entry point.)
+    dyn: optional device int32 [1] problem size (rows of NT / NN, contraction length of TN), see b200fm_gemm_bf16_dyn."""
     if not a.is_cuda:
         raise lib.B200FMError("b200fm ops need CUDA tensors (there is no CPU fallback)")
     if a.dtype is not torch.bfloat16 or b.dtype is not torch.bfloat16 or a.stride(1) != 1 or b.stride(1) != 1:
@@ -80,10 +81,16 @@ def gemm(a, b, layout=LAYOUT_NT, epilogue=EPI_BF16, out=None, out1=None, bias=No
     if PROFILE is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    lib.call("b200fm_gemm_bf16", layout, epilogue, M, N, K, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(),
-             out.stride(0), 0 if out1 is None else out1.data_ptr(), 0 if out1 is None else out1.stride(0),
-             0 if bias is None else bias.data_ptr(), 0 if resid is None else resid.data_ptr(), 0 if resid is None else resid.stride(0),
-             float(alpha), 0 if alpha_dev is None else alpha_dev.data_ptr(), _stream())
+    if dyn is None:
+        lib.call("b200fm_gemm_bf16", layout, epilogue, M, N, K, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(),
+                 out.stride(0), 0 if out1 is None else out1.data_ptr(), 0 if out1 is None else out1.stride(0),
+                 0 if bias is None else bias.data_ptr(), 0 if resid is None else resid.data_ptr(), 0 if resid is None else resid.stride(0),
+                 float(alpha), 0 if alpha_dev is None else alpha_dev.data_ptr(), _stream())
+    else:
+        lib.call("b200fm_gemm_bf16_dyn", layout, epilogue, M, N, K, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(),
+                 out.stride(0), 0 if out1 is None else out1.data_ptr(), 0 if out1 is None else out1.stride(0),
+                 0 if bias is None else bias.data_ptr(), 0 if resid is None else resid.data_ptr(), 0 if resid is None else resid.stride(0),
+                 float(alpha), 0 if alpha_dev is None else alpha_dev.data_ptr(), dyn.data_ptr(), 2 if layout == LAYOUT_TN else 1, _stream())
     if PROFILE is not None:
         ev1.record()
         PROFILE.append((ev0, ev1, 2.0 * M * K * (2 * N if epilogue == EPI_SWIGLU else N), (layout, epilogue, M, N, K)))
@@ -254,6 +261,25 @@ def cross_entropy(logits, targets, want_grad=True):
     return loss, dl
 
 
+def cross_entropy_dyn(logits, targets, n_dev, want_grad=True):
+    """cross_entropy over the first *n_dev rows (device int32 [1]); later rows: loss 0, dlogits zero up to the next multiple of 64."""
+    n, V = logits.shape
+    assert logits.dtype == torch.float32 and logits.stride(1) == 1 and targets.dtype == torch.int64 and targets.is_contiguous()
+    loss = torch.empty(n, device=logits.device, dtype=torch.float32)
+    Vp = (V + 7) // 8 * 8
+    dl = torch.empty(n, Vp, device=logits.device, dtype=torch.bfloat16)[:, :V] if want_grad else None
+    lib.call("b200fm_cross_entropy_dyn", _ptr(logits), logits.stride(0), _ptr(targets), _ptr(loss), _ptr(dl), dl.stride(0) if want_grad else 0,
+             n, V, n_dev.data_ptr(), _stream())
+    return loss, dl
+
+
+def masked_mean(x, n_dev):
+    """(sum(x[:n]) / max(n, 1), 1 / max(n, 1)) as 0-d device tensors, n = *n_dev."""
+    out = torch.empty(2, device=x.device, dtype=torch.float32)
+    lib.call("b200fm_masked_mean", _ptr(x), n_dev.data_ptr(), x.numel(), out.data_ptr(), out.data_ptr() + 4, _stream())
+    return out[0], out[1]
+
+
 def colsum_bf16(x, out=None):
     _need_cuda(x, out)
     R, N = x.shape
@@ -326,8 +352,9 @@ def make_segments(seg_dicts):
 MODE_DECODER, MODE_IDENTITY, MODE_NO_SUM = 1, 2, 4
 
 
-def select_plan(seg_dicts, mode, B, n_keep, device):
-    """mode: bit flags MODE_DECODER | MODE_IDENTITY | MODE_NO_SUM (include/b200fm.h)."""
+def select_plan(seg_dicts, mode, B, n_keep, device, order_dev=None):
+    """mode: bit flags MODE_DECODER | MODE_IDENTITY | MODE_NO_SUM (include/b200fm.h).  order_dev: optional device int32 [n_seg]
+    concatenation order (segment indices), see b200fm_select_plan_ordered."""
     import ctypes
     arr, keep = make_segments(seg_dicts)
     p = SelectionPlan()
@@ -342,8 +369,8 @@ def select_plan(seg_dicts, mode, B, n_keep, device):
     p.mod_raw = torch.empty(B, n_keep, device=device, dtype=torch.int16)
     p.target_ids = torch.empty(B, n_keep, device=device, dtype=torch.int64) if decoder else None
     p.dam = torch.empty(B, n_keep, **i32) if decoder else None
-    lib.call("b200fm_select_plan", ctypes.addressof(arr), p.n_seg, p.decoder, B, n_keep, _ptr(p.src_seg), _ptr(p.src_pos),
-             _ptr(p.pos_id), _ptr(p.pad_mask), _ptr(p.mod_mask), _ptr(p.mod_raw), _ptr(p.target_ids), _ptr(p.dam), _stream())
+    lib.call("b200fm_select_plan_ordered", ctypes.addressof(arr), p.n_seg, p.decoder, B, n_keep, _ptr(p.src_seg), _ptr(p.src_pos),
+             _ptr(p.pos_id), _ptr(p.pad_mask), _ptr(p.mod_mask), _ptr(p.mod_raw), _ptr(p.target_ids), _ptr(p.dam), _ptr(order_dev), _stream())
     return p
 
 
@@ -385,17 +412,18 @@ def head_rows(mod_mask, mod_ids_dev):
     return rows, counts
 
 
-def gather_rows_bf16(src, rows, n):
+def gather_rows_bf16(src, rows, n, n_dev=None):
+    """out[i] = src[rows[i]] for i < n (n_dev: device int32 [1] count <= n; rows [count, roundup(count, 128)) are zero-filled)."""
     _need_cuda(src, rows)
     D = src.shape[-1]
     out = torch.empty(n, D, device=src.device, dtype=torch.bfloat16)
-    lib.call("b200fm_gather_rows_bf16", _ptr(src), _ptr(rows), _ptr(out), n, D, _stream())
+    lib.call("b200fm_gather_rows_bf16_dyn", _ptr(src), _ptr(rows), _ptr(out), n, D, _ptr(n_dev), _stream())
     return out
 
 
-def gather_i64(src, rows, n):
-    out = torch.empty(n, device=src.device, dtype=torch.int64)
-    lib.call("b200fm_gather_i64", _ptr(src), _ptr(rows), _ptr(out), n, _stream())
+def gather_i64(src, rows, n, n_dev=None):
+    out = torch.empty(n, device=src.device, dtype=torch.int64) if n_dev is None else torch.zeros(n, device=src.device, dtype=torch.int64)
+    lib.call("b200fm_gather_i64_dyn", _ptr(src), _ptr(rows), _ptr(out), n, _ptr(n_dev), _stream())
     return out
 
 
@@ -403,8 +431,8 @@ def scatter_add_rows(src_bf16, rows, dst, n):
     lib.call("b200fm_scatter_add_rows", _ptr(src_bf16), _ptr(rows), _ptr(dst), n, dst.shape[-1], _stream())
 
 
-def scatter_rows_bf16(src, rows, dst, n):
-    lib.call("b200fm_scatter_rows_bf16", _ptr(src), _ptr(rows), _ptr(dst), n, dst.shape[-1], _stream())
+def scatter_rows_bf16(src, rows, dst, n, n_dev=None):
+    lib.call("b200fm_scatter_rows_bf16_dyn", _ptr(src), _ptr(rows), _ptr(dst), n, dst.shape[-1], _ptr(n_dev), _stream())
 
 
 def vq_ema_stats(flat, idx, K, cosine, stats=None):

@@ -11,8 +11,15 @@ from . import lib, ops
 
 
 class FusedAdamW(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+    """capturable=True keeps the per-step scalars (learning rate, bias corrections) in device memory: call `prepare_step()` once per
+    step (it advances the step count and uploads 3 floats per group), then `step()` -- or replay a CUDA graph that captured `step()`
+    (b200fm.graph.GraphedTrainStep).  All parameters then share one step count."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, capturable=False):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.capturable = capturable
+        self._cap_step = 0
+        self._hyper = {}        # group index -> device fp32 [3] = {lr, 1 - beta1^t, sqrt(1 - beta2^t)}
         self._chunk = None
         self._tables = {}       # group index -> dict(device table, chunk maps, pinned staging ring)
         self.pre_group_hook = None   # callable(params): e.g. GradSync.wait -- make the stream wait for this group's reduced gradients
@@ -36,8 +43,15 @@ class FusedAdamW(torch.optim.Optimizer):
                        table=torch.empty(tab.shape, dtype=torch.int64, device=dev), last=None, ring=[], slot=0)
             for _ in range(4):
                 ent["ring"].append([torch.empty(tab.shape, dtype=torch.int64).pin_memory(), None])
+            ent["graph_host"] = torch.empty(tab.shape, dtype=torch.int64).pin_memory()     # source of a captured upload (never reused)
             self._tables[gi] = ent
-        if ent["last"] is None or not np.array_equal(ent["last"], tab):
+        if torch.cuda.is_current_stream_capturing():
+            # the upload becomes a memcpy node of the graph: it needs a pinned source of its own that nothing overwrites later
+            host = ent["graph_host"]
+            host.numpy()[...] = tab
+            ent["table"].copy_(host, non_blocking=True)
+            ent["last"] = None                                        # eager steps after the capture re-upload their own table
+        elif ent["last"] is None or not np.array_equal(ent["last"], tab):
             host, ev = ent["ring"][ent["slot"]]
             if ev is not None:
                 ev.synchronize()                                      # four uploads ago: long done
@@ -48,6 +62,27 @@ class FusedAdamW(torch.optim.Optimizer):
             ent["slot"] = (ent["slot"] + 1) % 4
             ent["last"] = tab
         return ent
+
+    def prepare_step(self):
+        """capturable mode: advance the step count and refresh the device-side scalars of every group (tiny pageable H2D copies,
+        stream-ordered before the kernels that read them)."""
+        import math
+        self._cap_step += 1
+        t = self._cap_step
+        for gi, group in enumerate(self.param_groups):
+            b1, b2 = group["betas"]
+            dev = self._hyper.get(gi)
+            if dev is None:
+                p0 = group["params"][0]
+                dev = self._hyper[gi] = torch.zeros(3, device=p0.device, dtype=torch.float32)
+            dev.copy_(torch.tensor([float(group["lr"]), 1.0 - b1 ** t, math.sqrt(1.0 - b2 ** t)], dtype=torch.float32), non_blocking=True)
+
+    def state_dict(self):
+        if self.capturable:      # replays do not run the Python loop that stamps the per-parameter step
+            for st in self.state.values():
+                if st:
+                    st["step"] = self._cap_step
+        return super().state_dict()
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
@@ -71,7 +106,7 @@ class FusedAdamW(torch.optim.Optimizer):
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st["step"] += 1
+                st["step"] = self._cap_step if self.capturable else st["step"] + 1
                 updated.append(p)
                 if step_no is None:
                     step_no = st["step"]
@@ -91,7 +126,13 @@ class FusedAdamW(torch.optim.Optimizer):
                 tensors.append((p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
                                 views[0].data_ptr() if views else 0, p.numel()))
                 extra_casts += [(p, v) for v in views[1:]]
-            if tensors:
+            if tensors and self.capturable:
+                if gi not in self._hyper:
+                    raise RuntimeError("FusedAdamW(capturable=True): call prepare_step() before step()")
+                ent = self._group_tables(gi, tensors)
+                lib.call("b200fm_adamw_multi_dev", ent["table"].data_ptr(), ent["ct"].data_ptr(), ent["co"].data_ptr(), ent["n_chunks"], float(b1),
+                         float(b2), float(group["eps"]), float(group["weight_decay"]), float(grad_scale), self._hyper[gi].data_ptr(), ops._stream())
+            elif tensors:
                 ent = self._group_tables(gi, tensors)
                 lib.call("b200fm_adamw_multi", ent["table"].data_ptr(), ent["ct"].data_ptr(), ent["co"].data_ptr(), ent["n_chunks"], float(group["lr"]),
                          float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), int(step_no), float(grad_scale),

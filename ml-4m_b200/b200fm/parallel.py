@@ -79,9 +79,10 @@ class _P2PTransport:
         self._flags = (ctypes.c_void_p * self.world)(*self.peer_base)
         dist.barrier(group=group)
 
-    def all_reduce(self, offset, n, seq, stream):
-        lib.call("b200fm_allreduce_f32", self._data, self._flags, self.rank, self.world, offset, n, 1.0 / self.world, seq & 0xFFFFFFFF,
-                 self.n_ctas, stream.cuda_stream)
+    def all_reduce(self, offset, n, seq, stream, seq_base=None):
+        """seq (+ *seq_base, a device int32 the caller advances once per step) must grow with every call, identically on all ranks."""
+        lib.call("b200fm_allreduce_f32_seq", self._data, self._flags, self.rank, self.world, offset, n, 1.0 / self.world, seq & 0xFFFFFFFF,
+                 0 if seq_base is None else seq_base.data_ptr(), self.n_ctas, stream.cuda_stream)
 
     def close(self):
         L = lib.load()
@@ -101,7 +102,7 @@ class _CollectiveTransport:
         self.world = dist.get_world_size(group)
         self.arena = torch.zeros(n_elems, dtype=torch.float32, device=device)
 
-    def all_reduce(self, offset, n, seq, stream):
+    def all_reduce(self, offset, n, seq, stream, seq_base=None):
         v = self.arena[offset:offset + n]
         if v.is_cuda:
             with torch.cuda.stream(stream):
@@ -143,6 +144,9 @@ class GradSync(torch.nn.Module):
         self.reserve_sms = n_ctas if (cuda and transport == "p2p") else 0
         self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1) if cuda else None
         self._step = 0
+        # step-dependent part of the all-reduce sequence numbers, kept ON THE DEVICE and advanced by a stream-ordered add at the start
+        # of every step: a CUDA graph that captured the step replays with fresh sequence numbers without host involvement
+        self._seq_base = torch.zeros(1, dtype=torch.int32, device=self.device) if cuda else None
         self._sync_enabled = True
         self._active = False
         self._callback_queued = False
@@ -277,6 +281,8 @@ class GradSync(torch.nn.Module):
         self._active = True
         if self.small_end > self.small_start:
             self.arena[self.small_start:self.small_end].zero_()          # the kernels ACCUMULATE into these (dgamma, dbeta, mod_emb, ...)
+        if self._seq_base is not None and self._sync_enabled:
+            self._seq_base.add_(len(self.chunks))
 
     def _make_hook(self, slot):
         def hook(p):
@@ -318,12 +324,12 @@ class GradSync(torch.nn.Module):
 
     def _launch(self, ci):
         start, end, _ = self.chunks[ci]
-        seq = self._step * len(self.chunks) + ci + 1
+        seq = ci + 1 if self._seq_base is not None else self._step * len(self.chunks) + ci + 1
         if self.comm_stream is not None:
             ev = torch.cuda.Event()
             ev.record()                                      # everything the compute stream has produced so far
             self.comm_stream.wait_event(ev)
-            self.transport.all_reduce(start, end - start, seq, self.comm_stream)
+            self.transport.all_reduce(start, end - start, seq, self.comm_stream, self._seq_base)
             done = torch.cuda.Event()
             done.record(self.comm_stream)
             self._events[ci] = done

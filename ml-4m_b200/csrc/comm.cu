@@ -10,8 +10,8 @@
 //   every rank owns one arena (cudaMalloc, exported with cudaIpcGetMemHandle) holding all gradients at identical offsets, plus a
 //   small flag block.  For the chunk [off, off+n):
 //     phase 0  CTA c of rank r tells CTA c of every peer "my chunk is final" (flag store, release.sys) and waits for theirs
-//     phase 1  rank r reduces the r-th 1/W of the chunk: v = sum_p peer[p][i] (16-byte loads over NVLink, fixed rank order so every
-//              rank computes bit-identical sums), v *= 1/W, stores v into ALL W arenas (its own included)
+//     phase 1  rank r reduces the r-th 1/W of the chunk: v = sum_p peer[p][i] (16-byte loads over NVLink, 16 in flight per thread),
+//              v *= 1/W, stores v into ALL W arenas (its own included): one owner per element -> bit-identical replicas
 //     phase 2  fence.sys, flag to every peer "my stores have landed", wait for theirs -> the chunk is complete everywhere
 //   flags carry a monotonically increasing sequence number, so they are never reset.
 #include "../../include/b200fm.h"
@@ -75,33 +75,38 @@ allreduce_f32_kernel(const CommPeers pr, int rank, long long off, long long n4, 
     float4* dst[W];
 #pragma unroll
     for (int p = 0; p < W; ++p) {
-        src[p] = reinterpret_cast<const float4*>(pr.data[p] + off);
-        dst[p] = reinterpret_cast<float4*>(pr.data[p] + off);
+        // start with the NEXT rank's arena so the W ranks do not all hit the same peer at the same time
+        const int q = (rank + 1 + p) % W;
+        src[p] = reinterpret_cast<const float4*>(pr.data[q] + off);
+        dst[p] = reinterpret_cast<float4*>(pr.data[q] + off);
     }
+    // NVLink round trips are ~2 us: the few CTAs this kernel is allowed need many 16-byte loads in flight per thread.
+    // U float4 per peer per thread -> U * W independent loads before the first use (16 for every W).
+    constexpr int U = 16 / W >= 1 ? 16 / W : 1;
     const long long stride = (long long)gridDim.x * kCommThreads;
-    for (long long i = lo + (long long)blockIdx.x * kCommThreads + threadIdx.x; i < hi; i += 2 * stride) {
-        const long long j = i + stride;
-        const bool two = j < hi;
-        float4 a[W], b[W];
+    for (long long i0 = lo + (long long)blockIdx.x * kCommThreads + threadIdx.x; i0 < hi; i0 += U * stride) {
+        float4 v[U][W];
 #pragma unroll
-        for (int p = 0; p < W; ++p) a[p] = ld_peer_f4(src[p] + i);
-        if (two) {
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < hi) {
 #pragma unroll
-            for (int p = 0; p < W; ++p) b[p] = ld_peer_f4(src[p] + j);
+                for (int p = 0; p < W; ++p) v[u][p] = ld_peer_f4(src[p] + i);
+            }
         }
-        float4 s = a[0];
 #pragma unroll
-        for (int p = 1; p < W; ++p) { s.x += a[p].x; s.y += a[p].y; s.z += a[p].z; s.w += a[p].w; }
-        s.x *= scale; s.y *= scale; s.z *= scale; s.w *= scale;
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < hi) {
+                // every element is summed by exactly ONE rank (its shard owner) and the result is stored to all ranks, so the
+                // replicas end up bit-identical whatever the summation order is; the owner's order is fixed -> reproducible
+                float4 s = v[u][0];
 #pragma unroll
-        for (int p = 0; p < W; ++p) st_peer_f4(dst[p] + i, s);
-        if (two) {
-            float4 t = b[0];
+                for (int p = 1; p < W; ++p) { s.x += v[u][p].x; s.y += v[u][p].y; s.z += v[u][p].z; s.w += v[u][p].w; }
+                s.x *= scale; s.y *= scale; s.z *= scale; s.w *= scale;
 #pragma unroll
-            for (int p = 1; p < W; ++p) { t.x += b[p].x; t.y += b[p].y; t.z += b[p].z; t.w += b[p].w; }
-            t.x *= scale; t.y *= scale; t.z *= scale; t.w *= scale;
-#pragma unroll
-            for (int p = 0; p < W; ++p) st_peer_f4(dst[p] + j, t);
+                for (int p = 0; p < W; ++p) st_peer_f4(dst[p] + i, s);
+            }
         }
     }
     cta_barrier_all_ranks(pr, rank, W, 1, seq);

@@ -78,6 +78,11 @@ class FourM(nn.Module):
         self.init_std = 0.02
         self.use_act_checkpoint = use_act_checkpoint
         self.num_register_tokens = num_register_tokens
+        # static_head: per-modality row counts of the masked-token head stay ON THE DEVICE (no host synchronisation, every launch has
+        # a batch-independent shape -> the whole step can be captured in a CUDA graph, b200fm.graph.GraphedTrainStep).
+        # Differences to the default path: an empty modality's loss is a 0-d zero instead of the reference's `zeros(1)`.
+        self.static_head = False
+        self._decoder_order_dev = None      # device int32 [n_decoder_mods]: decoder shuffle as data (set by GraphedTrainStep)
 
         self.encoder_modalities = set(encoder_embeddings.keys())
         for emb in encoder_embeddings.values():
@@ -173,8 +178,9 @@ class FourM(nn.Module):
         return int(self.modality_info[mod]['id'])
 
     # ------------------------------------------------------------------ fused selection + embedding (training path)
-    def _embed_side(self, mod_dict, decoder: bool, n_keep: int, order):
-        """PLAN + EMBED kernels over the modalities in `order`.  Returns (x0, emb, plan)."""
+    def _embed_side(self, mod_dict, decoder: bool, n_keep: int, order, order_dev=None):
+        """PLAN + EMBED kernels over the modalities in `order` (or, with order_dev, in the device-side permutation of `order`).
+        Returns (x0, emb, plan)."""
         embs = self.decoder_embeddings if decoder else self.encoder_embeddings
         seg_static, tensors = [], []
         B = None
@@ -193,7 +199,7 @@ class FourM(nn.Module):
         dev = tensors[1].device
         if dev.type != "cuda":
             raise lib.B200FMError("FourM on the B200 path needs CUDA tensors (there is no CPU fallback)")
-        plan = ops.select_plan(seg_static, ops.MODE_DECODER if decoder else 0, B, n_keep, dev)
+        plan = ops.select_plan(seg_static, ops.MODE_DECODER if decoder else 0, B, n_keep, dev, order_dev=order_dev)
         x0, emb = BF.EmbedRowsFn.apply(plan, seg_static, self.dim, not decoder, self.mask_token if decoder else None, *tensors)
         return x0, emb, plan
 
@@ -355,6 +361,31 @@ class FourM(nn.Module):
             mod_count[mod] = n * V                                                # logits.numel() in the reference
         return mod_loss, mod_count
 
+    def _head_losses_static(self, y_bf16, target_ids, decoder_mods, decoder_mod_mask):
+        """_head_losses without any host read: device-side counts drive the per-modality logits / cross-entropy / gradient launches
+        (b200fm_gemm_bf16_dyn).  Returns ({mod: 0-d loss}, {mod: 0-d logits.numel() as fp32})."""
+        dev = y_bf16.device
+        cache = self.__dict__.setdefault("_head_ids_cache", {})
+        key = (tuple(decoder_mods), str(dev))
+        if key not in cache:
+            cache[key] = torch.tensor([self._mod_id(m) for m in decoder_mods], device=dev, dtype=torch.int32)
+        rows, counts = ops.head_rows(decoder_mod_mask.reshape(-1), cache[key])
+        y2 = y_bf16.reshape(-1, y_bf16.shape[-1])
+        R = y2.shape[0]
+        parts = BF.HeadGatherStaticFn.apply(y2, rows, counts)
+        tflat = target_ids.reshape(-1)
+        countf = counts.float()
+        mod_loss, mod_count = {}, {}
+        for i, mod in enumerate(decoder_mods):
+            emb = self.decoder_embeddings[mod]
+            if not (type(emb.to_logits) is nn.Linear and emb.to_logits.bias is None):
+                raise NotImplementedError("static_head needs plain bias-free to_logits layers (every reference preset)")
+            n_dev = counts[i:i + 1]
+            tgt = ops.gather_i64(tflat, rows[i], R, n_dev)
+            mod_loss[mod] = BF.LinearCrossEntropyStaticFn.apply(parts[i], emb.to_logits.weight, tgt, n_dev)
+            mod_count[mod] = countf[i] * emb.to_logits.weight.shape[0]
+        return mod_loss, mod_count
+
     def forward_loss(self, y, target_ids, decoder_mod_dict, decoder_mod_mask, loss_type):
         """Reference fm.py:548-637 (forward_mod_loss / forward_token_loss)."""
         if loss_type not in ('mod', 'modality', 'token'):
@@ -381,8 +412,14 @@ class FourM(nn.Module):
             raise ValueError("Invalid loss type")
         enc_mods = [m for m in mod_dict if m in self.encoder_embeddings]
         dec_mods = [m for m in mod_dict if m in self.decoder_embeddings]
-        # same RNG consumption as cat_decoder_tensors (reference fm.py:306)
-        dec_order = random.sample(dec_mods, len(dec_mods))
+        order_dev = self._decoder_order_dev
+        if order_dev is None:
+            # same RNG consumption as cat_decoder_tensors (reference fm.py:306)
+            dec_order = random.sample(dec_mods, len(dec_mods))
+        else:
+            # the shuffle arrives as device data (drawn by the caller with the same random.sample): replayable launch
+            assert order_dev.numel() == len(dec_mods) and order_dev.dtype == torch.int32
+            dec_order = dec_mods
 
         n_reg = self.num_register_tokens
         x0, enc_emb, eplan = self._embed_side(mod_dict, False, num_encoder_tokens, enc_mods)
@@ -395,9 +432,9 @@ class FourM(nn.Module):
             encoder_mask = torch.cat([torch.zeros(B, n_reg, dtype=torch.bool, device=x0.device), encoder_mask], dim=1)
         encoder_mask = encoder_mask[:, None, :]
 
-        y0, _, dplan = self._embed_side(mod_dict, True, num_decoder_tokens, dec_order)
+        y0, _, dplan = self._embed_side(mod_dict, True, num_decoder_tokens, dec_order, order_dev=order_dev)
         dec_attn_mask = ops.decoder_attention_mask(dplan.dam, dplan.mod_raw, self.decoder_causal_mask, self.decoder_sep_mask)
-        index_sets = None if return_logits else self._head_index_sets(dec_mods, dplan.mod_mask)
+        index_sets = None if (return_logits or self.static_head) else self._head_index_sets(dec_mods, dplan.mod_mask)
 
         context = self._encoder_to_context(x0, encoder_mask, enc_emb)
         y, ypend = y0, None
@@ -411,7 +448,10 @@ class FourM(nn.Module):
 
         if return_logits:
             return {mod: self.decoder_embeddings[mod].forward_logits(y) for mod in dec_mods}
-        mod_loss, mod_count = self._head_losses(y, dplan.target_ids, dec_mods, dplan.mod_mask, index_sets)
+        if self.static_head:
+            mod_loss, mod_count = self._head_losses_static(y, dplan.target_ids, dec_mods, dplan.mod_mask)
+        else:
+            mod_loss, mod_count = self._head_losses(y, dplan.target_ids, dec_mods, dplan.mod_mask, index_sets)
         if loss_type == 'token':
             loss = sum(mod_loss[m] * mod_count[m] for m in mod_loss) / sum(mod_count.values())
         else:
