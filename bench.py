@@ -359,6 +359,9 @@ def run_b200_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_evt = [torch.cuda.Event() for _ in range(2)]
+
     def timed(n_steps, e2e, step=step):
         calls0 = lib.CALLS["n"]
         sync()
@@ -368,9 +371,19 @@ def run_b200_arm(args):
         t_cpu0 = time.perf_counter()
         if e2e:
             # every step's batch is copied from pinned host memory inside the timed region, one batch ahead on a side stream
+            # device -> host read of EVERY step's loss, pipelined by one step: step i's loss travels to pinned memory while step
+            # i+1 is already queued (a blocking .item() would drain the GPU once per step)
+            i = 0
             for batch in DevicePrefetcher((host_batches[i % 2] for i in range(n_steps)), dev):
                 loss, mod_loss, gnorm = step(batch)
-                last = loss.item()                        # device -> host read of the step's result
+                loss_host[i % 2].copy_(loss.detach().reshape(1), non_blocking=True)
+                loss_evt[i % 2].record()
+                if i > 0:
+                    loss_evt[(i - 1) % 2].synchronize()
+                    last = float(loss_host[(i - 1) % 2])
+                i += 1
+            loss_evt[(i - 1) % 2].synchronize()
+            last = float(loss_host[(i - 1) % 2])
         else:
             for i in range(n_steps):
                 loss, mod_loss, gnorm = step(dev_batches[i % 2])
@@ -424,7 +437,10 @@ def run_b200_arm(args):
 
     # roofline of the dominant kernel family (tcgen05 GEMM): CUDA events around every launch during extra steps
     ops.PROFILE = []
-    eager_step(dev_batches[0]); eager_step(dev_batches[1])          # per-launch CUDA events need the launches issued from Python
+    static_head = model.static_head
+    model.static_head = False          # exact per-modality row counts on the host -> exact FLOPs per launch (the static head launches
+    eager_step(dev_batches[0]); eager_step(dev_batches[1])          # with upper-bound shapes); CUDA events need Python-issued launches
+    model.static_head = static_head
     torch.cuda.synchronize()
     gemm_ms = sum(s.elapsed_time(e) for s, e, _, _ in ops.PROFILE)
     gemm_flops = sum(f for _, _, f, _ in ops.PROFILE)
