@@ -250,6 +250,17 @@ int b200fm_vq_ema_stats(const float* z, const long long* idx, long long n, int K
 int b200fm_vq_ema_update_cosine(float* embed, float* cluster_size, const float* bins, const float* embed_sum, int K, int d, float decay,
                                 void* stream);
 
+/* ---- batch assembly on the device (fourm/data/masking.py:236-266 UnifiedMasking.image_mask; RGB loader normalisation) -------------
+ * mask_images: one row per (sample, image-like modality): noise fp32 [rows, L] (the reference's torch.rand), in_budget / tgt_budget
+ * int32 [rows] (tgt_budget NULL or < 0 = the reference's target_budget None) -> input_mask / target_mask uint8 [rows, L] (1 = masked),
+ * decoder_attention_mask int32 [rows, L].  Bit-exact with the reference for the same noise.
+ * patchify_u8: uint8 RGB [B,3,H,W] -> bf16 patches like b200fm_patchify, normalised on the fly (x/255 - mean[c]) / std[c]
+ * (mean3 / std3: HOST arrays of 3 floats), so a batch travels as 1 byte per value instead of 4.                                  */
+int b200fm_mask_images(const float* noise, const int32_t* in_budget, const int32_t* tgt_budget, uint8_t* input_mask,
+                       uint8_t* target_mask, int32_t* dam, long long rows, int L, void* stream);
+int b200fm_patchify_u8(const uint8_t* img, void* out, int B, int C, int H, int W, int P, const float* mean3, const float* std3,
+                       void* stream);
+
 /* ---- data-parallel gradient all-reduce over NVLink peer memory ------------------------------------------------------------
  * Replaces the NCCL all-reduce torch DDP issues for the reference's train step (run_training_4m.py:512; fp32 gradients, mean).
  * Every rank allocates one arena with comm_alloc (cudaMalloc, so it can be exported), exports it with comm_ipc_export (64-byte

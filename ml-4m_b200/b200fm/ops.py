@@ -309,6 +309,36 @@ def patchify(img, patch):
     return out
 
 
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)      # fourm/utils/data_constants.py
+
+
+def patchify_u8(img, patch, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """uint8 RGB [B,3,H,W] -> normalised bf16 patches (same layout as patchify)."""
+    import ctypes
+    _need_cuda(img)
+    assert img.dtype == torch.uint8 and img.is_contiguous()
+    B, C, H, W = img.shape
+    if H % patch or W % patch:
+        raise AssertionError(f"Image sizes {H}x{W} must be divisible by patch sizes {patch}x{patch}")
+    out = torch.empty(B * (H // patch) * (W // patch), patch * patch * C, device=img.device, dtype=torch.bfloat16)
+    m3, s3 = (ctypes.c_float * 3)(*mean), (ctypes.c_float * 3)(*std)
+    lib.call("b200fm_patchify_u8", _ptr(img), _ptr(out), B, C, H, W, patch, m3, s3, _stream())
+    return out
+
+
+def mask_images(noise, in_budget, tgt_budget=None):
+    """noise fp32 [..., L], budgets int32 [...] -> (input_mask bool [..., L], target_mask bool, decoder_attention_mask int32)."""
+    _need_cuda(noise, in_budget, tgt_budget)
+    assert noise.dtype == torch.float32 and noise.is_contiguous() and in_budget.dtype == torch.int32 and in_budget.is_contiguous()
+    L = noise.shape[-1]
+    rows = noise.numel() // L
+    im = torch.empty(noise.shape, device=noise.device, dtype=torch.bool)
+    tm = torch.empty(noise.shape, device=noise.device, dtype=torch.bool)
+    dam = torch.empty(noise.shape, device=noise.device, dtype=torch.int32)
+    lib.call("b200fm_mask_images", _ptr(noise), _ptr(in_budget), _ptr(tgt_budget), _ptr(im), _ptr(tm), _ptr(dam), rows, L, _stream())
+    return im, tm, dam
+
+
 def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, shadow=None):
     _need_cuda(p, g, m, v, shadow)
     lib.call("b200fm_adamw", _ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(shadow), p.numel(), float(lr), float(beta1), float(beta2),

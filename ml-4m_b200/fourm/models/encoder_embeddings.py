@@ -135,7 +135,12 @@ class ImageEncoderEmbedding(nn.Module):
         assert (H % self.patch_size[0] == 0) and (W % self.patch_size[1] == 0), \
             f'Image sizes {H}x{W} must be divisible by patch sizes {self.patch_size[0]}x{self.patch_size[1]}'
         assert self.patch_size[0] == self.patch_size[1], "square patches only on the B200 path"
-        patches = ops.patchify(img.float().contiguous(), self.patch_size[0])
+        if img.dtype == torch.uint8:
+            # raw 8-bit pixels: the loader's ToTensor + Normalize (ImageNet mean / std, fourm/data/modality_transforms.py RGBTransform) is
+            # applied inside the patchify kernel, so the batch crosses PCIe as 1 byte per value (b200fm.masking)
+            patches = ops.patchify_u8(img.contiguous(), self.patch_size[0])
+        else:
+            patches = ops.patchify(img.float().contiguous(), self.patch_size[0])
         if type(self.proj) is nn.Linear:
             return BF.LinearFn.apply(patches, self.proj.weight, self.proj.bias)
         return self.proj(patches)
