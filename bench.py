@@ -683,6 +683,13 @@ def run_vq_arm(args):
         sampler.start()
     ms, launches = timed(args.steps, False)
     ms_e2e, _ = timed(args.steps, True)
+    ms_bf16 = None
+    if not train:
+        # the same call under torch.autocast(bfloat16): bf16 operands instead of the fp32-faithful limb arithmetic
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            for _ in range(3):
+                step(dev_x[0])
+            ms_bf16, _ = timed(args.steps, False)
     clocks = sampler.stop() if rank == 0 else None
     ops.PROFILE = []
     step(dev_x[0]); step(dev_x[1])
@@ -715,14 +722,17 @@ def run_vq_arm(args):
             v, sec, cores, kind = _vq_cpu_tokenize(2, 1, 1)
             cpu = dict(value=v, unit="img/s", cores=cores, kind=kind, sample=f"1 timed VQ.tokenize of 2 images 256x256 (1 warm-up), fp32, {cores} threads of {os.cpu_count()}")
         name = ("VQ-VAE training step (ViT-B enc + dec, K=16384, EMA codebook, MSE, AdamW), BASELINE.json configs[4]" if train else
-                "VQ.tokenize (ViT-B encoder + codebook arg-max K=16384, d=32), 256x256, BASELINE.json configs[4] tokenizer forward")
+                "VQ.tokenize (ViT-B encoder + codebook arg-max K=16384, d=32), 256x256, called like save_vq_tokens.py:288 (no autocast -> "
+                "fp32-faithful limb arithmetic, 3 bf16 limb products per contraction), BASELINE.json configs[4] tokenizer forward")
+        mult = mult if train else 3                      # fp32-faithful: three limb GEMM terms per product
         line = dict(metric="images_per_sec", value=val, unit="img/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=per,
-                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype=("bf16" if train else "bf16x3 (fp32-faithful)"), data="synthetic",
                     config=dict(workload=name, global_batch=B * world, per_gpu_batch=B, image_size=256, tokens_per_image=256, parallelism=f"dp{world}",
                                 l2_policy="two alternating 50 MB input batches; activations exceed the 126 MB L2"),
                     e2e=dict(value=val_e2e, unit="img/s", h2d_bytes_per_step=host_x[0].numel() * 4, d2h_bytes_per_step=4 if train else B * 256 * 2,
                              ms_per_step=ms_e2e / args.steps),
-                    gpu_launches=launches, latents_per_sec=val * 256, model_tflops_per_gpu=model_tflops / 1, frac_of_bf16_peak=model_tflops / peaks["bf16"],
+                    gpu_launches=launches, latents_per_sec=val * 256,
+                    bf16_autocast_img_per_s=(None if ms_bf16 is None else world * B / (ms_bf16 / args.steps / 1e3)), model_tflops_per_gpu=model_tflops / 1, frac_of_bf16_peak=model_tflops / peaks["bf16"],
                     roofline=dict(bound="tensor", kernel="gemm_kernel<BN,LAYOUT,EPI> (all tcgen05 GEMM launches of a step)", achieved=achieved, peak=peaks["bf16"],
                                   unit="TFLOP/s", frac=achieved / peaks["bf16"], traffic=None, peak_source=peaks["src"], launches_per_step=n_gemm // 2,
                                   gemm_ms_per_step=gemm_ms / 2),

@@ -250,6 +250,15 @@ int b200fm_vq_ema_stats(const float* z, const long long* idx, long long n, int K
 int b200fm_vq_ema_update_cosine(float* embed, float* cluster_size, const float* bins, const float* embed_sum, int K, int d, float decay,
                                 void* stream);
 
+/* ---- fp32-faithful inference ("precise mode": callers that run the reference without bf16 autocast, save_vq_tokens.py:288) ------
+ * split_limbs: x fp32 [rows, K] (row stride ldx) -> bf16 [rows, terms * K]: the limb layout of the A (role 0) or B (role 1) operand
+ * of a bf16 GEMM over the contraction length terms * K that reproduces the fp32 product (terms 3: ~2^-16 relative, terms 6: fp32
+ * class).  attention_f32: softmax(q k^T * scale (masked)) v in fp32 FMA arithmetic, head_dim 64, same mask addressing as attention_fwd. */
+int b200fm_split_limbs(const float* x, long long ldx, void* out_bf16, long long rows, int K, int terms, int role, void* stream);
+int b200fm_attention_f32(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv, const uint8_t* mask,
+                         long long mask_b_stride, long long mask_q_stride, float* out, long long ldo, int B, int H, int Nq, int Nk,
+                         float scale, void* stream);
+
 /* ---- batch assembly on the device (fourm/data/masking.py:236-266 UnifiedMasking.image_mask; RGB loader normalisation) -------------
  * mask_images: one row per (sample, image-like modality): noise fp32 [rows, L] (the reference's torch.rand), in_budget / tgt_budget
  * int32 [rows] (tgt_budget NULL or < 0 = the reference's target_budget None) -> input_mask / target_mask uint8 [rows, L] (1 = masked),

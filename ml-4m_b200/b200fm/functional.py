@@ -113,6 +113,65 @@ def weight_bf16_padk(param, k_pad):
     return buf
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# precise mode: fp32-faithful inference for callers that run the reference WITHOUT bf16 autocast (VQ tokenization)
+# ----------------------------------------------------------------------------------------------------------------------
+_precise = {"on": False, "terms": 3}
+
+
+class precise:
+    """`with BF.precise():` -- inference-only (no autograd) code paths that support it (the ViT tokenizers) compute their contractions
+    from bf16 limbs of the fp32 operands (csrc/precise.cu): terms=3 ~ 2^-16 relative per product, terms=6 fp32 class."""
+
+    def __init__(self, terms=3):
+        assert terms in (3, 6)
+        self.terms = terms
+
+    def __enter__(self):
+        self.prev = dict(_precise)
+        _precise.update(on=True, terms=self.terms)
+        return self
+
+    def __exit__(self, *exc):
+        _precise.update(self.prev)
+
+
+def is_precise():
+    return _precise["on"] and not torch.is_grad_enabled()
+
+
+def weight_limbs(param):
+    """Limb layout (B operand) of an fp32 [N, K] weight for the current precise mode, cached per parameter version."""
+    terms = _precise["terms"]
+    root = _root(param)
+    key = (id(root), "limbs", terms, tuple(param.shape))
+    ver = (root._version, param.data_ptr())
+    hit = _shadow.get(key)
+    if hit is not None and hit[0] == ver and hit[2]() is root:
+        return hit[1]
+    with torch.no_grad():
+        w = param.detach()
+        if w.dtype != torch.float32 or not w.is_contiguous():
+            w = w.float().contiguous()
+        buf = ops.split_limbs(w, terms, 1)
+    _shadow[key] = (ver, buf, _wref(root))
+    return buf
+
+
+def linear_f32(x, weight, bias=None, cache=True):
+    """y (fp32) = x W^T + b with fp32-faithful arithmetic on the tcgen05 bf16 GEMM (limb products, fp32 accumulation).
+    cache=False: `weight` is a derived tensor (not a parameter or a view of one): its limbs are rebuilt per call."""
+    x2 = _as2d(x)
+    if x2.dtype != torch.float32:
+        x2 = x2.float()
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    a = ops.split_limbs(x2, _precise["terms"], 0)
+    wl = weight_limbs(weight) if cache else ops.split_limbs(weight.detach().float().contiguous(), _precise["terms"], 1)
+    y = ops.gemm(a, wl, epilogue=ops.EPI_F32, bias=bias, n_out=weight.shape[0])
+    return y.view(*x.shape[:-1], weight.shape[0])
+
+
 def shadow_views(param):
     """bf16 mirrors of `param` currently cached (the fused AdamW kernel writes the first one itself)."""
     ent = _shadow_views.get(id(param))

@@ -78,6 +78,9 @@ SIGNATURES = {
     "b200fm_gather_i64_dyn": [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p],
     "b200fm_scatter_rows_bf16_dyn": [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p],
     "b200fm_allreduce_f32_seq": [c_void_p, c_void_p, c_int, c_int, c_ll, c_ll, c_float, ctypes.c_uint, c_void_p, c_int, c_void_p],
+    "b200fm_split_limbs": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p],
+    "b200fm_attention_f32": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int,
+                             c_float, c_void_p],
     "b200fm_mask_images": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "b200fm_patchify_u8": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "b200fm_comm_flag_bytes": [],

@@ -309,6 +309,30 @@ def patchify(img, patch):
     return out
 
 
+def split_limbs(x, terms, role, out=None):
+    """fp32 [rows, K] (unit inner stride) -> bf16 [rows, terms*K] limb layout of a GEMM operand (role 0 = A, 1 = B)."""
+    _need_cuda(x, out)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    rows, K = x.shape
+    if out is None:
+        out = torch.empty(rows, terms * K, device=x.device, dtype=torch.bfloat16)
+    lib.call("b200fm_split_limbs", _ptr(x), x.stride(0), _ptr(out), rows, K, terms, role, _stream())
+    return out
+
+
+def attention_f32(q, k, v, B, H, Nq, Nk, mask=None, scale=None):
+    """fp32 attention (head_dim 64) on row views q [B*Nq, >=H*64], k / v [B*Nk, >=H*64]; returns fp32 [B*Nq, H*64]."""
+    _need_cuda(q, k, v, mask)
+    for t in (q, k, v):
+        assert t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1
+    scale = 64 ** -0.5 if scale is None else scale
+    out = torch.empty(B * Nq, H * 64, device=q.device, dtype=torch.float32)
+    mk, mp, mbs, mqs = _mask_args(mask, B, Nq, Nk)
+    lib.call("b200fm_attention_f32", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), mp, mbs, mqs, _ptr(out), out.stride(0),
+             B, H, Nq, Nk, float(scale), _stream())
+    return out
+
+
 IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)      # fourm/utils/data_constants.py
 
 

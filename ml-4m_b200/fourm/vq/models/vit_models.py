@@ -108,9 +108,22 @@ class Block(nn.Module):
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
 
     def forward(self, x, **kwargs):
+        if BF.is_precise():
+            return self._forward_precise(x)
         x = self.attn.forward_residual(BF.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, True), x)
         x = self.mlp.forward_residual(BF.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps, True), x)
         return x
+
+    def _forward_precise(self, x):
+        """The reference's fp32 block (vit_models.py:243-246 without autocast): fp32 LayerNorm, fp32-faithful linears, fp32 attention."""
+        B, N, C = x.shape
+        a = self.attn
+        h = BF.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, False)
+        qkv = BF.linear_f32(h, a.qkv.weight, a.qkv.bias).reshape(B * N, 3 * C)
+        o = ops.attention_f32(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, a.num_heads, N, N, None, a.scale).view(B, N, C)
+        x = x + BF.linear_f32(o, a.proj.weight, a.proj.bias)
+        h = BF.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps, False)
+        return x + BF.linear_f32(self.mlp.act(BF.linear_f32(h, self.mlp.fc1.weight, self.mlp.fc1.bias)), self.mlp.fc2.weight, self.mlp.fc2.bias)
 
 
 def _init_vit(module):
@@ -191,6 +204,8 @@ class ViTEncoder(nn.Module):
     def tokens(self, x: torch.Tensor):
         """[B, C, H, W] -> fp32 token stream [B, N, D] after the transformer (and the post-MLP), plus (N_H, N_W)."""
         B, C, H, W = x.shape
+        if BF.is_precise():
+            return self._tokens_precise(x)
         train_proj = self.patch_proj and torch.is_grad_enabled() and self.proj.weight.requires_grad
         if self.patch_proj:
             assert (H % self.P_H == 0) and (W % self.P_W == 0), f'Image sizes {H}x{W} must be divisible by patch sizes {self.P_H}x{self.P_W}'
@@ -215,6 +230,34 @@ class ViTEncoder(nn.Module):
         if hasattr(self, 'post_mlp'):
             h = BF.layer_norm(t, self.norm_mlp.weight, self.norm_mlp.bias, self.norm_mlp.eps, True)
             t = self.post_mlp.forward_residual(h, t)
+        return t, (N_H, N_W)
+
+    def _tokens_precise(self, x):
+        """`tokens` with fp32-faithful arithmetic (what the reference computes when it runs without autocast, save_vq_tokens.py:288)."""
+        B, C, H, W = x.shape
+        x = x.float()
+        if self.patch_proj:
+            assert (H % self.P_H == 0) and (W % self.P_W == 0), f'Image sizes {H}x{W} must be divisible by patch sizes {self.P_H}x{self.P_W}'
+            N_H, N_W = H // self.P_H, W // self.P_W
+            patches = x.reshape(B, C, N_H, self.P_H, N_W, self.P_W).permute(0, 2, 4, 3, 5, 1).reshape(B * N_H * N_W, self.P_H * self.P_W * C)
+            w_lin = self.proj.weight.detach().permute(0, 2, 3, 1).reshape(self.proj.weight.shape[0], -1)
+        else:
+            N_H, N_W = H, W
+            patches = x.permute(0, 2, 3, 1).reshape(B * H * W, C)
+            w_lin = self.proj.weight.detach().reshape(self.proj.weight.shape[0], -1)
+        Kp = (patches.shape[1] + 7) // 8 * 8                     # the GEMM wants 16-byte operand rows
+        if Kp != patches.shape[1]:
+            patches, w_lin = F.pad(patches, (0, Kp - patches.shape[1])), F.pad(w_lin, (0, Kp - w_lin.shape[1]))
+        pe = self.pos_emb
+        if pe.shape[-2:] != (N_H, N_W):
+            pe = F.interpolate(pe, size=(N_H, N_W), mode='bicubic', align_corners=False)
+        t = BF.linear_f32(patches.contiguous(), w_lin, self.proj.bias, cache=False).view(B, N_H * N_W, self.dim_tokens)
+        t = t + pe.flatten(2).transpose(1, 2).float()
+        t = self.blocks(t.contiguous())
+        if hasattr(self, 'post_mlp'):
+            h = BF.layer_norm(t, self.norm_mlp.weight, self.norm_mlp.bias, self.norm_mlp.eps, False)
+            m = self.post_mlp
+            t = t + BF.linear_f32(m.act(BF.linear_f32(h, m.fc1.weight, m.fc1.bias)), m.fc2.weight, m.fc2.bias)
         return t, (N_H, N_W)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

@@ -110,11 +110,22 @@ class VQ(nn.Module, PyTorchModelHubMixin):
         return x
 
     def latents(self, x: torch.Tensor) -> torch.Tensor:
-        """prepare_input -> ViT encoder -> 1x1 quant_proj: fp32 latents [B, Hq, Wq, d] (channel-last, the scan's layout)."""
+        """prepare_input -> ViT encoder -> 1x1 quant_proj: fp32 latents [B, Hq, Wq, d] (channel-last, the scan's layout).
+        Precision follows the caller like the reference's does: under `torch.autocast(bfloat16)` (run_training_vqvae.py) and whenever
+        gradients are recorded the contractions take bf16 operands; an inference call WITHOUT autocast -- `save_vq_tokens.py:288`
+        runs `tokenize` in fp32 -- uses the fp32-faithful limb arithmetic (b200fm.functional.precise), so the arg-min over the codebook
+        sees the reference's latents.  B200FM_VQ_PRECISION = bf16 | x3 | x6 overrides."""
+        import os
+        mode = os.environ.get("B200FM_VQ_PRECISION", "auto")
+        if mode == "auto":
+            mode = "bf16" if (torch.is_grad_enabled() or torch.is_autocast_enabled()) else "x3"
+        if mode != "bf16" and not torch.is_grad_enabled() and not BF.is_precise():
+            with BF.precise(6 if mode == "x6" else 3):
+                return self.latents(x)
         x = self.prepare_input(x)
         t, (Hq, Wq) = self.encoder.tokens(x)                                          # [B, N, D] fp32
         w = self.quant_proj.weight.reshape(self.latent_dim, self.enc_dim)
-        z = BF.LinearF32Fn.apply(t, w)
+        z = BF.linear_f32(t, w) if BF.is_precise() else BF.LinearF32Fn.apply(t, w)
         if self.quant_proj.bias is not None:
             z = z + self.quant_proj.bias
         return z.view(t.shape[0], Hq, Wq, self.latent_dim)
