@@ -40,7 +40,8 @@ int b200fm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, 
 
 /* Runtime options (defaults from the environment variable B200FM_<NAME upper-case>): "pdl" (1: programmatic dependent launch),
  * "gemm_cta_pairs" (1: cta_group::2 GEMM tiles), "ln_bwd_v2" (0: experimental LayerNorm-backward variant), "sm_reserve" (0: number
- * of SMs the persistent GEMM grids leave free, for a concurrent gradient all-reduce kernel).  Changing an
+ * of SMs the persistent GEMM grids leave free, for a concurrent gradient all-reduce kernel), "gemv" (1: NT problems with <= 8 rows --
+ * the linears of the K/V-cached decode loop -- run on an HBM-bound weight-streaming kernel instead of a tcgen05 tile).  Changing an
  * option affects launches issued afterwards; meant for A/B measurements inside one process.                          */
 int b200fm_set_option(const char* name, int value);
 int b200fm_get_option(const char* name, int* value);

@@ -446,6 +446,11 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
 
 static bool use_cta_pairs() { return option(kOptGemmCtaPairs) != 0; }
 
+// gemv.cu: weight-streaming kernel for M <= 8 rows (autoregressive decode)
+bool gemv_applicable(int layout, int epilogue, int M, int N, int K, long long lda, long long ldb);
+int launch_gemv(int epilogue, int M, int N, int K, const void* A, long long lda, const void* W, long long ldb, void* out0, long long ld0,
+                void* out1, long long ld1, const float* bias, float alpha, const float* alpha_dev, cudaStream_t stream);
+
 }  // namespace b200fm
 
 using namespace b200fm;
@@ -477,6 +482,8 @@ extern "C" int b200fm_gemm_bf16_dyn(int layout, int epilogue, int M, int N, int 
         B200FM_CHECK(out1 && (ld1 % 8) == 0 && (reinterpret_cast<uintptr_t>(out1) & 15) == 0, "gemm: second output missing or misaligned");
     if (epilogue == B200FM_EPI_RESID) B200FM_CHECK(resid != nullptr, "gemm: residual epilogue needs resid");
     if (epilogue == B200FM_EPI_SWIGLU) B200FM_CHECK(layout == LAYOUT_NT && (N % 8) == 0, "gemm: swiglu epilogue needs the NT layout and N %% 8 == 0");
+    if (dyn_dev == nullptr && option(kOptGemv) != 0 && gemv_applicable(layout, epilogue, M, N, K, lda, ldb))
+        return launch_gemv(epilogue, M, N, K, A, lda, B, ldb, out0, ld0, out1, ld1, bias, alpha, alpha_dev, stream);
 
     GemmArgs a;
     a.M = M; a.N = N; a.K = K;

@@ -19,6 +19,7 @@ static OptionSlot g_options[kOptCount] = {
     {"gemm_cta_pairs", "B200FM_GEMM_CTA_PAIRS", 1, 1, false},  // tcgen05 cta_group::2 GEMM tiles
     {"ln_bwd_v2", "B200FM_LN_BWD_V2", 0, 0, false},            // EXPERIMENTAL (not yet measured): LayerNorm backward with the dres loads hoisted
     {"sm_reserve", "B200FM_SM_RESERVE", 0, 0, false},          // SMs the persistent GEMM grids leave free (concurrent all-reduce kernel)
+    {"gemv", "B200FM_GEMV", 1, 1, false},                      // NT GEMMs with <= 8 rows run on the weight-streaming kernel (gemv.cu)
 };
 
 int option(int id) {

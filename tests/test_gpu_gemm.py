@@ -119,3 +119,40 @@ def test_gemm_degenerate_shapes():
     dy0 = torch.empty(0, 512, dtype=torch.bfloat16, device="cuda")
     dw = ops.gemm(dy0, x0, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32)               # [512, 128] from zero rows
     assert dw.shape == (512, 128) and float(dw.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 5, 8])
+def test_small_m_weight_streaming_kernel(M):
+    """NT problems with <= 8 rows (the linears of the K/V-cached decode loop) run on the weight-streaming kernel (csrc/gemv.cu):
+    bf16 / fp32 / SwiGLU epilogues vs fp32 torch on the same bf16 operands, and vs the tcgen05 tile path (option gemv = 0)."""
+    from b200fm import lib, ops
+    g = torch.Generator(device="cuda").manual_seed(M)
+    for N, K in ((2048, 2048), (30000, 768), (768, 5464), (100, 64)):
+        x = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+        w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+        bias = torch.randn(N, device="cuda", generator=g)
+        ref = x.float() @ w.float().t() + bias
+        y32 = ops.gemm(x, w, epilogue=ops.EPI_F32, bias=bias)
+        torch.testing.assert_close(y32, ref, rtol=1e-3, atol=1e-3)
+        y16 = ops.gemm(x, w, epilogue=ops.EPI_BF16, bias=bias, alpha=0.5)
+        torch.testing.assert_close(y16.float(), 0.5 * ref, rtol=1e-2, atol=1e-2)
+        lib.set_option("gemv", 0)
+        try:
+            t32 = ops.gemm(x, w, epilogue=ops.EPI_F32, bias=bias)
+        finally:
+            lib.set_option("gemv", 1)
+        torch.testing.assert_close(y32, t32, rtol=1e-3, atol=1e-3)
+    H, K = 5464, 2048
+    x = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w13 = (torch.randn(2 * H, K, device="cuda", generator=g) * 0.05).bfloat16()
+    ab, gate = ops.gemm(x, w13, epilogue=ops.EPI_SWIGLU)
+    a, b = x.float() @ w13[:H].float().t(), x.float() @ w13[H:].float().t()
+    torch.testing.assert_close(ab.float(), torch.cat([a, b], 1), rtol=1e-2, atol=1e-2)
+    ar, br = a.bfloat16().float(), b.bfloat16().float()
+    torch.testing.assert_close(gate.float(), torch.nn.functional.silu(ar).bfloat16().float() * br, rtol=2e-2, atol=2e-2)
+    lib.set_option("gemv", 0)
+    try:
+        ab2, gate2 = ops.gemm(x, w13, epilogue=ops.EPI_SWIGLU)
+    finally:
+        lib.set_option("gemv", 1)
+    torch.testing.assert_close(gate.float(), gate2.float(), rtol=2e-2, atol=2e-2)
