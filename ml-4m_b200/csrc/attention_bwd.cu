@@ -207,21 +207,29 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         uint8_t* sDS = smem + SM::kDS;
         uint32_t* stg = reinterpret_cast<uint32_t*>(smem + SM::kStage) + warp * 512;
         uint32_t it = 0, kvc = 0, stepc = 0;
-        for (int item = blockIdx.x; item < args.num_items; item += gridDim.x, ++it) {
-            const int h = item % args.H, b = item / args.H;
-            // per query row: saved statistics and D = rowsum(dO o O)
-            float m_[NQT], inv_[NQT], D_[NQT];
+        // per query row: saved statistics and D = rowsum(dO o O).  They are requested one item AHEAD (during the previous item's dQ
+        // epilogue): in round 1 the math warps spent ~40 % of their stall samples on exactly these loads (ncu source page, FSETP on m).
+        float m_n[NQT], inv_n[NQT], D_n[NQT];
+        auto prefetch_rows = [&](int item_) {
+            const int h_ = item_ % args.H, b_ = item_ / args.H;
 #pragma unroll
             for (int qt = 0; qt < NQT; ++qt) {
                 const int qrow = qt * 128 + r;
-                m_[qt] = 0.f; inv_[qt] = 0.f; D_[qt] = 0.f;
+                m_n[qt] = 0.f; inv_n[qt] = 0.f; D_n[qt] = 0.f;
                 if (qrow < args.Nq) {
-                    const long long si = (static_cast<long long>(b) * args.H + h) * args.Nq + qrow;
-                    const float2 st = reinterpret_cast<const float2*>(args.stats)[si];
-                    m_[qt] = st.x; inv_[qt] = st.y;
-                    D_[qt] = __ldg(args.dsum + si);
+                    const long long si = (static_cast<long long>(b_) * args.H + h_) * args.Nq + qrow;
+                    const float2 st = __ldg(reinterpret_cast<const float2*>(args.stats) + si);
+                    m_n[qt] = st.x; inv_n[qt] = st.y;
+                    D_n[qt] = __ldg(args.dsum + si);
                 }
             }
+        };
+        if (static_cast<int>(blockIdx.x) < args.num_items) prefetch_rows(blockIdx.x);
+        for (int item = blockIdx.x; item < args.num_items; item += gridDim.x, ++it) {
+            const int h = item % args.H, b = item / args.H;
+            float m_[NQT], inv_[NQT], D_[NQT];
+#pragma unroll
+            for (int qt = 0; qt < NQT; ++qt) { m_[qt] = m_n[qt]; inv_[qt] = inv_n[qt]; D_[qt] = D_n[qt]; }
             for (int kt = 0; kt < nkt; ++kt, ++kvc) {
 #pragma unroll
                 for (int qt = 0; qt < NQT; ++qt, ++stepc) {
@@ -235,15 +243,20 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     const float p_masked = (row_ok && m == kMaskedScore) ? inv : 0.f;
                     const float neg_ds = -D_[qt] * args.scale;                       // ds = p * (dp*scale - D*scale)
                     uint32_t mb[2], tail[2];
+                    uint4 mra[2], mrb[2];
+                    bool mfast[2];
 #pragma unroll
                     for (int cc = 0; cc < 2; ++cc) {
                         const int col0 = kt * 128 + (half * 2 + cc) * 32;
-                        mb[cc] = attn_mask_bits32(mrow, col0, args.Nk);
+                        mfast[cc] = attn_mask_issue32(mrow, col0, args.Nk, mra[cc], mrb[cc], mb[cc]);   // loads in flight across the wait below
                         const int valid = args.Nk - col0;
                         tail[cc] = valid >= 32 ? 0u : (valid <= 0 ? 0xffffffffu : (0xffffffffu << valid));
                     }
                     mbar_wait(sdp_full, stepc & 1);
                     tc_fence_after();
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc)
+                        if (mfast[cc]) mb[cc] = attn_mask_bits_from_raw(mra[cc], mrb[cc]);
 #pragma unroll
                     for (int cc = 0; cc < 2; ++cc) {
                         const int c = half * 2 + cc;                          // this warp's 32-key chunk of the 128-key tile
@@ -321,6 +334,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     attn_stage_store32(stg, lane, pk, base + 32, ld, kt * 128 + quarter * 32, args.Nk);
                 }
             }
+            if (item + static_cast<int>(gridDim.x) < args.num_items) prefetch_rows(item + gridDim.x);   // hidden behind the dQ epilogue
             mbar_wait(dq_full, it & 1);
             tc_fence_after();
 #pragma unroll

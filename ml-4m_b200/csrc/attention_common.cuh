@@ -41,6 +41,27 @@ B200FM_DEVINL uint32_t attn_mask_bits32(const uint8_t* mrow, int col0, int Nk) {
     return bits;
 }
 
+// Split form of attn_mask_bits32 for software pipelining: `issue` starts the two 16-byte loads of an aligned, complete 32-key chunk and
+// returns true (the words are consumed later by attn_mask_bits_from_raw, after the global-load latency has been hidden behind a barrier
+// wait or the previous item's epilogue); otherwise it computes the bits right away (byte loads) into `bits` and returns false.
+B200FM_DEVINL bool attn_mask_issue32(const uint8_t* mrow, int col0, int Nk, uint4& a, uint4& b, uint32_t& bits) {
+    bits = 0u;
+    if (mrow == nullptr) return false;
+    const uint8_t* p = mrow + col0;
+    if (col0 + 32 <= Nk && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        a = __ldg(reinterpret_cast<const uint4*>(p));
+        b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+        return true;
+    }
+    for (int j = 0; j < 32 && col0 + j < Nk; ++j) bits |= (__ldg(p + j) != 0 ? 1u : 0u) << j;
+    return false;
+}
+B200FM_DEVINL uint32_t attn_mask_bits_from_raw(const uint4& a, const uint4& b) {
+    return nonzero_bytes_to_bits(a.x) | (nonzero_bytes_to_bits(a.y) << 4) | (nonzero_bytes_to_bits(a.z) << 8) |
+           (nonzero_bytes_to_bits(a.w) << 12) | (nonzero_bytes_to_bits(b.x) << 16) | (nonzero_bytes_to_bits(b.y) << 20) |
+           (nonzero_bytes_to_bits(b.z) << 24) | (nonzero_bytes_to_bits(b.w) << 28);
+}
+
 // Warp-private smem staging for bf16 row tiles (same scheme as the GEMM epilogue): the thread = row register layout coming out
 // of TMEM is turned into row-contiguous 64 B global segments.  stg: 32 rows x 16 packed words (2 KB), XOR-swizzled 16 B quads.
 B200FM_DEVINL void attn_stage_store32(uint32_t* stg, int lane, const uint32_t (&p)[16], __nv_bfloat16* base, long long ld, int row0,

@@ -134,6 +134,19 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
         uint8_t* sp = smem + SM::kP;
         uint32_t it = 0;
+        // The mask bytes of an item's row are requested one item AHEAD (right after the previous item's softmax) and turned into bits only
+        // after the wait for the scores: in round 1 the softmax warps spent ~15 % of their samples stalled on these loads (ncu source page).
+        uint4 mra[NKT * 4], mrb[NKT * 4];
+        uint32_t mb[NKT * 4];
+        bool mfast[NKT * 4];
+        auto issue_mask = [&](int item_) {
+            const int qt_ = (item_ / args.H) % args.q_tiles, b_ = item_ / (args.H * args.q_tiles);
+            const int qrow_ = qt_ * 128 + r;
+            const uint8_t* mrow_ = args.mask ? args.mask + b_ * args.mask_b_stride + (qrow_ < args.Nq ? qrow_ : 0) * args.mask_q_stride : nullptr;
+#pragma unroll
+            for (int c = 0; c < NKT * 4; ++c) mfast[c] = attn_mask_issue32(mrow_, c * 32, args.Nk, mra[c], mrb[c], mb[c]);
+        };
+        if (static_cast<int>(blockIdx.x) < args.num_items) issue_mask(blockIdx.x);
         for (int item = blockIdx.x; item < args.num_items; item += gridDim.x, ++it) {
             const int h = item % args.H;
             const int qt = (item / args.H) % args.q_tiles;
@@ -141,20 +154,20 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             const uint32_t par = it & 1;
             const int qrow = qt * 128 + r;
             const bool row_ok = qrow < args.Nq;
-            const uint8_t* mrow = args.mask ? args.mask + b * args.mask_b_stride + (row_ok ? qrow : 0) * args.mask_q_stride : nullptr;
-
-            // mask bits of the whole row are fetched before the scores are ready (hides the global-load latency)
-            uint32_t mb[NKT * 4], tail[NKT * 4];
-            uint32_t any_masked = 0u;
+            uint32_t tail[NKT * 4];
 #pragma unroll
             for (int c = 0; c < NKT * 4; ++c) {
-                mb[c] = attn_mask_bits32(mrow, c * 32, args.Nk);                   // keys >= Nk report 0
                 const int valid = args.Nk - c * 32;                                // keys of this chunk that exist
                 tail[c] = valid >= 32 ? 0u : (valid <= 0 ? 0xffffffffu : (0xffffffffu << valid));
-                any_masked |= mb[c];
             }
             mbar_wait(s_full, par);
             tc_fence_after();
+            uint32_t any_masked = 0u;
+#pragma unroll
+            for (int c = 0; c < NKT * 4; ++c) {
+                if (mfast[c]) mb[c] = attn_mask_bits_from_raw(mra[c], mrb[c]);       // keys >= Nk report 0
+                any_masked |= mb[c];
+            }
             // pass 1: row maximum over the unmasked keys, on the raw scores (scale > 0 keeps the order); a masked key counts as
             // kMaskedScore in the log2 domain, exactly like masked_fill(-finfo.max) followed by the softmax's max
             float mu = -INFINITY;
@@ -221,6 +234,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(p_full);
+            if (item + static_cast<int>(gridDim.x) < args.num_items) issue_mask(item + gridDim.x);    // next item's mask, hidden behind P V + epilogue
 
             const float inv = 1.0f / sum;
             if (row_ok && args.stats) {
