@@ -685,11 +685,14 @@ def run_vq_arm(args):
     ms_e2e, _ = timed(args.steps, True)
     ms_bf16 = None
     if not train:
-        # the same call under torch.autocast(bfloat16): bf16 operands instead of the fp32-faithful limb arithmetic
-        with torch.autocast("cuda", dtype=torch.bfloat16):
+        # the same call with bf16 operands (what a caller under torch.autocast(bfloat16) gets) instead of the fp32-faithful limb arithmetic
+        os.environ["B200FM_VQ_PRECISION"] = "bf16"
+        try:
             for _ in range(3):
                 step(dev_x[0])
             ms_bf16, _ = timed(args.steps, False)
+        finally:
+            os.environ.pop("B200FM_VQ_PRECISION", None)
     clocks = sampler.stop() if rank == 0 else None
     ops.PROFILE = []
     step(dev_x[0]); step(dev_x[1])

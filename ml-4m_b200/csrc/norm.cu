@@ -141,6 +141,110 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, c
     }
 }
 
+// Pipelined variant (option "ln_bwd_v2" = 2): one CTA per SM holds 8 rows in flight in the default kernel, and every row costs two
+// dependent memory phases (x, dy -> two warp reductions -> dres -> stores): 3.7 TB/s.  Here a warp requests ALL operands of its NEXT row
+// (x, dy, dres) before it reduces the current one, so two rows per warp are in flight and the reductions overlap the loads.
+template <int VEC>
+struct LnRow {
+    float4 x[VEC];
+    uint2 dy[VEC];
+    float4 r[VEC];
+    float mean, rstd;
+};
+template <int VEC>
+B200FM_DEVINL void ln_row_load(LnRow<VEC>& b, const __nv_bfloat16* dy, const float* x, const float* mean_in, const float* rstd_in,
+                               const float* dres, int row, int lane) {
+    constexpr int D = VEC * 128;
+    b.mean = mean_in[row]; b.rstd = rstd_in[row];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        b.x[i] = reinterpret_cast<const float4*>(x + (size_t)row * D)[i * 32 + lane];
+        b.dy[i] = reinterpret_cast<const uint2*>(dy + (size_t)row * D)[i * 32 + lane];
+        b.r[i] = dres ? __ldcs(reinterpret_cast<const float4*>(dres + (size_t)row * D) + i * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+template <int VEC>
+B200FM_DEVINL void ln_row_finish(const LnRow<VEC>& b, const float4 (&g)[VEC], float4 (&pg)[VEC], float4 (&pb)[VEC], float* dx_out,
+                                 __nv_bfloat16* dx_bf16, int row, int lane) {
+    constexpr int D = VEC * 128;
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const float2 a = unpack_bf16x2(b.dy[i].x), c = unpack_bf16x2(b.dy[i].y);
+        const float4 d = make_float4(a.x, a.y, c.x, c.y);
+        const float4 xh = make_float4((b.x[i].x - b.mean) * b.rstd, (b.x[i].y - b.mean) * b.rstd, (b.x[i].z - b.mean) * b.rstd, (b.x[i].w - b.mean) * b.rstd);
+        const float4 gy = make_float4(d.x * g[i].x, d.y * g[i].y, d.z * g[i].z, d.w * g[i].w);
+        c1 += (gy.x + gy.y) + (gy.z + gy.w);
+        c2 += (gy.x * xh.x + gy.y * xh.y) + (gy.z * xh.z + gy.w * xh.w);
+        pg[i].x += d.x * xh.x; pg[i].y += d.y * xh.y; pg[i].z += d.z * xh.z; pg[i].w += d.w * xh.w;
+        pb[i].x += d.x; pb[i].y += d.y; pb[i].z += d.z; pb[i].w += d.w;
+    }
+    c1 = warp_sum(c1) * (1.0f / D);
+    c2 = warp_sum(c2) * (1.0f / D);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const float2 a = unpack_bf16x2(b.dy[i].x), c = unpack_bf16x2(b.dy[i].y);
+        const float4 d = make_float4(a.x, a.y, c.x, c.y);
+        const float4 xh = make_float4((b.x[i].x - b.mean) * b.rstd, (b.x[i].y - b.mean) * b.rstd, (b.x[i].z - b.mean) * b.rstd, (b.x[i].w - b.mean) * b.rstd);
+        float4 o;
+        o.x = b.rstd * (d.x * g[i].x - c1 - xh.x * c2) + b.r[i].x;
+        o.y = b.rstd * (d.y * g[i].y - c1 - xh.y * c2) + b.r[i].y;
+        o.z = b.rstd * (d.z * g[i].z - c1 - xh.z * c2) + b.r[i].z;
+        o.w = b.rstd * (d.w * g[i].w - c1 - xh.w * c2) + b.r[i].w;
+        reinterpret_cast<float4*>(dx_out + (size_t)row * D)[i * 32 + lane] = o;
+        if (dx_bf16)
+            reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * D)[i * 32 + lane] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+    }
+}
+template <int VEC>
+__global__ void __launch_bounds__(kLnWarps * 32)
+layernorm_bwd_pipe_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                          const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ dres,
+                          float* __restrict__ dx_out, __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma,
+                          float* __restrict__ dbeta, int rows) {
+    pdl_enter();
+    __shared__ float red[kLnWarps][128 + 4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 g[VEC], pg[VEC], pb[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        g[i] = reinterpret_cast<const float4*>(gamma)[i * 32 + lane];
+        pg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int stride = gridDim.x * kLnWarps;
+    int row = blockIdx.x * kLnWarps + warp;
+    LnRow<VEC> b0, b1;
+    if (row < rows) ln_row_load<VEC>(b0, dy, x, mean_in, rstd_in, dres, row, lane);
+    while (row < rows) {
+        const int r1 = row + stride;
+        if (r1 < rows) ln_row_load<VEC>(b1, dy, x, mean_in, rstd_in, dres, r1, lane);
+        ln_row_finish<VEC>(b0, g, pg, pb, dx_out, dx_bf16, row, lane);
+        if (r1 >= rows) break;
+        const int r2 = r1 + stride;
+        if (r2 < rows) ln_row_load<VEC>(b0, dy, x, mean_in, rstd_in, dres, r2, lane);
+        ln_row_finish<VEC>(b1, g, pg, pb, dx_out, dx_bf16, r1, lane);
+        row = r2;
+    }
+    if (dgamma == nullptr && dbeta == nullptr) return;
+    for (int pass = 0; pass < 2; ++pass) {
+        float* dst = pass == 0 ? dgamma : dbeta;
+        if (dst == nullptr) continue;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            __syncthreads();
+            *reinterpret_cast<float4*>(&red[warp][lane * 4]) = pass == 0 ? pg[i] : pb[i];
+            __syncthreads();
+            if (threadIdx.x < 128) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < kLnWarps; ++w) s += red[w][threadIdx.x];
+                atomicAdd(dst + i * 128 + threadIdx.x, s);
+            }
+        }
+    }
+}
+
 // EXPERIMENTAL variant (option "ln_bwd_v2", default off, not yet measured on hardware): identical arithmetic, but the dres loads are
 // issued together with x / dy instead of after the two warp reductions, so a row costs one memory round trip instead of two.
 template <int VEC, bool DY_BF16>
@@ -340,10 +444,12 @@ extern "C" int b200fm_layernorm_bwd(const void* dy, int dy_is_bf16, const float*
     B200FM_CHECK(D % 128 == 0 && D >= 128 && D <= 2048, "layernorm_bwd: D=%d unsupported", D);
     int grid = ln_grid(rows);
     if (grid > 148 * 2) grid = 148 * 2;       // fewer blocks -> fewer column atomics
-    const bool v2 = option(kOptLnBwdV2) != 0;
+    const bool v2 = option(kOptLnBwdV2) == 1;
+    const bool pipe = option(kOptLnBwdV2) == 2;
 #define LN_BWD(V)                                                                                                          \
     case V:                                                                                                                \
-        if (v2 && dy_is_bf16) B200FM_LAUNCH((layernorm_bwd_v2_kernel<V, true>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, dy, x, gamma, mean, rstd, dres, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows); \
+        if (pipe && dy_is_bf16) B200FM_LAUNCH((layernorm_bwd_pipe_kernel<V>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd, dres, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows); \
+        else if (v2 && dy_is_bf16) B200FM_LAUNCH((layernorm_bwd_v2_kernel<V, true>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, dy, x, gamma, mean, rstd, dres, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows); \
         else if (dy_is_bf16) B200FM_LAUNCH((layernorm_bwd_kernel<V, true>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, dy, x, gamma, mean, rstd, dres, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows); \
         else B200FM_LAUNCH((layernorm_bwd_kernel<V, false>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, dy, x, gamma, mean, rstd, dres, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows);          \
         break;

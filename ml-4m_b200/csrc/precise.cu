@@ -82,12 +82,13 @@ attention_f32_kernel(const float* __restrict__ q, long long ldq, const float* __
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
                 const int j = c0 + jj;
-                float acc = 0.f;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;                  // four independent chains: FMA latency is hidden by ILP
 #pragma unroll
                 for (int d = 0; d < 64; d += 4) {
                     const float4 kk = *reinterpret_cast<const float4*>(&ks[j][d]);
-                    acc = fmaf(qr[d], kk.x, acc); acc = fmaf(qr[d + 1], kk.y, acc); acc = fmaf(qr[d + 2], kk.z, acc); acc = fmaf(qr[d + 3], kk.w, acc);
+                    a0 = fmaf(qr[d], kk.x, a0); a1 = fmaf(qr[d + 1], kk.y, a1); a2 = fmaf(qr[d + 2], kk.z, a2); a3 = fmaf(qr[d + 3], kk.w, a3);
                 }
+                float acc = (a0 + a1) + (a2 + a3);
                 if (j >= nj) acc = -INFINITY;                                    // tile padding: excluded exactly
                 else if (mrow && mrow[k0 + j]) acc = -FLT_MAX;                    // masked_fill(-finfo.max), fm_utils.py:169
                 s[jj] = acc;

@@ -108,11 +108,10 @@ def test_vq_scan_full_size_properties():
     _check_scan(idx.cpu()[sub], V.cosine_scan(z[sub], cb), V.scan_scores(z[sub], cb, True), 1e-6)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("B200FM_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental kernel variants are validated on demand (B200FM_TEST_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("rows,D", [(37, 384), (16384, 768), (300, 1024)])
+@pytest.mark.parametrize("rows,D", [(37, 384), (16384, 768), (300, 1024), (9, 768)])
 def test_layernorm_bwd_v2_matches_v1(rows, D):
-    """Option "ln_bwd_v2" (dres loads hoisted ahead of the reductions) must reproduce the default kernel bit for bit on dx."""
+    """Option "ln_bwd_v2" = 1 (dres loads hoisted ahead of the reductions) and = 2 (two rows per warp in flight) must reproduce the
+    default kernel bit for bit on dx."""
     from b200fm import lib, ops
     g = torch.Generator().manual_seed(5)
     x = (torch.randn(rows, D, generator=g) * 2 + 0.3).cuda()
@@ -121,7 +120,7 @@ def test_layernorm_bwd_v2_matches_v1(rows, D):
     dres = torch.randn(rows, D, generator=g).cuda()
     _, mean, rstd = ops.layernorm_fwd(x, w, None, 1e-6)
     outs = []
-    for v in (0, 1):
+    for v in (0, 1, 2):
         lib.set_option("ln_bwd_v2", v)
         try:
             dgamma = torch.zeros(D, device="cuda")
@@ -129,5 +128,6 @@ def test_layernorm_bwd_v2_matches_v1(rows, D):
             outs.append((dx.clone(), dxb.clone(), dgamma.clone()))
         finally:
             lib.set_option("ln_bwd_v2", 0)
-    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
-    torch.testing.assert_close(outs[0][2], outs[1][2], rtol=1e-4, atol=1e-4 * rows ** 0.5)
+    for o in outs[1:]:
+        assert torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1])
+        torch.testing.assert_close(outs[0][2], o[2], rtol=1e-4, atol=1e-4 * rows ** 0.5)
