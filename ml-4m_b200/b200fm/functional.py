@@ -235,16 +235,55 @@ def _acc_f32(param, n, device):
     return v.view(-1) if v is not None else zeros_f32(n, device)
 
 
-def _wgrad(dy2, x2, weight, alpha_dev=None):
+# Weight-gradient GEMMs are LEAVES of the backward graph: nothing in backward consumes them.  Under CUDA-graph capture they can run
+# on a second captured stream, concurrently with the dgrad / attention / LayerNorm chain: the persistent GEMM grids are statically
+# scheduled, so the last partial wave of a kernel leaves SMs idle (2.6 waves of CTA-pair tiles for the K = N = 768 shapes) -- CTAs of
+# a wgrad kernel from the other stream fill them.  Enabled by GraphedTrainStep (B200FM_SIDE_WGRAD=1); operands are kept alive until
+# the join so the graph's allocator cannot reuse their blocks while the side stream still reads them.
+_side = {"stream": None, "keep": [], "used": False}
+
+
+def enable_side_wgrad(stream):
+    _side.update(stream=stream, keep=[], used=False)
+
+
+def side_stream():
+    return _side["stream"] if _side["used"] else None
+
+
+def join_side_wgrad(disable=False):
+    """Make the current stream wait for all side-stream weight gradients issued so far (before the optimizer reads them)."""
+    st = _side["stream"]
+    if st is not None and _side["used"]:
+        torch.cuda.current_stream().wait_stream(st)
+        _side["keep"].clear()
+        _side["used"] = False
+    if disable:
+        _side["stream"] = None
+
+
+def _tn_gemm(a, b, out, alpha_dev=None, dyn=None):
+    st = _side["stream"]
+    if st is None:
+        return ops.gemm(a, b, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32, out=out, alpha_dev=alpha_dev, dyn=dyn)
+    st.wait_stream(torch.cuda.current_stream())               # the producers of a / b (and of the output's previous contents)
+    with torch.cuda.stream(st):
+        res = ops.gemm(a, b, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32, out=out, alpha_dev=alpha_dev, dyn=dyn)
+    _side["keep"].append((a, b, alpha_dev, dyn))
+    _side["used"] = True
+    return res
+
+
+def _wgrad(dy2, x2, weight, alpha_dev=None, dyn=None):
     """dW (fp32) = dy^T x, written into the parameter's arena slot when there is one."""
-    return ops.gemm(dy2, x2, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32, out=_claim(weight), alpha_dev=alpha_dev)
+    return _tn_gemm(dy2, x2, _claim(weight), alpha_dev, dyn)
 
 
 def _wgrad13(dab, h, w1, w3, H, Hp):
     """[dW1; dW3] of a SwiGLU block: ONE [2Hp, D] GEMM output, placed over the adjacent fc1 / fc3 arena slots when possible."""
     s = getattr(w1, "_b200fm_slot", None)
     out = s.sync.claim_pair(w1, w3, Hp) if s is not None else None
-    dw13 = ops.gemm(dab, h, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32, out=out)
+    dw13 = _tn_gemm(dab, h, out)
     return dw13[:H], dw13[Hp:Hp + H]
 
 
@@ -582,7 +621,7 @@ class LinearCrossEntropyStaticFn(torch.autograd.Function):
         dh = ops.gemm(dlogits, wb, layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16, alpha_dev=coef, dyn=n_dev) if ctx.needs_input_grad[0] else None
         dw = None
         if weight.requires_grad:
-            dw = ops.gemm(dlogits, h, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32, out=_claim(weight), alpha_dev=coef, dyn=n_dev)
+            dw = _wgrad(dlogits, h, weight, alpha_dev=coef, dyn=n_dev)
         return dh, dw, None, None
 
 
@@ -866,7 +905,7 @@ class GatedMlpSubLayerFn(torch.autograd.Function):
             if Hp == H:
                 dw2 = _wgrad(db, g, w2)                                                     # [D, H], into the gradient arena when there is one
             else:
-                dw2 = ops.gemm(db, g, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32)[:, :H]  # [D, Hp] -> strided view (copied by autograd)
+                dw2 = _tn_gemm(db, g, None)[:, :H]                                         # [D, Hp] -> strided view (copied by autograd)
         db2 = ops.colsum_bf16(db) if has_b2 else None
         dab = ops.swiglu_bwd(ab, dg)
         dh = ops.gemm(dab, weight_bf16(w1, w3), layout=ops.LAYOUT_NN, epilogue=ops.EPI_BF16)

@@ -53,6 +53,7 @@ class GraphedTrainStep:
     def _step_body(self, batch):
         loss, mod_loss = self.net(batch, num_encoder_tokens=self.N, num_decoder_tokens=self.M, loss_type=self.loss_type)
         loss.backward()
+        BF.join_side_wgrad()            # (weight-gradient GEMMs that ran on the side stream, see functional._tn_gemm)
         self.opt.step()
         gnorm = None
         if self.want_norm:           # the logged gradient norm (native_scaler.py:56-65), read after the averaged gradients are final
@@ -107,10 +108,15 @@ class GraphedTrainStep:
         self.opt.zero_grad(set_to_none=True)
         g = torch.cuda.CUDAGraph()
         calls0 = lib.CALLS["n"]
+        import os
+        side = torch.cuda.Stream(device=dev) if os.environ.get("B200FM_SIDE_WGRAD", "0") == "1" else None
         try:
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                if side is not None:
+                    BF.enable_side_wgrad(side)
                 out = self._step_body(self.static_in)
         finally:
+            BF.join_side_wgrad(disable=True)
             BF.reset_zero_arena()
             lib.set_option("sm_reserve", 0)
             self.model._decoder_order_dev = None     # eager calls of the model (evaluation) draw their own shuffle again

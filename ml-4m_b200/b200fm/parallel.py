@@ -79,10 +79,10 @@ class _P2PTransport:
         self._flags = (ctypes.c_void_p * self.world)(*self.peer_base)
         dist.barrier(group=group)
 
-    def all_reduce(self, offset, n, seq, stream, seq_base=None):
+    def all_reduce(self, offset, n, seq, stream, seq_base=None, n_ctas=None):
         """seq (+ *seq_base, a device int32 the caller advances once per step) must grow with every call, identically on all ranks."""
         lib.call("b200fm_allreduce_f32_seq", self._data, self._flags, self.rank, self.world, offset, n, 1.0 / self.world, seq & 0xFFFFFFFF,
-                 0 if seq_base is None else seq_base.data_ptr(), self.n_ctas, stream.cuda_stream)
+                 0 if seq_base is None else seq_base.data_ptr(), n_ctas or self.n_ctas, stream.cuda_stream)
 
     def close(self):
         L = lib.load()
@@ -102,7 +102,7 @@ class _CollectiveTransport:
         self.world = dist.get_world_size(group)
         self.arena = torch.zeros(n_elems, dtype=torch.float32, device=device)
 
-    def all_reduce(self, offset, n, seq, stream, seq_base=None):
+    def all_reduce(self, offset, n, seq, stream, seq_base=None, n_ctas=None):
         v = self.arena[offset:offset + n]
         if v.is_cuda:
             with torch.cuda.stream(stream):
@@ -120,7 +120,7 @@ class GradSync(torch.nn.Module):
     """Wrap `model` like DDP: `net = GradSync(model); loss = net(...); loss.backward(); opt.step()`."""
 
     def __init__(self, model, process_group=None, transport="auto", chunk_mb=48, n_ctas=None, wait_at_end=True,
-                 broadcast_params=True, small_numel=SMALL_NUMEL):
+                 broadcast_params=True, small_numel=SMALL_NUMEL, n_ctas_tail=None):
         super().__init__()
         self.module = model
         self.group = process_group
@@ -134,9 +134,14 @@ class GradSync(torch.nn.Module):
         cuda = self.device.type == "cuda"
         if transport == "auto":
             transport = os.environ.get("B200FM_COMM", "p2p" if cuda and 2 <= self.world <= 8 else "collective")
+        # during backward the reductions have ~2/3 of a step to hide in: a few CTAs (= SMs taken from the GEMM grids) are enough.  The
+        # chunks that only become ready at the END of backward (embedding tables) are on the critical path: they get many CTAs, no
+        # compute kernel competes for the SMs at that point (AdamW of the early chunks is HBM-bound and shares them)
         if n_ctas is None:
-            n_ctas = int(os.environ.get("B200FM_COMM_CTAS", "8"))
-        self.n_ctas = n_ctas
+            n_ctas = int(os.environ.get("B200FM_COMM_CTAS", "6"))
+        if n_ctas_tail is None:
+            n_ctas_tail = int(os.environ.get("B200FM_COMM_CTAS_TAIL", "64"))
+        self.n_ctas, self.n_ctas_tail = n_ctas, max(n_ctas, n_ctas_tail)
         self.small_numel = small_numel
         self._layout(params, int(chunk_mb * (1 << 20) // 4))
         self.transport = (_P2PTransport if transport == "p2p" else _CollectiveTransport)(self.total, self.device, process_group, n_ctas)
@@ -322,14 +327,18 @@ class GradSync(torch.nn.Module):
             self._launch(self._next_chunk)
             self._next_chunk += 1
 
-    def _launch(self, ci):
+    def _launch(self, ci, tail=False):
         start, end, _ = self.chunks[ci]
         seq = ci + 1 if self._seq_base is not None else self._step * len(self.chunks) + ci + 1
         if self.comm_stream is not None:
             ev = torch.cuda.Event()
             ev.record()                                      # everything the compute stream has produced so far
             self.comm_stream.wait_event(ev)
-            self.transport.all_reduce(start, end - start, seq, self.comm_stream, self._seq_base)
+            from . import functional as BF
+            side = BF.side_stream()                          # weight gradients issued on the captured side stream (functional._tn_gemm)
+            if side is not None:
+                self.comm_stream.wait_stream(side)
+            self.transport.all_reduce(start, end - start, seq, self.comm_stream, self._seq_base, self.n_ctas_tail if tail else self.n_ctas)
             done = torch.cuda.Event()
             done.record(self.comm_stream)
             self._events[ci] = done
@@ -357,7 +366,7 @@ class GradSync(torch.nn.Module):
                 s.expected = max(1, s.count)
         if self._sync_enabled:
             while self._next_chunk < len(self.chunks):
-                self._launch(self._next_chunk)
+                self._launch(self._next_chunk, tail=self._learned)
                 self._next_chunk += 1
             if self.reserve_sms:
                 lib.set_option("sm_reserve", 0)
