@@ -314,7 +314,12 @@ def run_b200_arm(args):
                                                             bucket_cap_mb=int(os.environ.get("B200FM_DDP_BUCKET_MB", "25")))
         else:                        # gradient arena + NVLink peer-memory all-reduce kernel (b200fm.parallel / csrc/comm.cu)
             from b200fm.parallel import GradSync
-            net = gsync = GradSync(model, transport=comm, wait_at_end=False)
+            try:
+                net = gsync = GradSync(model, transport=comm, wait_at_end=False)
+            except Exception as exc:      # e.g. CUDA IPC not permitted between the ranks' containers: NCCL on the arena chunks instead
+                print(f"[bench] GradSync transport '{comm}' unavailable ({exc!r}); falling back to 'collective'", file=sys.stderr)
+                comm = "collective"
+                net = gsync = GradSync(model, transport=comm, wait_at_end=False)
             groups = gsync.split_param_groups(groups)
     # whole-step CUDA graph (b200fm.graph): the step is captured once and replayed; B200FM_GRAPH=0 issues every launch from Python
     use_graph = os.environ.get("B200FM_GRAPH", "1") != "0" and comm != "ddp"

@@ -109,23 +109,42 @@ def run(args, ClockSampler, measured_peaks, cpu_threads, reference_tree):
     torch.cuda.synchronize()
     ms_e2e = (time.perf_counter() - t0) * 1e3 / steps
     clocks = sampler_clk.stop()
-    # weight-streaming roofline of the dominant kernel family: the M = 1..2-row GEMMs of the AR loop read every weight once per token
-    ops.PROFILE = []
-    sampler_graph = os.environ.get("B200FM_GEN_GRAPH")
-    os.environ["B200FM_GEN_GRAPH"] = "0"                               # per-launch CUDA events need Python-issued launches
-    try:
-        one(False)
-    finally:
-        if sampler_graph is None:
-            os.environ.pop("B200FM_GEN_GRAPH", None)
-        else:
-            os.environ["B200FM_GEN_GRAPH"] = sampler_graph
+    # per-step breakdown: the same schedule, one step at a time, CUDA events around every step
+    from fourm.models.generate import _deep_clone
+    state = _deep_clone(make_sample(rgb_dev))
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(len(schedule) + 1)]
+    marks[0].record()
+    for i, info in enumerate(schedule):
+        state = sampler._one_step(state, info, i, 0.0, 0.8, tok, 0, write_all=False)
+        marks[i + 1].record()
     torch.cuda.synchronize()
-    small = [(s, e, key) for s, e, _, key in ops.PROFILE if key[2] <= 8]
-    gemm_ms = sum(s.elapsed_time(e) for s, e, _ in small)
-    gemm_bytes = sum(2.0 * (k[3] * (2 if k[1] == ops.EPI_SWIGLU else 1) * k[4] + k[2] * k[4] + k[2] * k[3]) for _, _, k in small)
-    all_ms = sum(s.elapsed_time(e) for s, e, _, _ in ops.PROFILE)
-    ops.PROFILE = None
+    breakdown = {info['target_domain']: round(marks[i].elapsed_time(marks[i + 1]), 1) for i, info in enumerate(schedule)}
+    # weight-streaming roofline of the dominant kernel of the AR loop: the M = 1 linears of one decode step, launched back to back
+    # over all 24 decoder blocks (2.8 GB of distinct bf16 weights per pass >> 126 MB L2), CUDA events around the whole pass
+    from b200fm import functional as BF
+    x1 = torch.randn(1, model.dim, device=dev).to(torch.bfloat16)
+    shapes = []
+    for blk in model.decoder:
+        sa, xa, mlp = blk.self_attn, blk.cross_attn, blk.mlp
+        shapes += [(BF.weight_bf16(sa.qkv.weight), None), (BF.weight_bf16(sa.proj.weight), None), (BF.weight_bf16(xa.q.weight), None),
+                   (BF.weight_bf16(xa.proj.weight), None), (BF.weight_bf16(mlp.fc1.weight, mlp.fc3.weight), "swiglu")]
+    def gemv_pass():
+        for w, kind in shapes:
+            if kind == "swiglu":
+                ops.gemm(x1, w, epilogue=ops.EPI_SWIGLU)
+            else:
+                ops.gemm(x1, w, epilogue=ops.EPI_BF16)
+    gemv_pass()
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(3):
+        gemv_pass()
+    g1.record()
+    torch.cuda.synchronize()
+    gemm_ms = g0.elapsed_time(g1) / 3
+    gemm_bytes = sum(w.numel() * 2 for w, _ in shapes)
+    all_ms = gemm_ms
     peaks = measured_peaks()
     achieved = gemm_bytes / (gemm_ms * 1e-3) / 1e9 if gemm_ms > 0 else 0.0
     n_tok = {m: int(host_out[m].shape[1]) for m in targets}
@@ -138,10 +157,10 @@ def run(args, ClockSampler, measured_peaks, cpu_threads, reference_tree):
                             l2_policy="weights (5.6 GB bf16) exceed the 126 MB L2: every decode step streams them from HBM"),
                 e2e=dict(value=ms_e2e / 1e3, unit="s", h2d_bytes_per_step=rgb_host.numel() * 4,
                          d2h_bytes_per_step=int(sum(v.numel() * v.element_size() for v in host_out.values())), ms_per_step=ms_e2e),
-                gpu_launches=launches, tokens_generated=n_tok,
-                roofline=dict(bound="hbm", kernel="gemm_kernel<128,NT,*> at M <= 8 rows (weight streaming of the AR loop)", achieved=achieved,
+                gpu_launches=launches, tokens_generated=n_tok, ms_per_target=breakdown,
+                roofline=dict(bound="hbm", kernel="gemv_kernel<2, *> (csrc/gemv.cu): the M = 1 linears of one K/V-cached decode step over the 24 decoder blocks", achieved=achieved,
                               peak=peaks["hbm"], unit="GB/s", frac=achieved / peaks["hbm"], traffic=None, peak_source=peaks["src"],
-                              gemm_ms_small_m=gemm_ms, gemm_ms_all=all_ms),
+                              gemv_ms_per_decode_pass=gemm_ms, weight_bytes_per_pass=gemm_bytes, launches_per_pass=len(shapes)),
                 clocks=clocks)
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_sample(cpu_threads())
