@@ -122,6 +122,14 @@ int b200fm_cross_entropy(const float* logits, long long ld, const int64_t* targe
 int b200fm_cross_entropy_dyn(const float* logits, long long ld, const int64_t* targets, float* loss_rows, void* dlogits,
                              long long ldd, long long n_max, int V, const int* n_dev, void* stream);
 int b200fm_masked_mean(const float* x, const int* n_dev, long long n_max, float* mean_out, float* inv_n_out, void* stream);
+/* Fused masked-token head (fm.py:589-600 `to_logits` + F.cross_entropy): loss_rows[i] = logsumexp(h_i W^T) - (h_i W^T)[target_i] and
+ * (optional) dlogits bf16 [M, V] = softmax(h_i W^T) - onehot(target_i) WITHOUT materialising the fp32 logits: the logits tile stays in
+ * TMEM / registers; pass 1 writes per-(row, 128-column slot) (max, sum exp) partials into ws (fp32 [M, 2 * head_ce_ws_slots(V)]) and the
+ * target logit, a row reduction produces lse / loss, pass 2 recomputes the tile and writes the bf16 gradient directly.
+ * n_dev (optional): device-side row count as in gemm_bf16_dyn; rows [n, roundup64(n)) of dlogits are zero-filled.           */
+int b200fm_head_ce_ws_slots(int V);
+int b200fm_head_ce(const void* h, long long ldh, const void* W, long long ldw, const int64_t* targets, const int* n_dev, int M, int V,
+                   int K, float* ws, float* tlogit, float* lse, float* loss_rows, void* dlogits, long long ldd, void* stream);
 /* colsum_bf16: out[c] += sum_r x[r,c] (bias gradients of nn.Linear layers with bias).                                   */
 int b200fm_colsum_bf16(const void* x, long long ld, float* out, long long R, int N, void* stream);
 /* cast_f32_bf16: bf16 shadow of fp32 master weights / activations (what autocast does per call in the reference).       */

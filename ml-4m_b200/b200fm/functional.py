@@ -5,6 +5,7 @@ LayerNorm statistics are fp32 and its output is consumed as bf16; every Linear /
 operands with fp32 accumulation and produces bf16; weight gradients are produced in fp32 directly (the reference rounds
 them to bf16 first).  Master weights stay fp32 `nn.Parameter`s; their bf16 shadows are cached per parameter version.
 """
+import os
 import weakref
 
 import torch
@@ -575,15 +576,23 @@ def attention(q, k, v, mask, B, H, Nq, Nk, scale):
 # ----------------------------------------------------------------------------------------------------------------------
 # masked-token head: logits GEMM + cross-entropy, gradient kept as bf16 (softmax - onehot)
 # ----------------------------------------------------------------------------------------------------------------------
+# The masked-token head keeps the logits inside the GEMM (b200fm_head_ce: statistics epilogue, row reduction, gradient epilogue) instead
+# of writing fp32 [rows, V] logits and re-reading them in a cross-entropy kernel.  B200FM_FUSED_HEAD=0 selects the two-kernel path.
+FUSED_HEAD = os.environ.get("B200FM_FUSED_HEAD", "1") != "0"
+
+
 class LinearCrossEntropyFn(torch.autograd.Function):
     """mean_i CE(h_i W^T, t_i)  (fm.py:592-598).  h bf16 [n, D], W fp32 master [V, D], targets int64 [n]."""
 
     @staticmethod
     def forward(ctx, h, weight, targets):
         wb = weight_bf16(weight)
-        logits = ops.gemm(h, wb, epilogue=ops.EPI_F32, n_out=weight.shape[0])
-        loss_rows, dlogits = ops.cross_entropy(logits, targets, want_grad=True)
-        del logits
+        if FUSED_HEAD:
+            loss_rows, dlogits = ops.head_ce(h, wb, weight.shape[0], targets, want_grad=True)
+        else:
+            logits = ops.gemm(h, wb, epilogue=ops.EPI_F32, n_out=weight.shape[0])
+            loss_rows, dlogits = ops.cross_entropy(logits, targets, want_grad=True)
+            del logits
         ctx.save_for_backward(h, weight, dlogits)
         return loss_rows.mean()
 
@@ -606,9 +615,12 @@ class LinearCrossEntropyStaticFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, weight, targets, n_dev):
         wb = weight_bf16(weight)
-        logits = ops.gemm(h, wb, epilogue=ops.EPI_F32, n_out=weight.shape[0], dyn=n_dev)
-        loss_rows, dlogits = ops.cross_entropy_dyn(logits, targets, n_dev, want_grad=True)
-        del logits
+        if FUSED_HEAD:
+            loss_rows, dlogits = ops.head_ce(h, wb, weight.shape[0], targets, n_dev, want_grad=True)
+        else:
+            logits = ops.gemm(h, wb, epilogue=ops.EPI_F32, n_out=weight.shape[0], dyn=n_dev)
+            loss_rows, dlogits = ops.cross_entropy_dyn(logits, targets, n_dev, want_grad=True)
+            del logits
         loss, inv_n = ops.masked_mean(loss_rows, n_dev)
         ctx.save_for_backward(h, weight, dlogits, n_dev, inv_n)
         return loss

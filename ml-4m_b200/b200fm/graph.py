@@ -129,3 +129,65 @@ class GraphedTrainStep:
         self.static_in = self.static_out = None
         self.model._decoder_order_dev = None
         self.eager_left = 1
+
+
+class GraphedCall:
+    """CUDA-graph replay of an inference call with tensor inputs and tensor outputs (e.g. `VQ.tokenize` on a fixed batch shape: ~190
+    launches whose host issue time exceeds their GPU time).  One graph per input signature (shapes + dtypes); the first `eager_calls`
+    calls of a signature run eagerly (weight-limb / bf16-shadow / allocator caches fill up), the next one is captured.
+
+        tok = GraphedCall(lambda x: vq.tokenize(x))
+        tokens = tok(images)                       # clones of the graph's output buffers (clone=False: valid until the next call)
+
+    `inputs(*example)` returns the graph's static input buffers, so a loader can copy pinned host memory straight into them and call
+    `replay(*example)`.  The callee must be free of host synchronisation and must not depend on host-side state that changes between
+    calls (weights updated in place are fine: the graph reads them where they live; re-create the wrapper after replacing parameters)."""
+
+    def __init__(self, fn, eager_calls=2, clone=True):
+        self.fn, self.eager_calls, self.clone = fn, max(1, eager_calls), clone
+        self._seen, self._graphs = {}, {}
+
+    @staticmethod
+    def _key(args):
+        return tuple((tuple(a.shape), a.dtype, a.device.index) for a in args)
+
+    def _get(self, args):
+        key = self._key(args)
+        ent = self._graphs.get(key)
+        if ent is None:
+            n = self._seen.get(key, 0)
+            if n < self.eager_calls:
+                self._seen[key] = n + 1
+                return None
+            static_in = [torch.empty_like(a) for a in args]
+            for s, a in zip(static_in, args):
+                s.copy_(a)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(g, capture_error_mode="thread_local"):
+                out = self.fn(*static_in)
+            ent = self._graphs[key] = (static_in, g, out)
+        return ent
+
+    def inputs(self, *example):
+        ent = self._get(example)
+        return None if ent is None else ent[0]
+
+    def replay(self, *example):
+        static_in, g, out = self._graphs[self._key(example)]
+        g.replay()
+        return out
+
+    def __call__(self, *args):
+        ent = self._get(args)
+        if ent is None:
+            with torch.no_grad():
+                return self.fn(*args)
+        static_in, g, out = ent
+        for s, a in zip(static_in, args):
+            if s.data_ptr() != a.data_ptr():
+                s.copy_(a, non_blocking=True)
+        g.replay()
+        if not self.clone:
+            return out
+        return out.clone() if torch.is_tensor(out) else type(out)(o.clone() if torch.is_tensor(o) else o for o in out)

@@ -83,6 +83,9 @@ SIGNATURES = {
                              c_float, c_void_p],
     "b200fm_mask_images": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "b200fm_patchify_u8": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "b200fm_head_ce_ws_slots": [c_int],
+    "b200fm_head_ce": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                       c_void_p, c_ll, c_void_p],
     "b200fm_comm_flag_bytes": [],
     "b200fm_comm_alloc": [c_ll, c_void_p],
     "b200fm_comm_free": [c_void_p],

@@ -8,6 +8,8 @@ EPI_BF16, EPI_F32, EPI_RESID, EPI_SWIGLU, EPI_GELU, EPI_TANH = 0, 1, 2, 3, 4, 5
 
 
 PROFILE = None     # bench.py sets this to a list: (start_event, end_event, flops) per GEMM launch
+RECORD = None      # bench.py sets this to a list: the keyword arguments of every GEMM launch of a step (tensors kept alive), to replay
+                   # exactly that launch sequence back to back as a CUDA graph (GEMM-family throughput under the step's launch conditions)
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
@@ -78,6 +80,9 @@ def gemm(a, b, layout=LAYOUT_NT, epilogue=EPI_BF16, out=None, out1=None, bias=No
             if out1 is not None:
                 out1.zero_()
         return (out, out1) if two else out
+    if RECORD is not None:
+        RECORD.append((dict(a=a, b=b, layout=layout, epilogue=epilogue, out=out, out1=out1, bias=bias, resid=resid, alpha=alpha,
+                            alpha_dev=alpha_dev, n_out=n_out, dyn=dyn), 2.0 * M * K * (2 * N if epilogue == EPI_SWIGLU else N)))
     if PROFILE is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -271,6 +276,26 @@ def cross_entropy_dyn(logits, targets, n_dev, want_grad=True):
     lib.call("b200fm_cross_entropy_dyn", _ptr(logits), logits.stride(0), _ptr(targets), _ptr(loss), _ptr(dl), dl.stride(0) if want_grad else 0,
              n, V, n_dev.data_ptr(), _stream())
     return loss, dl
+
+
+def head_ce(h, wb, V, targets, n_dev=None, want_grad=True):
+    """Fused masked-token head: loss_rows fp32 [n] = CE(h W^T, targets) and dlogits bf16 [n, V] = softmax - onehot, the fp32 logits
+    never leave the GEMM's accumulator (b200fm_head_ce: statistics pass, row reduction, gradient pass).  h bf16 [n, D]; wb bf16
+    [>=V, D]; n_dev: optional device row count (rows behind it: loss 0, dlogits zero up to the next multiple of 64)."""
+    _need_cuda(h, wb, targets)
+    n, D = h.shape
+    assert h.dtype == torch.bfloat16 and wb.dtype == torch.bfloat16 and h.stride(1) == 1 and wb.stride(1) == 1 and wb.shape[0] >= V
+    assert targets.dtype == torch.int64 and targets.is_contiguous() and targets.numel() >= n
+    slots = 2 * ((V + 255) // 256)                                                # == b200fm_head_ce_ws_slots(V) float2 partials per row
+    ws = torch.empty(n, 2 * slots, device=h.device, dtype=torch.float32)
+    aux = torch.empty(3, n, device=h.device, dtype=torch.float32)                 # target logit, lse, loss
+    Vp = (V + 7) // 8 * 8
+    dl = torch.empty(n, Vp, device=h.device, dtype=torch.bfloat16)[:, :V] if want_grad else None
+    if RECORD is not None:
+        RECORD.append(("head_ce", n, V, D))
+    lib.call("b200fm_head_ce", _ptr(h), h.stride(0), _ptr(wb), wb.stride(0), _ptr(targets), n_dev.data_ptr() if n_dev is not None else None,
+             n, V, D, _ptr(ws), _ptr(aux[0]), _ptr(aux[1]), _ptr(aux[2]), _ptr(dl), dl.stride(0) if want_grad else 0, _stream())
+    return aux[2], dl
 
 
 def masked_mean(x, n_dev):

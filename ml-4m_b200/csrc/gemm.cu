@@ -49,7 +49,13 @@ struct GemmArgs {
     // The launch (grid, tensor maps, split-K plan) is sized for the upper bounds; tiles / K blocks beyond the device value are skipped.
     const int* dyn_dev;
     int dyn_mode;
+    // fused masked-token head (EPI_CE_STATS / EPI_CE_GRAD, fm.py:589-600): the logits tile never leaves the SM
+    const long long* targets;     // int64 [M]
+    const float* lse;             // EPI_CE_GRAD: fp32 [M] log-sum-exp of every row
 };
+
+constexpr int EPI_CE_STATS = 6;   // out0 = float2 ws[M][ld0] per-(row, column slot) (max, sum exp(l - max)); out1 = fp32 tlogit[M] (target logit)
+constexpr int EPI_CE_GRAD = 7;    // out0 = bf16 [M, ld0] softmax(l) - onehot(target), rows [M_dyn, roundup64(M_dyn)) zero-filled
 
 // CTA2: a CTA pair (cluster of 2, one TPC) computes a 256 x BN tile with tcgen05.mma.cta_group::2 -- each CTA stages its own
 // 128 rows of A and only HALF of the B tile (BN/2 rows), so the per-SM smem fill per MMA-cycle drops by a third.
@@ -317,6 +323,61 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 const float alpha = args.alpha * (args.alpha_dev ? __ldg(args.alpha_dev) : 1.0f);
                 constexpr int kChunks = BN / 64;                 // 32-column chunks per epilogue warp
                 const int c0 = half * kChunks;
+                if constexpr (EPI == EPI_CE_STATS || EPI == EPI_CE_GRAD) {
+                    // ---- fused cross-entropy head: thread = row holds its logits of this tile in registers, 32 columns at a time ----
+                    constexpr float kLog2e = 1.4426950408889634f;
+                    const int tgt = row_ok ? static_cast<int>(args.targets[row]) : -1;
+                    if constexpr (EPI == EPI_CE_STATS) {
+                        float run_m = -INFINITY, run_s = 0.f;
+#pragma unroll 1
+                        for (int c = c0; c < c0 + kChunks; ++c) {
+                            const int n = n0 + c * 32;
+                            if (n >= args.N) break;               // warp-uniform
+                            uint32_t r[32];
+                            tmem_ld_x32(t_acc + c * 32, r);
+                            tmem_ld_wait();
+                            float cm = -INFINITY;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (n + j < args.N) cm = fmaxf(cm, __uint_as_float(r[j]));
+                            const float m_new = fmaxf(run_m, cm);
+                            float cs = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (n + j < args.N) cs += exp2f((__uint_as_float(r[j]) - m_new) * kLog2e);
+                            run_s = run_s * exp2f((run_m - m_new) * kLog2e) + cs;      // run_m = -inf on the first chunk: factor 0
+                            run_m = m_new;
+                            if (tgt >= n && tgt < n + 32) {
+                                float tl = 0.f;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) if (n + j == tgt) tl = __uint_as_float(r[j]);
+                                reinterpret_cast<float*>(args.out1)[row] = tl;
+                            }
+                        }
+                        if (row_ok && n0 + c0 * 32 < args.N)
+                            reinterpret_cast<float2*>(args.out0)[static_cast<long long>(row) * args.ld0 + n_blk * 2 + half] = make_float2(run_m, run_s);
+                    } else {
+                        const float lse2 = row_ok ? args.lse[row] * kLog2e : 0.f;
+                        const int m_fill = min((M_ + 63) & ~63, args.M);          // rows [M_, m_fill) are written as zeros (see header)
+#pragma unroll 1
+                        for (int c = c0; c < c0 + kChunks; ++c) {
+                            const int n = n0 + c * 32;
+                            if (n >= args.N) break;
+                            uint32_t r[32];
+                            tmem_ld_x32(t_acc + c * 32, r);
+                            tmem_ld_wait();
+                            uint32_t p[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                float v0 = 0.f, v1 = 0.f;
+                                if (row_ok) {
+                                    v0 = exp2f(fmaf(__uint_as_float(r[2 * j]), kLog2e, -lse2)) - (n + 2 * j == tgt ? 1.0f : 0.0f);
+                                    v1 = exp2f(fmaf(__uint_as_float(r[2 * j + 1]), kLog2e, -lse2)) - (n + 2 * j + 1 == tgt ? 1.0f : 0.0f);
+                                }
+                                p[j] = pack_bf16x2(v0, v1);
+                            }
+                            stage_store_bf16(stg_u, lane, p, reinterpret_cast<__nv_bfloat16*>(args.out0), args.ld0, row_base, n, m_fill, args.N, (args.ld0 & 7) == 0);
+                        }
+                    }
+                } else
 #pragma unroll 1
                 for (int c = c0; c < c0 + kChunks; ++c) {
                     uint32_t r[32];
@@ -462,16 +523,30 @@ extern "C" int b200fm_gemm_bf16(int layout, int epilogue, int M, int N, int K, c
                                 stream_);
 }
 
+static int gemm_impl(int layout, int epilogue, int M, int N, int K, const void* A, long long lda, const void* B,
+                     long long ldb, void* out0, long long ld0, void* out1, long long ld1, const float* bias,
+                     const float* resid, long long ldr, float alpha, const float* alpha_dev, const int* dyn_dev,
+                     int dyn_mode, const long long* targets, const float* lse, void* stream_);
+
 extern "C" int b200fm_gemm_bf16_dyn(int layout, int epilogue, int M, int N, int K, const void* A, long long lda, const void* B,
                                     long long ldb, void* out0, long long ld0, void* out1, long long ld1, const float* bias,
                                     const float* resid, long long ldr, float alpha, const float* alpha_dev, const int* dyn_dev,
                                     int dyn_mode, void* stream_) {
+    B200FM_CHECK(epilogue >= 0 && epilogue <= 5, "gemm: bad epilogue %d", epilogue);
+    return gemm_impl(layout, epilogue, M, N, K, A, lda, B, ldb, out0, ld0, out1, ld1, bias, resid, ldr, alpha, alpha_dev, dyn_dev, dyn_mode,
+                     nullptr, nullptr, stream_);
+}
+
+static int gemm_impl(int layout, int epilogue, int M, int N, int K, const void* A, long long lda, const void* B,
+                     long long ldb, void* out0, long long ld0, void* out1, long long ld1, const float* bias,
+                     const float* resid, long long ldr, float alpha, const float* alpha_dev, const int* dyn_dev,
+                     int dyn_mode, const long long* targets, const float* lse, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     B200FM_CHECK(dyn_dev == nullptr || (dyn_mode == 1 && layout != LAYOUT_TN) || (dyn_mode == 2 && layout == LAYOUT_TN && epilogue == B200FM_EPI_F32),
                  "gemm: dyn_mode %d does not fit layout %d / epilogue %d (1: rows of NT/NN, 2: contraction length of TN + EPI_F32)", dyn_mode, layout, epilogue);
     B200FM_CHECK(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
     B200FM_CHECK(layout >= 0 && layout <= 2, "gemm: bad layout %d", layout);
-    B200FM_CHECK(epilogue >= 0 && epilogue <= 5, "gemm: bad epilogue %d", epilogue);
+    B200FM_CHECK(epilogue >= 0 && epilogue <= 7, "gemm: bad epilogue %d", epilogue);
     const int act = (epilogue == B200FM_EPI_TANH) ? 1 : 0;
     if (epilogue == B200FM_EPI_TANH) epilogue = B200FM_EPI_GELU;
     B200FM_CHECK(A && B && out0, "gemm: null pointer");
@@ -490,6 +565,7 @@ extern "C" int b200fm_gemm_bf16_dyn(int layout, int epilogue, int M, int N, int 
     a.out0 = out0; a.ld0 = ld0; a.out1 = out1; a.ld1 = ld1; a.bias = bias; a.resid = resid; a.ldr = ldr;
     a.n_half = N; a.alpha = alpha; a.alpha_dev = alpha_dev; a.act = act;
     a.dyn_dev = dyn_dev; a.dyn_mode = dyn_dev ? dyn_mode : 0;
+    a.targets = targets; a.lse = lse;
     a.num_m_blocks = (M + kBM - 1) / kBM;
 
     // tile width: 256 when there is enough N to fill it and enough tiles to fill the machine, else 128
@@ -499,6 +575,9 @@ extern "C" int b200fm_gemm_bf16_dyn(int layout, int epilogue, int M, int N, int 
     if (epilogue == B200FM_EPI_SWIGLU) {
         BN = 256;                                   // 128 a-columns + 128 b-columns per tile
         a.num_n_blocks = (N + 127) / 128;
+    } else if (epilogue == EPI_CE_STATS || epilogue == EPI_CE_GRAD) {
+        BN = 256;                                   // fixed: the statistics workspace is indexed by (n block, column half)
+        a.num_n_blocks = (N + 255) / 256;
     } else {
         const int tiles256 = a.num_m_blocks * ((N + 255) / 256);
         const int num_kb = (K + kBK - 1) / kBK;
@@ -558,6 +637,8 @@ extern "C" int b200fm_gemm_bf16_dyn(int layout, int epilogue, int M, int N, int 
     B200FM_GEMM_CASE(128, LAYOUT_NT, B200FM_EPI_RESID)
     B200FM_GEMM_CASE(256, LAYOUT_NT, B200FM_EPI_SWIGLU)
     B200FM_GEMM_CASE(256, LAYOUT_NT, B200FM_EPI_GELU)
+    B200FM_GEMM_CASE(256, LAYOUT_NT, EPI_CE_STATS)
+    B200FM_GEMM_CASE(256, LAYOUT_NT, EPI_CE_GRAD)
     B200FM_GEMM_CASE(128, LAYOUT_NT, B200FM_EPI_GELU)
     B200FM_GEMM_CASE(256, LAYOUT_NN, B200FM_EPI_BF16)
     B200FM_GEMM_CASE(128, LAYOUT_NN, B200FM_EPI_BF16)
@@ -569,4 +650,54 @@ extern "C" int b200fm_gemm_bf16_dyn(int layout, int epilogue, int M, int N, int 
     B200FM_GEMM_CASE(128, LAYOUT_TN, B200FM_EPI_BF16)
 #undef B200FM_GEMM_CASE
     B200FM_CHECK(false, "gemm: unsupported combination layout=%d epilogue=%d BN=%d", layout, epilogue, BN);
+}
+
+
+// ---- fused masked-token head: logits GEMM with the cross-entropy in its epilogue (no [rows, V] fp32 logits tensor) -----------------
+namespace b200fm {
+// one warp per row: combine the per-(n block, column half) partials into the row's log-sum-exp and its loss
+__global__ void __launch_bounds__(256)
+ce_reduce_kernel(const float2* __restrict__ ws, int slots, int V, const float* __restrict__ tlogit, const int* __restrict__ n_dev, long long M,
+                 float* __restrict__ lse, float* __restrict__ loss_rows) {
+    pdl_enter();
+    const long long row = (blockIdx.x * 256ll + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const long long n = n_dev ? min((long long)max(0, __ldg(n_dev)), M) : M;
+    if (row >= n) { if (lane == 0) { loss_rows[row] = 0.f; lse[row] = 0.f; } return; }
+    float m = -INFINITY;
+    for (int s = lane; s < slots; s += 32)
+        if ((s >> 1) * 256 + (s & 1) * 128 < V) m = fmaxf(m, ws[row * slots + s].x);
+    m = warp_max(m);
+    float acc = 0.f;
+    for (int s = lane; s < slots; s += 32)
+        if ((s >> 1) * 256 + (s & 1) * 128 < V) { const float2 p = ws[row * slots + s]; acc += p.y * __expf(p.x - m); }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        const float l = m + logf(acc);
+        lse[row] = l;
+        loss_rows[row] = l - tlogit[row];
+    }
+}
+}  // namespace b200fm
+
+extern "C" int b200fm_head_ce_ws_slots(int V) { return 2 * ((V + 255) / 256); }
+
+extern "C" int b200fm_head_ce(const void* h, long long ldh, const void* W, long long ldw, const int64_t* targets, const int* n_dev, int M,
+                              int V, int K, float* ws, float* tlogit, float* lse, float* loss_rows, void* dlogits, long long ldd,
+                              void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (M == 0) return 0;
+    B200FM_CHECK(h && W && targets && ws && tlogit && lse && loss_rows, "head_ce: null pointer");
+    B200FM_CHECK(dlogits == nullptr || (ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(dlogits) & 15) == 0), "head_ce: dlogits must be 16 B aligned with ldd %% 8 == 0");
+    const int slots = b200fm_head_ce_ws_slots(V);
+    int rc = gemm_impl(LAYOUT_NT, EPI_CE_STATS, M, V, K, h, ldh, W, ldw, ws, slots, tlogit, 0, nullptr, nullptr, 0, 1.0f, nullptr, n_dev, n_dev ? 1 : 0,
+                       reinterpret_cast<const long long*>(targets), nullptr, stream_);
+    if (rc) return rc;
+    B200FM_LAUNCH(ce_reduce_kernel, dim3((unsigned)((M * 32ll + 255) / 256)), dim3(256), 0, stream, 1, reinterpret_cast<const float2*>(ws), slots, V, tlogit, n_dev,
+                  (long long)M, lse, loss_rows);
+    B200FM_CUDA(cudaGetLastError());
+    if (dlogits == nullptr) return 0;
+    return gemm_impl(LAYOUT_NT, EPI_CE_GRAD, M, V, K, h, ldh, W, ldw, dlogits, ldd, nullptr, 0, nullptr, nullptr, 0, 1.0f, nullptr, n_dev, n_dev ? 1 : 0,
+                     reinterpret_cast<const long long*>(targets), lse, stream_);
 }

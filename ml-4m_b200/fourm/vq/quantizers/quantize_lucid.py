@@ -194,7 +194,7 @@ class VectorQuantize(nn.Module):
         if self.norm_latents:
             z = l2norm(z)
         quantize, embed_ind = self._codebook(z)
-        loss = torch.tensor([0.], device=x.device, requires_grad=self.training)
+        loss = torch.zeros(1, device=x.device, requires_grad=self.training)   # a fill kernel: torch.tensor([0.], device=...) is a blocking pageable H2D copy
         if self.training:
             quantize = z + (quantize - z).detach()                               # straight-through (reference :532)
             if self.commitment_weight > 0:

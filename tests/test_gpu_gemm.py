@@ -156,3 +156,34 @@ def test_small_m_weight_streaming_kernel(M):
     finally:
         lib.set_option("gemv", 1)
     torch.testing.assert_close(gate.float(), gate2.float(), rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("n,V,D", [(1, 1000, 384), (130, 1000, 384), (517, 16384, 768), (3000, 30000, 768), (257, 133, 64), (4096, 8192, 1024)])
+def test_fused_head_cross_entropy(n, V, D):
+    """b200fm_head_ce (logits stay in the accumulator: statistics epilogue -> row reduction -> gradient epilogue) vs torch fp32
+    cross-entropy on the same bf16 operands, and vs the two-kernel path (fp32 logits GEMM + cross-entropy kernel).  Covers V not a
+    multiple of the 256-column tile / 128-column half and a device-side row count (rows behind it: loss 0, gradient rows zero up to
+    the next multiple of 64, later rows untouched)."""
+    from b200fm import ops
+    g = torch.Generator(device="cuda").manual_seed(n + V)
+    h = torch.randn(n, D, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(V, D, device="cuda", generator=g) * (3.0 / D ** 0.5)).bfloat16()       # logits ~ N(0, 9): peaked softmax rows
+    t = torch.randint(0, V, (n,), device="cuda", generator=g)
+    logits = h.float() @ w.float().t()
+    ref_loss = torch.nn.functional.cross_entropy(logits, t, reduction="none")
+    ref_grad = torch.softmax(logits, -1)
+    ref_grad[torch.arange(n), t] -= 1.0
+    loss, dl = ops.head_ce(h, w, V, t)
+    torch.testing.assert_close(loss, ref_loss, rtol=1e-4, atol=2e-4)
+    torch.testing.assert_close(dl.float(), ref_grad, rtol=1e-2, atol=2e-4)
+    l2, d2 = ops.cross_entropy(ops.gemm(h, w, epilogue=ops.EPI_F32), t)
+    torch.testing.assert_close(loss, l2, rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(dl.float(), d2.float(), rtol=1e-2, atol=1e-5)
+    for m in sorted({0, 1, n // 2, n}):
+        nd = torch.tensor([m], dtype=torch.int32, device="cuda")
+        loss, dl = ops.head_ce(h, w, V, t, nd)
+        torch.testing.assert_close(loss[:m], ref_loss[:m], rtol=1e-4, atol=2e-4)
+        assert float(loss[m:].abs().sum()) == 0.0
+        torch.testing.assert_close(dl[:m].float(), ref_grad[:m], rtol=1e-2, atol=2e-4)
+        m64 = min((m + 63) // 64 * 64, n)
+        assert float(dl[m:m64].float().abs().sum()) == 0.0

@@ -254,7 +254,7 @@ import fourm.utils as utils, fourm.models.generate as gen
 from fourm.data.modality_info import MODALITY_INFO
 ov, ref = "{root}/ml-4m_b200/", "/root/reference/"
 assert fm.__file__.startswith(ov) and fu.__file__.startswith(ov) and ee.__file__.startswith(ov) and vq.__file__.startswith(ov)
-assert utils.__file__.startswith(ref) and gen.__file__.startswith(ref)
+assert utils.__file__.startswith(ref) and gen.__file__.startswith(ov)      # generation is an overlay module since round 2
 mods = ["rgb@224", "caption", "tok_depth@224"]
 mk = lambda m, side: MODALITY_INFO[m][side]() if MODALITY_INFO[m]["type"] != "img" else MODALITY_INFO[m][side](patch_size=16, image_size=224)
 enc = {{m: mk(m, "encoder_embedding") for m in mods}}
