@@ -367,7 +367,7 @@ def run_b200_arm(args):
     loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_evt = [torch.cuda.Event() for _ in range(2)]
 
-    def timed(n_steps, e2e, step=step):
+    def timed(n_steps, e2e, step=step, host_batches=host_batches):
         calls0 = lib.CALLS["n"]
         sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -419,7 +419,31 @@ def run_b200_arm(args):
         sampler.start()
     ms, launches, loss_val = timed(args.steps, e2e=False)
     cpu_issue_ms = timed.cpu_ms
-    ms_e2e, _, loss_e2e = timed(args.steps, e2e=True)
+    # end to end.  Wire format of the RGB modality: "uint8" (default) ships the raw 8-bit pixels and applies the loader's ToTensor +
+    # Normalize inside the patchify kernel (fourm/models/encoder_embeddings.py, b200fm.masking): 22 MB per step over PCIe instead of the
+    # 80 MB of the reference's fp32 wire format, which is measured as well (`e2e_fp32_wire`).  Same step otherwise.
+    e2e_wire = os.environ.get("B200FM_E2E_WIRE", "uint8")
+    ms_e2e_f32, _, loss_e2e = timed(args.steps, e2e=True)
+    ms_e2e, h2d_e2e = ms_e2e_f32, h2d
+    if e2e_wire == "uint8":
+        gu = torch.Generator().manual_seed(99 + rank)
+        hb_u8 = []
+        for hb in host_batches:
+            nb = {m: dict(dd) for m, dd in hb.items()}
+            shp = hb["rgb@224"]["tensor"].shape
+            nb["rgb@224"]["tensor"] = torch.randint(0, 256, shp, dtype=torch.uint8, generator=gu).pin_memory()
+            hb_u8.append(nb)
+        step_u8 = eager_step
+        if use_graph:
+            gstep_u8 = GraphedTrainStep(net, opt, n_tok, n_tok, loss_type="mod")
+            step_u8 = gstep_u8
+        dev_u8 = {m: {k: v.to(dev) for k, v in dd.items()} for m, dd in hb_u8[0].items()}
+        for _ in range(4):                                    # 2 eager calls + the capture + 1 replay
+            step_u8(dev_u8)
+        ms_e2e, _, loss_e2e = timed(args.steps, e2e=True, step=step_u8, host_batches=hb_u8)
+        h2d_e2e = batch_bytes(hb_u8[0])
+        if use_graph:
+            gstep_u8.release()
     clocks = sampler.stop() if rank == 0 else None
     ms_nocomm, params_equal = None, None
     if world > 1:
@@ -475,7 +499,8 @@ def run_b200_arm(args):
         gg = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gg, capture_error_mode="thread_local"):
             for kw, _ in recs:
-                ops.gemm(**kw)
+                kw = dict(kw)
+                getattr(ops, kw.pop("_fn", "gemm"))(**kw)
         for _ in range(2):
             gg.replay()
         torch.cuda.synchronize()
@@ -513,7 +538,10 @@ def run_b200_arm(args):
                                 model=args.model, global_batch=B * world, per_gpu_batch=B, seq_len=2 * n_tok, encoder_tokens=n_tok,
                                 decoder_tokens=n_tok, parallelism=f"dp{world}", params_m=round(n_params / 1e6, 1),
                                 l2_policy="per-step working set (activations+grads > 2 GB) exceeds the 126 MB L2; two alternating input batches"),
-                    e2e=dict(value=tps_e2e, unit="tokens/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
+                    e2e=dict(value=tps_e2e, unit="tokens/s", h2d_bytes_per_step=h2d_e2e, d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps,
+                             rgb_wire_format=("uint8 pixels, normalised on the GPU" if e2e_wire == "uint8" else "fp32, normalised by the loader")),
+                    e2e_fp32_wire=dict(value=tokens_per_step / (ms_e2e_f32 / args.steps / 1e3), unit="tokens/s", h2d_bytes_per_step=h2d,
+                                       d2h_bytes_per_step=4, ms_per_step=ms_e2e_f32 / args.steps),
                     gpu_launches=launches, loss=loss_val, host_issue_ms_per_step=cpu_issue_ms,
                     launch_mode=("cuda-graph replay of the whole step (b200fm.graph.GraphedTrainStep)" if use_graph else "python-issued launches"),
                     model_tflops_per_gpu=model_tflops / world,

@@ -39,9 +39,10 @@ int b200fm_abi_version(void);
 int b200fm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin);
 
 /* Runtime options (defaults from the environment variable B200FM_<NAME upper-case>): "pdl" (1: programmatic dependent launch),
- * "gemm_cta_pairs" (1: cta_group::2 GEMM tiles), "ln_bwd_v2" (0: experimental LayerNorm-backward variant), "sm_reserve" (0: number
+ * "gemm_cta_pairs" (1: cta_group::2 GEMM tiles), "ln_bwd_v2" (LayerNorm-backward variant 0..3; 3 = gamma in shared memory, 2 CTAs per SM), "ln_fwd_v2" (1: LayerNorm forward with gamma / beta in shared memory, 4 CTAs per SM), "sm_reserve" (0: number
  * of SMs the persistent GEMM grids leave free, for a concurrent gradient all-reduce kernel), "gemv" (1: NT problems with <= 8 rows --
- * the linears of the K/V-cached decode loop -- run on an HBM-bound weight-streaming kernel instead of a tcgen05 tile).  Changing an
+ * the linears of the K/V-cached decode loop -- run on an HBM-bound weight-streaming kernel instead of a tcgen05 tile), "gemv_prefetch"
+ * (1: that kernel pulls its weight rows into L2 before it waits for the preceding kernel of the stream).  Changing an
  * option affects launches issued afterwards; meant for A/B measurements inside one process.                          */
 int b200fm_set_option(const char* name, int value);
 int b200fm_get_option(const char* name, int* value);
@@ -234,6 +235,10 @@ int b200fm_gather_i64(const int64_t* src, const int32_t* rows, int64_t* out, lon
 int b200fm_gather_rows_bf16_dyn(const void* src, const int32_t* rows, void* out, long long n, int D, const int* n_dev, void* stream);
 int b200fm_gather_i64_dyn(const int64_t* src, const int32_t* rows, int64_t* out, long long n, const int* n_dev, void* stream);
 int b200fm_scatter_rows_bf16_dyn(const void* src, const int32_t* rows, void* dst, long long n, int D, const int* n_dev, void* stream);
+/* K/V cache append of the decode loop (replaces the growing torch.cat of generate.py's per-token forward): cache bf16 [B, L, row_w];
+ * cache[b, *pos_dev, col0 : col0 + width] = src[b, 0 : width] (src bf16 [B, >= width], row stride ld_src).  *pos_dev int64 on the device. */
+int b200fm_kv_append(const void* src, long long ld_src, void* cache, long long L, long long row_w, const int64_t* pos_dev, int B,
+                     int width, int col0, void* stream);
 /* dst bf16 [*, D] row rows[i] = src bf16 [n, D] row i (backward of gather_rows_bf16; distinct destination rows).           */
 int b200fm_scatter_rows_bf16(const void* src, const int32_t* rows, void* dst, long long n, int D, void* stream);
 /* dst fp32 [*, D] rows[i] += src bf16 [n, D] row i (distinct destination rows).                                             */

@@ -60,9 +60,15 @@ def _lin(lin, x_bf16):
     return ops.gemm(x_bf16, BF.weight_bf16(lin.weight), epilogue=ops.EPI_BF16, bias=lin.bias, n_out=lin.weight.shape[0])
 
 
-def _gated_mlp(mlp, h):
+def _lin_resid(lin, x_bf16, resid):
+    """resid (fp32) + bf16(lin(x)): the residual add as the GEMM's epilogue (no cast / add kernels between the linears, so the whole
+    decode step stays one chain of programmatically dependent launches)."""
+    return ops.gemm(x_bf16, BF.weight_bf16(lin.weight), epilogue=ops.EPI_RESID, bias=lin.bias, resid=resid, n_out=lin.weight.shape[0])
+
+
+def _gated_mlp(mlp, h, resid=None):
     """fc2(silu(fc1 h) * fc3 h) on bf16 rows, with the zero-padded operands the training path uses for widths that are not
-    multiples of 8 (4M-L 2730, 4M-XL 5461)."""
+    multiples of 8 (4M-L 2730, 4M-XL 5461).  resid: fp32 rows to add the result to (returns fp32)."""
     w1, w3, w2 = mlp.fc1.weight, mlp.fc3.weight, mlp.fc2.weight
     H = w1.shape[0]
     Hp = (H + 7) // 8 * 8
@@ -73,6 +79,8 @@ def _gated_mlp(mlp, h):
         bias13[Hp:Hp + H] = mlp.fc3.bias
     _, g = ops.gemm(h, BF.weight_bf16(w1, w3), epilogue=ops.EPI_SWIGLU, bias=bias13)
     w2b = BF.weight_bf16(w2) if Hp == H else BF.weight_bf16_padk(w2, Hp)
+    if resid is not None:
+        return ops.gemm(g, w2b, epilogue=ops.EPI_RESID, bias=mlp.fc2.bias, resid=resid, n_out=w2.shape[0])
     return ops.gemm(g, w2b, epilogue=ops.EPI_BF16, bias=mlp.fc2.bias, n_out=w2.shape[0])
 
 
@@ -120,22 +128,26 @@ class CachedDecoder:
             if hasattr(sa, "q_norm"):
                 q, k = BF.head_norm(q, H, sa.q_norm), BF.head_norm(k, H, sa.k_norm)
             cache = self.kv_self[li]
-            cache.index_copy_(1, self.pos_dev, torch.cat([k, qkv[:, 2 * D:]], dim=1)[:, None, :])
+            if hasattr(sa, "q_norm"):                                             # normalised keys are their own tensor
+                ops.kv_append(k, cache, self.pos_dev, 0)
+                ops.kv_append(qkv[:, 2 * D:], cache, self.pos_dev, D)
+            else:
+                ops.kv_append(qkv[:, D:], cache, self.pos_dev, 0)                 # k | v are adjacent in the qkv row
             c2 = cache.view(B * L, 2 * D)
             o, _ = ops.attention_fwd(q, c2[:, :D], c2[:, D:], B, H, 1, L, self.sa_mask, sa.scale)
-            x = x + _lin(sa.proj, o).float()
+            x = _lin_resid(sa.proj, o, x)                                         # x + proj(o): the add is the GEMM's epilogue
             q = _lin(xa.q, _ln(blk.query_norm, x))
             if hasattr(xa, "q_norm"):
                 q = BF.head_norm(q, H, xa.q_norm)
             kv = self.kv_ctx[li]
             o, _ = ops.attention_fwd(q, kv[:, :D], kv[:, D:], B, H, 1, self.N, self.enc_mask, xa.scale)
-            x = x + _lin(xa.proj, o).float()
+            x = _lin_resid(xa.proj, o, x)
             h = _ln(blk.norm2, x)
             mlp = blk.mlp
             if hasattr(mlp, "fc3"):
-                x = x + _gated_mlp(mlp, h).float()
+                x = _gated_mlp(mlp, h, resid=x)
             else:
-                x = x + _lin(mlp.fc2, BF.MlpActFn.apply(h, mlp.fc1.weight, mlp.fc1.bias, "gelu")).float()
+                x = _lin_resid(mlp.fc2, BF.MlpActFn.apply(h, mlp.fc1.weight, mlp.fc1.bias, "gelu"), x)
         self.pos_dev.add_(1)
         return _ln(self.model.decoder_norm, x)
 

@@ -83,6 +83,7 @@ SIGNATURES = {
                              c_float, c_void_p],
     "b200fm_mask_images": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "b200fm_patchify_u8": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "b200fm_kv_append": [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_int, c_int, c_int, c_void_p],
     "b200fm_head_ce_ws_slots": [c_int],
     "b200fm_head_ce": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                        c_void_p, c_ll, c_void_p],
@@ -151,7 +152,7 @@ def call(name, *args):
 
 
 def set_option(name: str, value: int) -> None:
-    """Runtime option of the kernel library (include/b200fm.h: "pdl", "gemm_cta_pairs", "ln_bwd_v2", "sm_reserve", "gemv"); for in-process A/B measurements."""
+    """Runtime option of the kernel library (include/b200fm.h: "pdl", "gemm_cta_pairs", "ln_bwd_v2", "sm_reserve", "gemv", "gemv_prefetch", "ln_fwd_v2"); for in-process A/B measurements."""
     check(load().b200fm_set_option(name.encode(), int(value)), "b200fm_set_option")
 
 

@@ -278,6 +278,16 @@ def cross_entropy_dyn(logits, targets, n_dev, want_grad=True):
     return loss, dl
 
 
+def kv_append(src, cache, pos_dev, col0=0):
+    """cache bf16 [B, L, W]; cache[b, pos, col0 : col0 + src.shape[1]] = src[b] with pos = *pos_dev (device int64 [1])."""
+    _need_cuda(src, cache, pos_dev)
+    B, L, W = cache.shape
+    assert src.dtype == torch.bfloat16 and cache.dtype == torch.bfloat16 and cache.is_contiguous() and src.stride(1) == 1 and src.shape[0] == B
+    assert pos_dev.dtype == torch.int64
+    lib.call("b200fm_kv_append", _ptr(src), src.stride(0), _ptr(cache), L, W, _ptr(pos_dev), B, src.shape[1], col0, _stream())
+    return cache
+
+
 def head_ce(h, wb, V, targets, n_dev=None, want_grad=True):
     """Fused masked-token head: loss_rows fp32 [n] = CE(h W^T, targets) and dlogits bf16 [n, V] = softmax - onehot, the fp32 logits
     never leave the GEMM's accumulator (b200fm_head_ce: statistics pass, row reduction, gradient pass).  h bf16 [n, D]; wb bf16
@@ -291,10 +301,16 @@ def head_ce(h, wb, V, targets, n_dev=None, want_grad=True):
     aux = torch.empty(3, n, device=h.device, dtype=torch.float32)                 # target logit, lse, loss
     Vp = (V + 7) // 8 * 8
     dl = torch.empty(n, Vp, device=h.device, dtype=torch.bfloat16)[:, :V] if want_grad else None
-    if RECORD is not None:
-        RECORD.append(("head_ce", n, V, D))
+    if RECORD is not None:        # two tcgen05 GEMM passes over the same operands (statistics, gradient)
+        RECORD.append((dict(_fn="head_ce", h=h, wb=wb, V=V, targets=targets, n_dev=n_dev, want_grad=want_grad), (4.0 if want_grad else 2.0) * n * V * D))
+    if PROFILE is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     lib.call("b200fm_head_ce", _ptr(h), h.stride(0), _ptr(wb), wb.stride(0), _ptr(targets), n_dev.data_ptr() if n_dev is not None else None,
              n, V, D, _ptr(ws), _ptr(aux[0]), _ptr(aux[1]), _ptr(aux[2]), _ptr(dl), dl.stride(0) if want_grad else 0, _stream())
+    if PROFILE is not None:
+        ev1.record()
+        PROFILE.append((ev0, ev1, (4.0 if want_grad else 2.0) * n * V * D, ("head_ce", n, V, D)))
     return aux[2], dl
 
 

@@ -490,6 +490,38 @@ extern "C" int b200fm_gather_rows_bf16_dyn(const void* src, const int32_t* rows,
     return 0;
 }
 
+// K/V cache append of the autoregressive decode loop: cache[b, *pos, col0 : col0 + width] = src[b, 0 : width] (bf16), the position read
+// from device memory so the launch can sit in a CUDA graph.  One CTA per sequence; 16-byte moves when the geometry allows.
+namespace b200fm {
+__global__ void __launch_bounds__(256)
+kv_append_kernel(const __nv_bfloat16* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ cache, long long L, long long row_w,
+                 const long long* __restrict__ pos_dev, int width, int col0, int vec) {
+    pdl_enter();
+    const long long pos = __ldg(pos_dev);
+    if (pos < 0 || pos >= L) return;
+    const __nv_bfloat16* s = src + blockIdx.x * ld_src;
+    __nv_bfloat16* d = cache + (blockIdx.x * L + pos) * row_w + col0;
+    if (vec) {
+        for (int i = threadIdx.x; i < width / 8; i += blockDim.x) reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(s)[i];
+    } else {
+        for (int i = threadIdx.x; i < width; i += blockDim.x) d[i] = s[i];
+    }
+}
+}  // namespace b200fm
+
+extern "C" int b200fm_kv_append(const void* src, long long ld_src, void* cache, long long L, long long row_w, const int64_t* pos_dev, int B,
+                                int width, int col0, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (B == 0 || width == 0) return 0;
+    B200FM_CHECK(src && cache && pos_dev && col0 >= 0 && col0 + width <= row_w, "kv_append: bad arguments");
+    const int vec = (width % 8 == 0 && col0 % 8 == 0 && row_w % 8 == 0 && ld_src % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(cache) & 15) == 0) ? 1 : 0;
+    B200FM_LAUNCH(kv_append_kernel, dim3(B), dim3(256), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(src), ld_src,
+                  reinterpret_cast<__nv_bfloat16*>(cache), L, row_w, reinterpret_cast<const long long*>(pos_dev), width, col0, vec);
+    B200FM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int b200fm_gather_i64(const int64_t* src, const int32_t* rows, int64_t* out, long long n, void* stream_) {
     return b200fm_gather_i64_dyn(src, rows, out, n, nullptr, stream_);
 }

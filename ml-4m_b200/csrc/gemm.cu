@@ -510,7 +510,8 @@ static bool use_cta_pairs() { return option(kOptGemmCtaPairs) != 0; }
 // gemv.cu: weight-streaming kernel for M <= 8 rows (autoregressive decode)
 bool gemv_applicable(int layout, int epilogue, int M, int N, int K, long long lda, long long ldb);
 int launch_gemv(int epilogue, int M, int N, int K, const void* A, long long lda, const void* W, long long ldb, void* out0, long long ld0,
-                void* out1, long long ld1, const float* bias, float alpha, const float* alpha_dev, cudaStream_t stream);
+                void* out1, long long ld1, const float* bias, const float* resid, long long ldr, float alpha, const float* alpha_dev,
+                cudaStream_t stream);
 
 }  // namespace b200fm
 
@@ -558,7 +559,7 @@ static int gemm_impl(int layout, int epilogue, int M, int N, int K, const void* 
     if (epilogue == B200FM_EPI_RESID) B200FM_CHECK(resid != nullptr, "gemm: residual epilogue needs resid");
     if (epilogue == B200FM_EPI_SWIGLU) B200FM_CHECK(layout == LAYOUT_NT && (N % 8) == 0, "gemm: swiglu epilogue needs the NT layout and N %% 8 == 0");
     if (dyn_dev == nullptr && option(kOptGemv) != 0 && gemv_applicable(layout, epilogue, M, N, K, lda, ldb))
-        return launch_gemv(epilogue, M, N, K, A, lda, B, ldb, out0, ld0, out1, ld1, bias, alpha, alpha_dev, stream);
+        return launch_gemv(epilogue, M, N, K, A, lda, B, ldb, out0, ld0, out1, ld1, bias, resid, ldr, alpha, alpha_dev, stream);
 
     GemmArgs a;
     a.M = M; a.N = N; a.K = K;

@@ -3,7 +3,7 @@
 // tcgen05 tile wastes > 98 % of its MMA rows here and, worse, only N / BN CTAs (16 for N = 2048) pull weights from HBM: the 4M-XL
 // decode step measured 0.7 TB/s through the tensor-core GEMM.  This kernel is HBM-bound by construction: every warp owns output
 // columns, streams the corresponding weight rows with 16-byte loads (4 in flight per lane), keeps the few activation rows in
-// shared memory, and reduces with shuffles.  Epilogues: bf16, fp32, SwiGLU (a = fc1 row, b = fc3 row, g = silu(a) * b with the
+// shared memory, and reduces with shuffles.  Epilogues: bf16, fp32, fp32 residual add, SwiGLU (a = fc1 row, b = fc3 row, g = silu(a) * b with the
 // tcgen05 epilogue's rounding points).  Dispatched from b200fm_gemm_bf16 (NT layout, M <= 8): callers do not see it.
 #include "../../include/b200fm.h"
 #include "common.cuh"
@@ -21,9 +21,11 @@ struct GemvArgs {
     void* out0; long long ld0;
     void* out1; long long ld1;
     const float* bias;
+    const float* resid; long long ldr;
     const float* alpha_dev;
     float alpha;
     int M, N, K, n_half;
+    int prefetch;
 };
 
 B200FM_DEVINL uint4 ldg_stream(const uint4* p) {
@@ -66,7 +68,26 @@ B200FM_DEVINL void row_dot(const __nv_bfloat16* wrow, const uint4* arow, int kch
 template <int MM, int EPI>
 __global__ void __launch_bounds__(kGemvWarps * 32)
 gemv_kernel(const GemvArgs a) {
-    pdl_enter();
+    pdl_trigger();
+    // The weights do not depend on the preceding kernels of a decode step (only the activation rows do): pull this warp's first rows
+    // into L2 BEFORE waiting for the predecessor.  In a chain of programmatically dependent launches this kernel is resident while
+    // the previous one still runs, so the HBM stream of layer i+1 overlaps the execution of layer i.  (A prefetch is a hint: if an
+    // earlier kernel does rewrite the weights, L2 stays coherent.)
+    if (a.prefetch) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const long long row_bytes = (long long)a.K * 2;
+        int n = blockIdx.x * kGemvWarps + warp;
+#pragma unroll 1
+        for (int it = 0; it < 2 && n < a.N; ++it, n += gridDim.x * kGemvWarps) {
+            const char* r0 = reinterpret_cast<const char*>(a.W + (long long)n * a.ldb);
+            for (long long off = lane * 128ll; off < row_bytes; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(r0 + off));
+            if constexpr (EPI == B200FM_EPI_SWIGLU) {
+                const char* r1 = reinterpret_cast<const char*>(a.W + (long long)(a.n_half + n) * a.ldb);
+                for (long long off = lane * 128ll; off < row_bytes; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + off));
+            }
+        }
+    }
+    pdl_wait();
     extern __shared__ uint4 smem_a[];                    // [MM][K / 8] chunks of 8 bf16
     const int kchunks = a.K / 8;
     for (int i = threadIdx.x; i < MM * kchunks; i += kGemvWarps * 32) {
@@ -100,6 +121,10 @@ gemv_kernel(const GemvArgs a) {
 #pragma unroll
                 for (int m = 0; m < MM; ++m) if (m == lane) v = acc[m];
                 if (a.bias) v += a.bias[n];
+                if constexpr (EPI == B200FM_EPI_RESID) {          // out = resid + bf16(acc + bias), like the tile kernel's epilogue
+                    reinterpret_cast<float*>(a.out0)[(long long)lane * a.ld0 + n] = a.resid[(long long)lane * a.ldr + n] + bf16_round(v);
+                    continue;
+                }
                 v *= alpha;
                 if constexpr (EPI == B200FM_EPI_F32) reinterpret_cast<float*>(a.out0)[(long long)lane * a.ld0 + n] = v;
                 else reinterpret_cast<__nv_bfloat16*>(a.out0)[(long long)lane * a.ld0 + n] = __float2bfloat16_rn(v);
@@ -126,21 +151,24 @@ static int launch_gemv_t(const GemvArgs& a, cudaStream_t stream) {
 
 bool gemv_applicable(int layout, int epilogue, int M, int N, int K, long long lda, long long ldb) {
     if (layout != 0 || M > kGemvMaxM || M < 1) return false;
-    if (epilogue != B200FM_EPI_BF16 && epilogue != B200FM_EPI_F32 && epilogue != B200FM_EPI_SWIGLU) return false;
+    if (epilogue != B200FM_EPI_BF16 && epilogue != B200FM_EPI_F32 && epilogue != B200FM_EPI_SWIGLU && epilogue != B200FM_EPI_RESID) return false;
     if ((K % 8) != 0 || (lda % 8) != 0 || (ldb % 8) != 0) return false;
     const int mm = M <= 2 ? 2 : (M <= 4 ? 4 : 8);
     return (size_t)mm * K * 2 <= 200 * 1024 && N >= 64;
 }
 
 int launch_gemv(int epilogue, int M, int N, int K, const void* A, long long lda, const void* W, long long ldb, void* out0, long long ld0,
-                void* out1, long long ld1, const float* bias, float alpha, const float* alpha_dev, cudaStream_t stream) {
+                void* out1, long long ld1, const float* bias, const float* resid, long long ldr, float alpha, const float* alpha_dev,
+                cudaStream_t stream) {
     GemvArgs a;
+    a.resid = resid; a.ldr = ldr;
     a.A = reinterpret_cast<const __nv_bfloat16*>(A); a.lda = lda; a.W = reinterpret_cast<const __nv_bfloat16*>(W); a.ldb = ldb;
     a.out0 = out0; a.ld0 = ld0; a.out1 = out1; a.ld1 = ld1; a.bias = bias; a.alpha = alpha; a.alpha_dev = alpha_dev;
-    a.M = M; a.N = N; a.K = K; a.n_half = N;
+    a.M = M; a.N = N; a.K = K; a.n_half = N; a.prefetch = option(kOptGemvPrefetch);
 #define B200FM_GEMV_CASE(MM_)                                                                                     \
     if (epilogue == B200FM_EPI_BF16) return launch_gemv_t<MM_, B200FM_EPI_BF16>(a, stream);                       \
     if (epilogue == B200FM_EPI_F32) return launch_gemv_t<MM_, B200FM_EPI_F32>(a, stream);                         \
+    if (epilogue == B200FM_EPI_RESID) return launch_gemv_t<MM_, B200FM_EPI_RESID>(a, stream);                     \
     return launch_gemv_t<MM_, B200FM_EPI_SWIGLU>(a, stream);
     if (M <= 2) { B200FM_GEMV_CASE(2) }
     if (M <= 4) { B200FM_GEMV_CASE(4) }

@@ -15,17 +15,20 @@
 namespace b200fm {
 
 // out [rows, terms * K] bf16; role 0 = A operand, 1 = B operand; terms in {3, 6}
+B200FM_DEVINL void limbs_of(float v, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
+    h = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(h);
+    m = __float2bfloat16_rn(r1);
+    l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+}
 __global__ void split_limbs_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out, long long rows, int K, int terms, int role) {
     pdl_enter();
     const long long total = rows * K;
     const long long ldo = (long long)terms * K;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / K; const int c = (int)(i % K);
-        const float v = x[r * ldx + c];
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        const float r1 = v - __bfloat162float(h);
-        const __nv_bfloat16 m = __float2bfloat16_rn(r1);
-        const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+        __nv_bfloat16 h, m, l;
+        limbs_of(x[r * ldx + c], h, m, l);
         __nv_bfloat16* o = out + r * ldo + c;
         if (terms == 3) {
             if (role == 0) { o[0] = h; o[K] = m; o[2 * K] = h; }
@@ -33,6 +36,32 @@ __global__ void split_limbs_kernel(const float* __restrict__ x, long long ldx, _
         } else {
             if (role == 0) { o[0] = h; o[K] = m; o[2 * K] = l; o[3 * K] = h; o[4 * K] = m; o[5 * K] = h; }
             else           { o[0] = h; o[K] = h; o[2 * K] = h; o[3 * K] = m; o[4 * K] = m; o[5 * K] = l; }
+        }
+    }
+}
+// 16-byte version (K % 8 == 0, 16-byte aligned rows): one thread = 8 consecutive elements, two float4 loads, `terms` uint4 stores
+__global__ void __launch_bounds__(256)
+split_limbs_vec_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out, long long rows, int K, int terms, int role) {
+    pdl_enter();
+    const int kc = K / 8;
+    const long long total = rows * kc;
+    const long long ldo = (long long)terms * K;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / kc; const int c = (int)(i % kc) * 8;
+        const float4 v0 = __ldcs(reinterpret_cast<const float4*>(x + r * ldx + c)), v1 = __ldcs(reinterpret_cast<const float4*>(x + r * ldx + c) + 1);
+        const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        __align__(16) __nv_bfloat16 h[8], m[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) limbs_of(v[e], h[e], m[e], l[e]);
+        const uint4 H = *reinterpret_cast<const uint4*>(h), M = *reinterpret_cast<const uint4*>(m), L = *reinterpret_cast<const uint4*>(l);
+        __nv_bfloat16* o = out + r * ldo + c;
+        auto st = [&](int slot, const uint4& w) { *reinterpret_cast<uint4*>(o + (long long)slot * K) = w; };
+        if (terms == 3) {
+            if (role == 0) { st(0, H); st(1, M); st(2, H); }
+            else           { st(0, H); st(1, H); st(2, M); }
+        } else {
+            if (role == 0) { st(0, H); st(1, M); st(2, L); st(3, H); st(4, M); st(5, H); }
+            else           { st(0, H); st(1, H); st(2, H); st(3, M); st(4, M); st(5, L); }
         }
     }
 }
@@ -130,9 +159,11 @@ extern "C" int b200fm_split_limbs(const float* x, long long ldx, void* out_bf16,
     if (rows == 0 || K == 0) return 0;
     B200FM_CHECK(x && out_bf16, "split_limbs: null pointer");
     B200FM_CHECK((terms == 3 || terms == 6) && (role == 0 || role == 1), "split_limbs: terms must be 3 or 6, role 0 (A) or 1 (B)");
-    const long long total = rows * K;
-    const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-    B200FM_LAUNCH(split_limbs_kernel, dim3(grid), dim3(256), 0, stream, 1, x, ldx, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, K, terms, role);
+    const bool vec = K % 8 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0;
+    const long long total = vec ? rows * (K / 8) : rows * K;
+    const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+    if (vec) B200FM_LAUNCH(split_limbs_vec_kernel, dim3(grid), dim3(256), 0, stream, 1, x, ldx, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, K, terms, role);
+    else B200FM_LAUNCH(split_limbs_kernel, dim3(grid), dim3(256), 0, stream, 1, x, ldx, reinterpret_cast<__nv_bfloat16*>(out_bf16), rows, K, terms, role);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }

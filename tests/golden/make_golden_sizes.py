@@ -84,7 +84,7 @@ def main():
         for mode in ("fp32", "bf16", "fp64"):
             res, grads = run(model, batch, N, seed, mode)
             if mode in ("fp64", "bf16"):
-                res["grad_slices"] = {k: grads[k].flatten()[:256].clone() for k in keys if k in grads}
+                res["grad_slices"] = {k: grads[k].flatten()[:4096].clone() for k in keys if k in grads}
             gold["runs"][mode] = res
             print(tag, mode, res["loss"], f"{time.time() - t0:.0f}s", flush=True)
         r = gold["runs"]

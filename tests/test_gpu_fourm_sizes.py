@@ -79,14 +79,18 @@ def test_loss_logits_and_gradients_at_benchmarked_size(tag):
     assert err_mod <= tol_mod
     assert our_max <= 3 * ref_max, (worst_k, our_max, ref_max)
     assert our_med <= 3 * ref_med and our_p90 <= 3 * ref_p90
-    # element-wise on 256 elements of 11 tensors: relative L2 error of each slice against 3 x the reference's own worst slice error
-    # (pooled over the 11 tensors; the max over 256 elements of ONE tensor is too noisy a statistic to compare single draws)
+    # element-wise on the first elements (up to 4096) of 11 tensors: relative L2 error of each slice vs fp64, pooled (rms) over the
+    # tensors, against 3 x the same statistic of the reference's bf16 run; no single tensor beyond 5 x the reference's worst
     def slice_rel(get):
-        return {k: float((get(k) - sl).norm() / (sl.norm() + 1e-300)) for k, sl in r64["grad_slices"].items()}
-    ref_sl = slice_rel(lambda k: r16["grad_slices"][k])
-    our_sl = slice_rel(lambda k: grads[k].flatten()[:256].double().cpu())
-    print(f"[{tag}] grad-slice worst relative L2 error: ours {max(our_sl.values()):.4f} ({max(our_sl, key=our_sl.get)}), reference bf16 {max(ref_sl.values()):.4f}")
-    assert max(our_sl.values()) <= 3 * max(ref_sl.values())
+        return {k: float((get(k, sl.numel()) - sl).norm() / (sl.norm() + 1e-300)) for k, sl in r64["grad_slices"].items()}
+    ref_sl = slice_rel(lambda k, n: r16["grad_slices"][k])
+    our_sl = slice_rel(lambda k, n: grads[k].flatten()[:n].double().cpu())
+    rms = lambda d: (sum(v * v for v in d.values()) / len(d)) ** 0.5
+    print(f"[{tag}] grad-slice relative L2 error: ours rms {rms(our_sl):.4f}, worst {max(our_sl.values()):.4f} ({max(our_sl, key=our_sl.get)}); "
+          f"reference bf16 rms {rms(ref_sl):.4f}, worst {max(ref_sl.values()):.4f}")
+    print(f"[{tag}]   per tensor ours/ref: " + ", ".join(f"{k}: {our_sl[k]:.4f}/{ref_sl[k]:.4f}" for k in our_sl))
+    assert rms(our_sl) <= 3 * rms(ref_sl)
+    assert max(our_sl.values()) <= 5 * max(ref_sl.values())
 
     random.seed(gold["py_seed"])
     with torch.no_grad():

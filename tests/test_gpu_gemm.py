@@ -136,6 +136,9 @@ def test_small_m_weight_streaming_kernel(M):
         torch.testing.assert_close(y32, ref, rtol=1e-3, atol=1e-3)
         y16 = ops.gemm(x, w, epilogue=ops.EPI_BF16, bias=bias, alpha=0.5)
         torch.testing.assert_close(y16.float(), 0.5 * ref, rtol=1e-2, atol=1e-2)
+        res = torch.randn(M, N, device="cuda", generator=g)
+        yr = ops.gemm(x, w, epilogue=ops.EPI_RESID, bias=bias, resid=res)                   # resid + bf16(acc + bias)
+        torch.testing.assert_close(yr, res + ref.bfloat16().float(), rtol=1e-2, atol=1e-2)
         lib.set_option("gemv", 0)
         try:
             t32 = ops.gemm(x, w, epilogue=ops.EPI_F32, bias=bias)
@@ -187,3 +190,48 @@ def test_fused_head_cross_entropy(n, V, D):
         torch.testing.assert_close(dl[:m].float(), ref_grad[:m], rtol=1e-2, atol=2e-4)
         m64 = min((m + 63) // 64 * 64, n)
         assert float(dl[m:m64].float().abs().sum()) == 0.0
+
+
+def test_kv_append_writes_one_cache_row():
+    """b200fm_kv_append: cache[b, *pos, col0:col0+w] = src[b] with the position in device memory; everything else untouched; an
+    out-of-range position is a no-op."""
+    from b200fm import ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for B, L, W, w, col0 in ((2, 7, 256, 256, 0), (3, 5, 512, 256, 256), (1, 4, 24, 7, 3)):
+        cache = torch.randn(B, L, W, device="cuda", generator=g).bfloat16()
+        src_full = torch.randn(B, w + 16, device="cuda", generator=g).bfloat16()
+        src = src_full[:, 8:8 + w] if w % 8 == 0 else src_full[:, 1:1 + w]
+        for pos in (0, L - 1, L):
+            ref = cache.clone()
+            if pos < L:
+                ref[:, pos, col0:col0 + w] = src
+            out = ops.kv_append(src, cache.clone(), torch.tensor([pos], device="cuda"), col0)
+            assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("terms,tol", [(3, 2e-5), (6, 2e-6)])
+def test_fp32_faithful_linear_and_attention(terms, tol):
+    """b200fm.functional.linear_f32 (bf16 limb products on the tcgen05 GEMM; vectorised and scalar limb-split kernels) and
+    ops.attention_f32 against fp64: relative error of an fp32 matmul, not of a bf16 one (which is ~4e-3)."""
+    from b200fm import functional as BF
+    from b200fm import ops
+    g = torch.Generator(device="cuda").manual_seed(terms)
+    for M, K, N in ((300, 768, 512), (64, 104, 72), (1000, 3072, 768)):
+        x = torch.randn(M, K, device="cuda", generator=g)
+        if K == 104:                                            # a misaligned row view: the scalar limb-split kernel
+            x = torch.randn(M, K + 3, device="cuda", generator=g)[:, 1:1 + K]
+        w = torch.randn(N, K, device="cuda", generator=g) * 0.1
+        b = torch.randn(N, device="cuda", generator=g)
+        with BF.precise(terms):
+            y = BF.linear_f32(x, w, b, cache=False)
+        ref = x.double() @ w.double().t() + b.double()
+        err = float((y.double() - ref).norm() / ref.norm())
+        bf16_err = float(((x.bfloat16().double() @ w.bfloat16().double().t() + b.double()) - ref).norm() / ref.norm())
+        assert err <= tol and err < bf16_err / 50, (M, K, N, err, bf16_err)
+    B, H, N, D = 3, 4, 197, 64
+    qkv = torch.randn(B * N, 3 * H * D, device="cuda", generator=g)
+    C = H * D
+    o = ops.attention_f32(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, H, N, N, None, D ** -0.5)
+    q, k, v = (t.view(B, N, H, D).permute(0, 2, 1, 3).double() for t in (qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]))
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * D ** -0.5, -1) @ v).permute(0, 2, 1, 3).reshape(B * N, C)
+    assert float((o.double() - ref).norm() / ref.norm()) <= 2e-6
