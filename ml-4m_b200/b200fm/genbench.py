@@ -114,9 +114,10 @@ def run(args, ClockSampler, measured_peaks, cpu_threads, reference_tree):
     state = _deep_clone(make_sample(rgb_dev))
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(len(schedule) + 1)]
     marks[0].record()
-    for i, info in enumerate(schedule):
-        state = sampler._one_step(state, info, i, 0.0, 0.8, tok, 0, write_all=False)
-        marks[i + 1].record()
+    with torch.no_grad():
+        for i, info in enumerate(schedule):
+            state = sampler._one_step(state, info, i, 0.0, 0.8, tok, 0, write_all=False)
+            marks[i + 1].record()
     torch.cuda.synchronize()
     breakdown = {info['target_domain']: round(marks[i].elapsed_time(marks[i + 1]), 1) for i, info in enumerate(schedule)}
     # weight-streaming roofline of the dominant kernel of the AR loop: the M = 1 linears of one decode step, launched back to back

@@ -52,6 +52,7 @@ struct GemmArgs {
     // fused masked-token head (EPI_CE_STATS / EPI_CE_GRAD, fm.py:589-600): the logits tile never leaves the SM
     const long long* targets;     // int64 [M]
     const float* lse;             // EPI_CE_GRAD: fp32 [M] log-sum-exp of every row
+    int debug;                    // option "gemm_debug" (measurement only): 1 = epilogue reads TMEM but stores nothing, 2 = epilogue skipped
 };
 
 constexpr int EPI_CE_STATS = 6;   // out0 = float2 ws[M][ld0] per-(row, column slot) (max, sum exp(l - max)); out1 = fp32 tlogit[M] (target logit)
@@ -293,11 +294,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 __nv_bfloat16* gg = reinterpret_cast<__nv_bfloat16*>(args.out1);
                 const bool vec_ok = (args.ld0 & 7) == 0 && (args.ld1 & 7) == 0 && (args.n_half & 7) == 0;
 #pragma unroll 1
-                for (int c = half * (HB / 64); c < (half + 1) * (HB / 64); ++c) {        // 32 gate columns per iteration
+                for (int c = half * (HB / 64); c < (half + 1) * (HB / 64) && args.debug != 2; ++c) {        // 32 gate columns per iteration
                     uint32_t ra[32], rb[32];
                     tmem_ld_x32(t_acc + c * 32, ra);
                     tmem_ld_x32(t_acc + HB + c * 32, rb);
                     tmem_ld_wait();
+                    if (args.debug == 1) continue;
                     const int n = n0 + c * 32;
                     uint32_t pa[16], pb[16], pg[16];
 #pragma unroll
@@ -379,12 +381,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     }
                 } else
 #pragma unroll 1
-                for (int c = c0; c < c0 + kChunks; ++c) {
+                for (int c = c0; c < c0 + kChunks && args.debug != 2; ++c) {
                     uint32_t r[32];
                     tmem_ld_x32(t_acc + c * 32, r);
                     tmem_ld_wait();
                     const int n = n0 + c * 32;
                     if (n >= args.N) continue;                   // warp-uniform
+                    if (args.debug == 1) continue;
                     if (empty_acc) {                             // warp-uniform; only reachable with a device-side K (dyn_mode 2)
                         if (args.k_splits > 1) continue;         // nothing to add
 #pragma unroll
@@ -566,7 +569,7 @@ static int gemm_impl(int layout, int epilogue, int M, int N, int K, const void* 
     a.out0 = out0; a.ld0 = ld0; a.out1 = out1; a.ld1 = ld1; a.bias = bias; a.resid = resid; a.ldr = ldr;
     a.n_half = N; a.alpha = alpha; a.alpha_dev = alpha_dev; a.act = act;
     a.dyn_dev = dyn_dev; a.dyn_mode = dyn_dev ? dyn_mode : 0;
-    a.targets = targets; a.lse = lse;
+    a.targets = targets; a.lse = lse; a.debug = option(kOptGemmDebug);
     a.num_m_blocks = (M + kBM - 1) / kBM;
 
     // tile width: 256 when there is enough N to fill it and enough tiles to fill the machine, else 128

@@ -48,40 +48,51 @@ B200FM_DEVINL void dot8(const uint4& w, const uint4* arow, int chunk, int kchunk
     }
 }
 
-// dot products of weight row `wrow` with the MM activation rows in smem (K in 8-element chunks), full warp, result in every lane
-template <int MM>
-B200FM_DEVINL void row_dot(const __nv_bfloat16* wrow, const uint4* arow, int kchunks, int lane, float (&acc)[MM]) {
+// Weight rows are streamed in batches of 8 x 16 B per lane (one 4 KB row of a K = 2048 layer = ONE batch): all loads of a batch are
+// issued before the first FMA, so a warp keeps 4 KB (8 KB with the SwiGLU row pair) in flight instead of 2 KB, and the first batch is
+// requested BEFORE the activation rows are staged in shared memory -- the kernel's critical path is one memory round trip.
+constexpr int kGemvBatch = 8;
+
+template <int NR>
+B200FM_DEVINL void load_batch(const uint4* const (&wp)[NR], int c0, int kchunks, uint4 (&w)[NR][kGemvBatch]) {
 #pragma unroll
-    for (int m = 0; m < MM; ++m) acc[m] = 0.f;
-    const uint4* wp = reinterpret_cast<const uint4*>(wrow);
-    int c = lane;
-    for (; c + 96 < kchunks; c += 128) {                 // 4 independent 16-byte loads in flight per lane
-        const uint4 w0 = ldg_stream(wp + c), w1 = ldg_stream(wp + c + 32), w2 = ldg_stream(wp + c + 64), w3 = ldg_stream(wp + c + 96);
-        dot8<MM>(w0, arow, c, kchunks, acc); dot8<MM>(w1, arow, c + 32, kchunks, acc);
-        dot8<MM>(w2, arow, c + 64, kchunks, acc); dot8<MM>(w3, arow, c + 96, kchunks, acc);
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int j = 0; j < kGemvBatch; ++j) {
+            const int c = c0 + j * 32;
+            w[r][j] = c < kchunks ? ldg_stream(wp[r] + c) : make_uint4(0u, 0u, 0u, 0u);
+        }
+}
+template <int MM, int NR>
+B200FM_DEVINL void fma_batch(const uint4 (&w)[NR][kGemvBatch], const uint4* arow, int c0, int kchunks, float (&acc)[NR][MM]) {
+#pragma unroll
+    for (int j = 0; j < kGemvBatch; ++j) {
+        const int c = c0 + j * 32;
+        if (c < kchunks) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) dot8<MM>(w[r][j], arow, c, kchunks, acc[r]);
+        }
     }
-    for (; c < kchunks; c += 32) dot8<MM>(ldg_stream(wp + c), arow, c, kchunks, acc);
-#pragma unroll
-    for (int m = 0; m < MM; ++m) acc[m] = warp_sum(acc[m]);
 }
 
 template <int MM, int EPI>
 __global__ void __launch_bounds__(kGemvWarps * 32)
 gemv_kernel(const GemvArgs a) {
+    constexpr int NR = EPI == B200FM_EPI_SWIGLU ? 2 : 1;                  // weight rows per output column
     pdl_trigger();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // The weights do not depend on the preceding kernels of a decode step (only the activation rows do): pull this warp's first rows
     // into L2 BEFORE waiting for the predecessor.  In a chain of programmatically dependent launches this kernel is resident while
     // the previous one still runs, so the HBM stream of layer i+1 overlaps the execution of layer i.  (A prefetch is a hint: if an
     // earlier kernel does rewrite the weights, L2 stays coherent.)
     if (a.prefetch) {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         const long long row_bytes = (long long)a.K * 2;
         int n = blockIdx.x * kGemvWarps + warp;
 #pragma unroll 1
         for (int it = 0; it < 2 && n < a.N; ++it, n += gridDim.x * kGemvWarps) {
             const char* r0 = reinterpret_cast<const char*>(a.W + (long long)n * a.ldb);
             for (long long off = lane * 128ll; off < row_bytes; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(r0 + off));
-            if constexpr (EPI == B200FM_EPI_SWIGLU) {
+            if constexpr (NR == 2) {
                 const char* r1 = reinterpret_cast<const char*>(a.W + (long long)(a.n_half + n) * a.ldb);
                 for (long long off = lane * 128ll; off < row_bytes; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + off));
             }
@@ -90,23 +101,50 @@ gemv_kernel(const GemvArgs a) {
     pdl_wait();
     extern __shared__ uint4 smem_a[];                    // [MM][K / 8] chunks of 8 bf16
     const int kchunks = a.K / 8;
+    int n = blockIdx.x * kGemvWarps + warp;
+    uint4 w[NR][kGemvBatch];
+    const uint4* wp[NR];
+    if (n < a.N) {                                       // first batch of weight loads in flight across the activation staging
+        wp[0] = reinterpret_cast<const uint4*>(a.W + (long long)n * a.ldb);
+        if constexpr (NR == 2) wp[1] = reinterpret_cast<const uint4*>(a.W + (long long)(a.n_half + n) * a.ldb);
+        load_batch<NR>(wp, lane, kchunks, w);
+    }
     for (int i = threadIdx.x; i < MM * kchunks; i += kGemvWarps * 32) {
         const int m = i / kchunks, c = i % kchunks;
         smem_a[i] = m < a.M ? *reinterpret_cast<const uint4*>(a.A + (long long)m * a.lda + c * 8) : make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float alpha = a.alpha * (a.alpha_dev ? __ldg(a.alpha_dev) : 1.0f);
-    for (int n = blockIdx.x * kGemvWarps + warp; n < a.N; n += gridDim.x * kGemvWarps) {
-        float acc[MM];
-        row_dot<MM>(a.W + (long long)n * a.ldb, smem_a, kchunks, lane, acc);
+    for (; n < a.N; n += gridDim.x * kGemvWarps) {
+        float acc[NR][MM];
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+#pragma unroll
+            for (int m = 0; m < MM; ++m) acc[r][m] = 0.f;
+        for (int c0 = lane; c0 < kchunks; c0 += 32 * kGemvBatch) {
+            fma_batch<MM, NR>(w, smem_a, c0, kchunks, acc);
+            // next batch: of this row, or the first batch of the warp's next row
+            const int c1 = c0 + 32 * kGemvBatch;
+            if (c1 < kchunks) {
+                load_batch<NR>(wp, c1, kchunks, w);
+            } else {
+                const int n1 = n + gridDim.x * kGemvWarps;
+                if (n1 < a.N) {
+                    wp[0] = reinterpret_cast<const uint4*>(a.W + (long long)n1 * a.ldb);
+                    if constexpr (NR == 2) wp[1] = reinterpret_cast<const uint4*>(a.W + (long long)(a.n_half + n1) * a.ldb);
+                    load_batch<NR>(wp, lane, kchunks, w);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+#pragma unroll
+            for (int m = 0; m < MM; ++m) acc[r][m] = warp_sum(acc[r][m]);
         if constexpr (EPI == B200FM_EPI_SWIGLU) {
-            float accb[MM];
-            row_dot<MM>(a.W + (long long)(a.n_half + n) * a.ldb, smem_a, kchunks, lane, accb);
             if (lane < a.M) {
                 float va = 0.f, vb = 0.f;
 #pragma unroll
-                for (int m = 0; m < MM; ++m) if (m == lane) { va = acc[m]; vb = accb[m]; }
+                for (int m = 0; m < MM; ++m) if (m == lane) { va = acc[0][m]; vb = acc[NR - 1][m]; }
                 if (a.bias) { va += a.bias[n]; vb += a.bias[a.n_half + n]; }
                 __nv_bfloat16* ab = reinterpret_cast<__nv_bfloat16*>(a.out0) + (long long)lane * a.ld0;
                 const __nv_bfloat16 pa = __float2bfloat16_rn(va), pb = __float2bfloat16_rn(vb);
@@ -119,15 +157,15 @@ gemv_kernel(const GemvArgs a) {
             if (lane < a.M) {
                 float v = 0.f;
 #pragma unroll
-                for (int m = 0; m < MM; ++m) if (m == lane) v = acc[m];
+                for (int m = 0; m < MM; ++m) if (m == lane) v = acc[0][m];
                 if (a.bias) v += a.bias[n];
                 if constexpr (EPI == B200FM_EPI_RESID) {          // out = resid + bf16(acc + bias), like the tile kernel's epilogue
                     reinterpret_cast<float*>(a.out0)[(long long)lane * a.ld0 + n] = a.resid[(long long)lane * a.ldr + n] + bf16_round(v);
-                    continue;
+                } else {
+                    v *= alpha;
+                    if constexpr (EPI == B200FM_EPI_F32) reinterpret_cast<float*>(a.out0)[(long long)lane * a.ld0 + n] = v;
+                    else reinterpret_cast<__nv_bfloat16*>(a.out0)[(long long)lane * a.ld0 + n] = __float2bfloat16_rn(v);
                 }
-                v *= alpha;
-                if constexpr (EPI == B200FM_EPI_F32) reinterpret_cast<float*>(a.out0)[(long long)lane * a.ld0 + n] = v;
-                else reinterpret_cast<__nv_bfloat16*>(a.out0)[(long long)lane * a.ld0 + n] = __float2bfloat16_rn(v);
             }
         }
     }
@@ -143,7 +181,7 @@ static int launch_gemv_t(const GemvArgs& a, cudaStream_t stream) {
         configured = smem;
     }
     const int want = (a.N + kGemvWarps - 1) / kGemvWarps;
-    const int cap = usable_sm_count() * 4;
+    const int cap = usable_sm_count() * (EPI == B200FM_EPI_SWIGLU ? 2 : 3);   // resident CTAs per SM at 124 / 85 registers: one wave, rows pipelined inside the warps
     B200FM_LAUNCH(kern, dim3(want < cap ? want : cap), dim3(kGemvWarps * 32), smem, stream, 1, a);
     B200FM_CUDA(cudaGetLastError());
     return 0;

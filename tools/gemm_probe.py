@@ -1,28 +1,44 @@
-"""Back-to-back timing of the 4M-B GEMM shapes in isolation (hot L2, boost clocks): the upper bound the in-step numbers of
-profiles/r1_gemm_shapes_*.json are compared with."""
-import os, sys, torch
-import os
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ml-4m_b200"))
-from b200fm import ops
-def t(fn, n=30):
-    for _ in range(5): fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n): fn()
-    e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / n * 1e3
-R = 16384
-x = torch.randn(R, 768, device="cuda").bfloat16(); xk = torch.randn(R, 2048, device="cuda").bfloat16()
-w_qkv = torch.randn(2304, 768, device="cuda").bfloat16(); w_p = torch.randn(768, 768, device="cuda").bfloat16()
-w2 = torch.randn(768, 2048, device="cuda").bfloat16(); w13 = torch.randn(4096, 768, device="cuda").bfloat16()
-dy = torch.randn(R, 2304, device="cuda").bfloat16()
-for name, fn, fl in [("NT 16384x2304x768", lambda: ops.gemm(x, w_qkv), 2 * R * 2304 * 768),
-                     ("NT 16384x768x768", lambda: ops.gemm(x, w_p), 2 * R * 768 * 768),
-                     ("NT 16384x768x2048", lambda: ops.gemm(xk, w2), 2 * R * 768 * 2048),
-                     ("NT swiglu 16384x2048x768", lambda: ops.gemm(x, w13, epilogue=ops.EPI_SWIGLU), 2 * R * 4096 * 768),
-                     ("TN 2304x768x16384", lambda: ops.gemm(dy, x, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32), 2 * R * 2304 * 768),
-                     ("TN 768x768x16384", lambda: ops.gemm(x, x, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32), 2 * R * 768 * 768),
-                     ("TN 768x2048x16384", lambda: ops.gemm(x, xk, layout=ops.LAYOUT_TN, epilogue=ops.EPI_F32), 2 * R * 768 * 2048)]:
-    us = t(fn)
-    print(f"{name:28s} {us:7.1f} us  {fl / us / 1e6:7.1f} TF/s")
+"""Where does the tcgen05 GEMM lose time at the 4M-B shapes?  Times each shape with the normal epilogue, with an epilogue that reads the
+accumulator but stores nothing (option gemm_debug = 1) and with the epilogue skipped entirely (= 2): the difference separates the cost of
+the mainloop (TMA + MMA) from TMEM read-out and from the staged global stores.  Rotating operand sets (> L2)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "ml-4m_b200"))
+import torch
+from b200fm import lib, ops
+
+M = 16384
+SHAPES = [("qkv NT bf16", ops.LAYOUT_NT, ops.EPI_BF16, M, 2304, 768), ("proj NT bf16", ops.LAYOUT_NT, ops.EPI_BF16, M, 768, 768),
+          ("fc13 NT swiglu", ops.LAYOUT_NT, ops.EPI_SWIGLU, M, 2048, 768), ("fc2 NT bf16", ops.LAYOUT_NT, ops.EPI_BF16, M, 768, 2048),
+          ("dgrad NN bf16", ops.LAYOUT_NN, ops.EPI_BF16, M, 768, 2304), ("wgrad TN f32", ops.LAYOUT_TN, ops.EPI_F32, 2304, 768, M),
+          ("big NT bf16", ops.LAYOUT_NT, ops.EPI_BF16, 8192, 8192, 8192)]
+S = 4
+torch.manual_seed(0)
+for name, layout, epi, m, n, k in SHAPES:
+    if layout == ops.LAYOUT_NT:
+        As = [torch.randn(m, k, device="cuda").bfloat16() for _ in range(S)]
+        Bs = [torch.randn((2 * n if epi == ops.EPI_SWIGLU else n), k, device="cuda").bfloat16() for _ in range(S)]
+    elif layout == ops.LAYOUT_NN:
+        As = [torch.randn(m, k, device="cuda").bfloat16() for _ in range(S)]
+        Bs = [torch.randn(k, n, device="cuda").bfloat16() for _ in range(S)]
+    else:
+        As = [torch.randn(k, m, device="cuda").bfloat16() for _ in range(S)]
+        Bs = [torch.randn(k, n, device="cuda").bfloat16() for _ in range(S)]
+    flops = 2.0 * m * k * (2 * n if epi == ops.EPI_SWIGLU else n)
+    outs = None
+    res = []
+    for dbg in (0, 1, 2):
+        lib.set_option("gemm_debug", dbg)
+        r = ops.gemm(As[0], Bs[0], layout=layout, epilogue=epi)
+        o0, o1 = (r if isinstance(r, tuple) else (r, None))
+        for i in range(4):
+            ops.gemm(As[i % S], Bs[i % S], layout=layout, epilogue=epi, out=o0, out1=o1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for i in range(40):
+            ops.gemm(As[i % S], Bs[i % S], layout=layout, epilogue=epi, out=o0, out1=o1)
+        e1.record(); torch.cuda.synchronize()
+        res.append(e0.elapsed_time(e1) / 40 * 1e3)
+    lib.set_option("gemm_debug", 0)
+    print(f"{name:16s} {m:6d}x{n:5d}x{k:5d}  normal {res[0]:7.1f} us ({flops / res[0] / 1e6:7.1f} TF/s)   no-store {res[1]:7.1f} us ({flops / res[1] / 1e6:7.1f})   "
+          f"no-epilogue {res[2]:7.1f} us ({flops / res[2] / 1e6:7.1f})")
