@@ -504,12 +504,25 @@ class MlpActFn(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------------------------------
 # attention
 # ----------------------------------------------------------------------------------------------------------------------
+ATTN_BWD_MAX_TOKENS = 256      # b200fm_attention_bwd: query / key tiles of one (batch, head) item live in TMEM for the whole item
+
+
+def _check_trainable_length(ctx, Nq, Nk):
+    """The forward accepts longer sequences (attention_fwd_long, generation contexts) than the backward kernel: fail in the FORWARD of a
+    pass that records gradients, not half-way through backward()."""
+    if any(ctx.needs_input_grad) and max(Nq, Nk) > ATTN_BWD_MAX_TOKENS:
+        raise ValueError(f"attention over {Nq} queries x {Nk} keys cannot be trained on the B200 path: the backward kernel supports at most "
+                         f"{ATTN_BWD_MAX_TOKENS} tokens per side (encoder tokens + register tokens, decoder tokens); run it under torch.no_grad() "
+                         f"or lower num_encoder_tokens / num_decoder_tokens")
+
+
 class AttentionFn(torch.autograd.Function):
     """softmax(q k^T * scale, masked) v per head on 2-D row views (fm_utils.py:160-180 / 197-219).
     q [B*Nq, H*64], k / v [B*Nk, H*64] bf16 (column slices of packed qkv / kv buffers are fine)."""
 
     @staticmethod
     def forward(ctx, q, k, v, mask, B, H, Nq, Nk, scale):
+        _check_trainable_length(ctx, Nq, Nk)
         out, stats = ops.attention_fwd(q, k, v, B, H, Nq, Nk, mask, scale)
         ctx.save_for_backward(q, k, v, out, stats, mask)
         ctx.dims = (B, H, Nq, Nk, scale)
@@ -795,6 +808,7 @@ class SelfAttnSubLayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, ypend, mask, nw, nb, qkv_w, qkv_b, proj_w, proj_b, eps, heads, scale):
         B, N, D = x.shape
+        _check_trainable_length(ctx, N, N)
         x2, y2 = _prep_stream(x, ypend, D)
         s2, h, mean, rstd = ops.add_layernorm_fwd(x2, y2, nw, nb, eps)
         qkv = ops.gemm(h, weight_bf16(qkv_w), epilogue=ops.EPI_BF16, bias=qkv_b, n_out=3 * D)
@@ -833,6 +847,7 @@ class CrossAttnSubLayerFn(torch.autograd.Function):
     def forward(ctx, x, ypend, context, mask, qnw, qnb, cnw, cnb, q_w, q_b, kv_w, kv_b, proj_w, proj_b, eps_q, eps_c, heads, scale):
         B, N, D = x.shape
         M = context.shape[1]
+        _check_trainable_length(ctx, N, M)
         x2, y2 = _prep_stream(x, ypend, D)
         c2 = context.reshape(B * M, D)
         if not c2.is_contiguous():

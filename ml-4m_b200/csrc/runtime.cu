@@ -17,7 +17,7 @@ struct OptionSlot { const char* name; const char* env; int def; int value; bool 
 static OptionSlot g_options[kOptCount] = {
     {"pdl", "B200FM_PDL", 1, 1, false},                        // programmatic dependent launch on every kernel
     {"gemm_cta_pairs", "B200FM_GEMM_CTA_PAIRS", 1, 1, false},  // tcgen05 cta_group::2 GEMM tiles
-    {"ln_bwd_v2", "B200FM_LN_BWD_V2", 0, 0, false},            // LayerNorm backward variants 1 / 2 (measured: no difference inside a step)
+    {"ln_bwd_v2", "B200FM_LN_BWD_V2", 1, 1, false},            // LayerNorm backward: 1 = dres loads hoisted (35.4 us vs 47.4 us stand-alone at 16384 x 768: tools/ln_bench.py), 0 / 2 / 3 = other variants
     {"sm_reserve", "B200FM_SM_RESERVE", 0, 0, false},          // SMs the persistent GEMM grids leave free (concurrent all-reduce kernel)
     {"gemv", "B200FM_GEMV", 1, 1, false},                      // NT GEMMs with <= 8 rows run on the weight-streaming kernel (gemv.cu)
     {"gemv_prefetch", "B200FM_GEMV_PREFETCH", 1, 1, false},    // gemv.cu: L2-prefetch the weight rows BEFORE waiting for the predecessor grid

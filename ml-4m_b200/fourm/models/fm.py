@@ -290,12 +290,20 @@ class FourM(nn.Module):
             y = blk(y, context, sa_mask=decoder_attention_mask, xa_mask=encoder_mask)
         return self.decoder_norm(y)
 
+    def _block_pending(self, blk, *args, **kw):
+        """blk.forward_pending, recomputed in backward when `use_act_checkpoint` is set (the reference stores the flag, fm.py:113,
+        and leaves the wrapping to its FSDP launcher; here the flag alone trades the block's saved activations for a second forward)."""
+        if self.use_act_checkpoint and torch.is_grad_enabled():
+            from torch.utils.checkpoint import checkpoint
+            return checkpoint(lambda *a: blk.forward_pending(*a, **kw), *args, use_reentrant=False)
+        return blk.forward_pending(*args, **kw)
+
     def _encoder_to_context(self, x, encoder_mask, encoder_emb):
         """encoder blocks -> encoder_norm -> decoder_proj_context(x) + encoder_emb (reference fm.py:678-679); the norm
         emits the bf16 GEMM operand and the `+ encoder_emb` rides in the GEMM epilogue."""
         ypend = None
         for blk in self.encoder:
-            x, ypend = blk.forward_pending(x, ypend, mask=encoder_mask)
+            x, ypend = self._block_pending(blk, x, ypend, mask=encoder_mask)
         np_ = _norm_params(self.encoder_norm)
         if np_ is not None and type(self.decoder_proj_context) is nn.Linear and x.dtype == torch.float32:
             return BF.NormLinearResidualFn.apply(x, ypend, np_[0], np_[1], self.decoder_proj_context.weight,
@@ -439,7 +447,7 @@ class FourM(nn.Module):
         context = self._encoder_to_context(x0, encoder_mask, enc_emb)
         y, ypend = y0, None
         for blk in self.decoder:
-            y, ypend = blk.forward_pending(y, ypend, context, sa_mask=dec_attn_mask, xa_mask=encoder_mask)
+            y, ypend = self._block_pending(blk, y, ypend, context, sa_mask=dec_attn_mask, xa_mask=encoder_mask)
         np_ = _norm_params(self.decoder_norm)
         if np_ is not None and y.dtype == torch.float32:
             y = BF.AddLayerNormFn.apply(y, ypend, np_[0], np_[1], np_[2])      # bf16: the head GEMMs' operand

@@ -162,3 +162,34 @@ def test_context_norm_trains_with_detached_context():
     blk(x, ctx2).float().square().mean().backward()
     torch.testing.assert_close(blk.context_norm.weight.grad, g_det, rtol=1e-4, atol=1e-7)
     assert ctx2.grad is not None
+
+
+def test_activation_checkpointing_and_trainable_length():
+    """`use_act_checkpoint=True` recomputes every block in backward (same loss, same gradients up to the order of fp32
+    atomics); a sequence longer than the backward kernel supports is rejected in the FORWARD of a gradient-recording pass, while the
+    same call under no_grad runs (attention_fwd_long)."""
+    import random
+    from b200fm.compat import build_mod7_embeddings, create_model
+    from oracle import fourm_oracle as O
+    outs = []
+    for ckpt in (False, True):
+        torch.manual_seed(3)
+        enc, dec, info = build_mod7_embeddings()
+        model = create_model("fm_tiny_6e_6d_swiglu_nobias", encoder_embeddings=enc, decoder_embeddings=dec, modality_info=info,
+                             use_act_checkpoint=ckpt).cuda()
+        batch = {m: {k: v.cuda() for k, v in d.items()} for m, d in O.synthetic_mod7_batch(2, seed=5).items()}
+        random.seed(1)
+        loss, _ = model(batch, 128, 128)
+        loss.backward()
+        outs.append((float(loss), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}))
+    assert abs(outs[0][0] - outs[1][0]) <= 1e-6
+    assert outs[0][1].keys() == outs[1][1].keys()
+    for k, g in outs[0][1].items():
+        torch.testing.assert_close(outs[1][1][k], g, rtol=1e-3, atol=1e-6, msg=k)
+    from b200fm import functional as BF
+    q = torch.randn(2 * 300, 128, device="cuda").bfloat16()
+    kv = torch.randn(2 * 300, 128, device="cuda").bfloat16()
+    with torch.no_grad():
+        assert BF.AttentionFn.apply(q, kv, kv, None, 2, 2, 300, 300, 0.125).shape == (600, 128)
+    with pytest.raises(ValueError, match="cannot be trained"):
+        BF.AttentionFn.apply(q.requires_grad_(), kv, kv, None, 2, 2, 300, 300, 0.125)
