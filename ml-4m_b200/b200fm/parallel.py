@@ -137,8 +137,11 @@ class GradSync(torch.nn.Module):
         # during backward the reductions have ~2/3 of a step to hide in: a few CTAs (= SMs taken from the GEMM grids) are enough.  The
         # chunks that only become ready at the END of backward (embedding tables) are on the critical path: they get many CTAs, no
         # compute kernel competes for the SMs at that point (AdamW of the early chunks is HBM-bound and shares them)
+        # "slim" all-reduce CTAs (option comm_slim / B200FM_COMM_SLIM=1): 128 threads, <= 64 registers -- co-resident with the persistent
+        # backward kernels instead of on SMs reserved for them; the bytes in flight come from the CTA count
+        self.slim = cuda and transport == "p2p" and lib.get_option("comm_slim") != 0
         if n_ctas is None:
-            n_ctas = int(os.environ.get("B200FM_COMM_CTAS", "6"))
+            n_ctas = int(os.environ.get("B200FM_COMM_CTAS", "48" if self.slim else "6"))
         if n_ctas_tail is None:
             n_ctas_tail = int(os.environ.get("B200FM_COMM_CTAS_TAIL", "64"))
         self.n_ctas, self.n_ctas_tail = n_ctas, max(n_ctas, n_ctas_tail)
@@ -146,7 +149,7 @@ class GradSync(torch.nn.Module):
         self._layout(params, int(chunk_mb * (1 << 20) // 4))
         self.transport = (_P2PTransport if transport == "p2p" else _CollectiveTransport)(self.total, self.device, process_group, n_ctas)
         self.arena = self.transport.arena
-        self.reserve_sms = n_ctas if (cuda and transport == "p2p") else 0
+        self.reserve_sms = n_ctas if (cuda and transport == "p2p" and not self.slim) else 0
         self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1) if cuda else None
         self._step = 0
         # step-dependent part of the all-reduce sequence numbers, kept ON THE DEVICE and advanced by a stream-ordered add at the start

@@ -62,8 +62,12 @@ B200FM_DEVINL void cta_barrier_all_ranks(const CommPeers& pr, int rank, int worl
     __syncthreads();
 }
 
-template <int W>
-__global__ void __launch_bounds__(kCommThreads, 1)
+// Two launch shapes.  "wide": few CTAs of 512 threads with 16 loads in flight per thread -- they need SMs of their own (the persistent
+// GEMM / attention grids leave `sm_reserve` SMs free for them).  "slim" (THREADS = 128, <= 64 registers, no shared memory): small enough
+// to be CO-RESIDENT with a persistent kernel's CTA on the same SM (320 x 168 + 128 x 64 registers fit the file), so no SM has to be taken
+// away from the backward pass; the bytes in flight come from the number of CTAs (32-64) instead.
+template <int W, int THREADS, int UTOT>
+__global__ void __launch_bounds__(THREADS, THREADS == 128 ? 8 : 1)
 allreduce_f32_kernel(const CommPeers pr, int rank, long long off, long long n4, float scale, uint32_t seq, const uint32_t* seq_base_dev) {
     // CUDA-graph replays: the sequence number must differ per replay, so its step-dependent part is read from device memory
     if (seq_base_dev != nullptr) seq += *reinterpret_cast<const volatile uint32_t*>(seq_base_dev);
@@ -82,9 +86,9 @@ allreduce_f32_kernel(const CommPeers pr, int rank, long long off, long long n4, 
     }
     // NVLink round trips are ~2 us: the few CTAs this kernel is allowed need many 16-byte loads in flight per thread.
     // U float4 per peer per thread -> U * W independent loads before the first use (16 for every W).
-    constexpr int U = 16 / W >= 1 ? 16 / W : 1;
-    const long long stride = (long long)gridDim.x * kCommThreads;
-    for (long long i0 = lo + (long long)blockIdx.x * kCommThreads + threadIdx.x; i0 < hi; i0 += U * stride) {
+    constexpr int U = UTOT / W >= 1 ? UTOT / W : 1;
+    const long long stride = (long long)gridDim.x * THREADS;
+    for (long long i0 = lo + (long long)blockIdx.x * THREADS + threadIdx.x; i0 < hi; i0 += U * stride) {
         float4 v[U][W];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -171,8 +175,12 @@ extern "C" int b200fm_allreduce_f32_seq(void* const* peer_data, void* const* pee
     }
     const long long n4 = n_elems / 4;
     // plain launch (no programmatic dependent launch): the kernel must not start before the producers of the chunk have finished
+    const bool slim = option(kOptCommSlim) != 0;
 #define B200FM_AR_CASE(W_)                                                                                                   \
-    case W_: allreduce_f32_kernel<W_><<<n_ctas, kCommThreads, 0, stream>>>(pr, rank, offset_elems, n4, scale, seq, seq_base_dev); break;
+    case W_:                                                                                                                 \
+        if (slim) allreduce_f32_kernel<W_, 128, 8><<<n_ctas, 128, 0, stream>>>(pr, rank, offset_elems, n4, scale, seq, seq_base_dev); \
+        else allreduce_f32_kernel<W_, kCommThreads, 16><<<n_ctas, kCommThreads, 0, stream>>>(pr, rank, offset_elems, n4, scale, seq, seq_base_dev); \
+        break;
     switch (world) {
         B200FM_AR_CASE(2) B200FM_AR_CASE(3) B200FM_AR_CASE(4) B200FM_AR_CASE(5) B200FM_AR_CASE(6) B200FM_AR_CASE(7) B200FM_AR_CASE(8)
         default: B200FM_CHECK(false, "allreduce_f32: unsupported world size %d", world);

@@ -78,7 +78,16 @@ B200FM_DEVINL float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 //
 // bf16: 32 rows x 16 packed words, XOR-swizzled 16 B quads (conflict-free for both the row-wise write and the 8-row read)
 B200FM_DEVINL void stage_store_bf16(uint32_t* stg, int lane, const uint32_t (&p)[16], __nv_bfloat16* out, long long ld, int row_base, int n,
-                                    int M, int N, bool vec_ok) {
+                                    int M, int N, bool vec_ok, int dbg = 0) {
+    if (dbg == 4) {      // measurement: thread = row writes its 64 contiguous bytes straight from registers (no shared-memory staging)
+        const int grow = row_base + lane;
+        if (grow < M && n + 32 <= N && vec_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(out + static_cast<long long>(grow) * ld + n);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[q] = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+        }
+        return;
+    }
     const int sw = (lane >> 1) & 3;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -89,7 +98,7 @@ B200FM_DEVINL void stage_store_bf16(uint32_t* stg, int lane, const uint32_t (&p)
         const int rl = i * 8 + (lane >> 2), quad = lane & 3;
         const uint4 w = *reinterpret_cast<const uint4*>(stg + rl * 16 + 4 * (quad ^ ((rl >> 1) & 3)));
         const int grow = row_base + rl, gcol = n + quad * 8;
-        if (grow < M && gcol < N) {
+        if (grow < M && gcol < N && dbg != 3) {          // dbg 3 (measurement): staging traffic only, no global stores
             __nv_bfloat16* dst = out + static_cast<long long>(grow) * ld + gcol;
             if (vec_ok && gcol + 8 <= N) {
                 *reinterpret_cast<uint4*>(dst) = w;
@@ -316,9 +325,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                         const float2 ar = unpack_bf16x2(pa[j]), br = unpack_bf16x2(pb[j]);
                         pg[j] = pack_bf16x2(bf16_round(silu_f(ar.x)) * br.x, bf16_round(silu_f(ar.y)) * br.y);
                     }
-                    stage_store_bf16(stg_u, lane, pa, ab, args.ld0, row_base, n, M_, args.N, vec_ok);
-                    stage_store_bf16(stg_u, lane, pb, ab + args.n_half, args.ld0, row_base, n, M_, args.N, vec_ok);
-                    stage_store_bf16(stg_u, lane, pg, gg, args.ld1, row_base, n, M_, args.N, vec_ok);
+                    stage_store_bf16(stg_u, lane, pa, ab, args.ld0, row_base, n, M_, args.N, vec_ok, args.debug);
+                    stage_store_bf16(stg_u, lane, pb, ab + args.n_half, args.ld0, row_base, n, M_, args.N, vec_ok, args.debug);
+                    stage_store_bf16(stg_u, lane, pg, gg, args.ld1, row_base, n, M_, args.N, vec_ok, args.debug);
                 }
             } else {
                 const int n0 = n_blk * BN;
@@ -406,7 +415,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                             p[j] = pack_bf16x2(v0, v1);
                         }
                         const bool vec0 = (args.ld0 & 7) == 0;
-                        stage_store_bf16(stg_u, lane, p, reinterpret_cast<__nv_bfloat16*>(args.out0), args.ld0, row_base, n, M_, args.N, vec0);
+                        stage_store_bf16(stg_u, lane, p, reinterpret_cast<__nv_bfloat16*>(args.out0), args.ld0, row_base, n, M_, args.N, vec0, args.debug);
                         if constexpr (EPI == B200FM_EPI_GELU) {
                             uint32_t g[16];
 #pragma unroll

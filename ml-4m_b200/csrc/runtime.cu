@@ -23,6 +23,7 @@ static OptionSlot g_options[kOptCount] = {
     {"gemv_prefetch", "B200FM_GEMV_PREFETCH", 1, 1, false},    // gemv.cu: L2-prefetch the weight rows BEFORE waiting for the predecessor grid
     {"ln_fwd_v2", "B200FM_LN_FWD_V2", 0, 0, false},            // norm.cu: LayerNorm forward with gamma / beta in shared memory (4 CTAs per SM)
     {"gemm_debug", "B200FM_GEMM_DEBUG", 0, 0, false},          // MEASUREMENT ONLY (wrong results): 1 = GEMM epilogue stores nothing, 2 = epilogue skipped
+    {"comm_slim", "B200FM_COMM_SLIM", 0, 0, false},            // comm.cu: all-reduce CTAs of 128 threads / 64 registers, co-resident with the persistent kernels (no SM reservation)
 };
 
 int option(int id) {

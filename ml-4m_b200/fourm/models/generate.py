@@ -219,6 +219,11 @@ class GenerationSampler(nn.Module):
         self.rng_device = None       # None: random numbers on the tensors' device (the reference's behaviour); "cpu": host generator
         self.batch_cfg = True        # conditional + unconditional pass as one batch
         self.kv_cache = True         # K/V-cached autoregressive loop (falls back when the model has non-plain modules)
+        # The reference tests "every sequence holds an EOS" on the host after EVERY token (generate.py:1011-1013), which drains the GPU
+        # queue once per token.  Here the per-token flags stay on the device and are read every `eos_check_every` tokens; the sequence
+        # is then cut at the first token where the condition held, so the returned tokens are the reference's.  (The extra tokens drawn
+        # meanwhile advance the random stream; with rng_device = "cpu" -- the parity mode -- the check is per token like the reference's.)
+        self.eos_check_every = 8
 
     # ------------------------------------------------------------------ sampling
     def top_k_top_p_filtering(self, logits, top_k=0.0, top_p=0.0):
@@ -537,7 +542,9 @@ class GenerationSampler(nn.Module):
             dec_state = decode.CachedDecoder(model, ctx, enc_mask, seq_len + out.shape[1])
             for t in range(out.shape[1] - 1):                      # prime the cache with all but the last given token
                 dec_state.step((emb_mod.token_emb(out[:, t]) + y_emb[:, t]).repeat(k, 1))
-        for _ in range(seq_len):
+        check_every = 1 if self.rng_device == "cpu" else max(1, int(self.eos_check_every))
+        flags, flag_len = [], []
+        for step_i in range(seq_len):
             cur = out.shape[1]
             if cached:
                 h = dec_state.step((emb_mod.token_emb(out[:, -1]) + y_emb[:, cur - 1]).repeat(k, 1))
@@ -554,8 +561,15 @@ class GenerationSampler(nn.Module):
                 probs = F.softmax(self.top_k_top_p_filtering(last, top_k, top_p) / temperature, dim=-1)
                 nxt = self._multinomial(probs)[:, None]
             out = torch.cat((out, nxt.to(out.dtype)), dim=-1)
-            if use_eos and (out == eos_token).any(dim=-1).all():
-                break
+            if use_eos:
+                flags.append((out == eos_token).any(dim=-1).all())
+                flag_len.append(out.shape[1])
+                if len(flags) >= check_every or step_i == seq_len - 1:
+                    hit = torch.stack(flags).nonzero()             # one host read for the whole window
+                    if hit.numel() > 0:
+                        out = out[:, :flag_len[int(hit[0])]]       # the length at which the reference's per-token test fires
+                        break
+                    flags, flag_len = [], []
         return out, False
 
     def autoregressive_step_batched(self, mod_dict, target_mod, temperature, top_k: Union[float, int], top_p: float, use_eos=True,

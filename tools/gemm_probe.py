@@ -1,6 +1,7 @@
 """Where does the tcgen05 GEMM lose time at the 4M-B shapes?  Times each shape with the normal epilogue, with an epilogue that reads the
 accumulator but stores nothing (option gemm_debug = 1) and with the epilogue skipped entirely (= 2): the difference separates the cost of
-the mainloop (TMA + MMA) from TMEM read-out and from the staged global stores.  Rotating operand sets (> L2)."""
+the mainloop (TMA + MMA) from TMEM read-out and from the staged global stores; = 3 keeps the shared-memory staging but drops the global
+stores, = 4 stores straight from registers (bf16 epilogues only).  Rotating operand sets (> L2)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "ml-4m_b200"))
@@ -27,7 +28,7 @@ for name, layout, epi, m, n, k in SHAPES:
     flops = 2.0 * m * k * (2 * n if epi == ops.EPI_SWIGLU else n)
     outs = None
     res = []
-    for dbg in (0, 1, 2):
+    for dbg in (0, 1, 2, 3, 4):
         lib.set_option("gemm_debug", dbg)
         r = ops.gemm(As[0], Bs[0], layout=layout, epilogue=epi)
         o0, o1 = (r if isinstance(r, tuple) else (r, None))
@@ -41,4 +42,4 @@ for name, layout, epi, m, n, k in SHAPES:
         res.append(e0.elapsed_time(e1) / 40 * 1e3)
     lib.set_option("gemm_debug", 0)
     print(f"{name:16s} {m:6d}x{n:5d}x{k:5d}  normal {res[0]:7.1f} us ({flops / res[0] / 1e6:7.1f} TF/s)   no-store {res[1]:7.1f} us ({flops / res[1] / 1e6:7.1f})   "
-          f"no-epilogue {res[2]:7.1f} us ({flops / res[2] / 1e6:7.1f})")
+          f"no-epilogue {res[2]:7.1f} us ({flops / res[2] / 1e6:7.1f})   staging-only {res[3]:7.1f} us   direct-stg {res[4]:7.1f} us")
