@@ -105,11 +105,13 @@ def cpu_threads():
 
 def gemm_traffic_per_launch():
     """DRAM bytes (read + write) per GEMM launch of a 4M-B step, from the committed ncu capture (never measured in this process)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_step_traffic.json")) as f:
-            return float(json.load(f)["gemm"]["dram_bytes_per_launch"])
-    except (OSError, KeyError, ValueError):
-        return None
+    for name in ("r2_step_traffic.json", "r1_step_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return float(json.load(f)["gemm"]["dram_bytes_per_launch"]), name
+        except (OSError, KeyError, ValueError):
+            continue
+    return None, None
 
 
 def reference_tree():
@@ -553,8 +555,8 @@ def run_b200_arm(args):
                                   how=("the step's GEMM launch sequence replayed back to back (CUDA graph, PDL on), CUDA events around 5 replays"
                                        if gemm_graph_ms else "CUDA events around every launch (serialised)"),
                                   achieved_serialised=achieved, frac_serialised=achieved / peaks["bf16"], gemm_ms_per_step_replayed=gemm_graph_ms,
-                                  traffic=gemm_traffic_per_launch(),
-                                  traffic_unit="bytes/launch (dram read+write, ncu: profiles/r1_step_traffic.json)", peak_source=peaks["src"],
+                                  traffic=gemm_traffic_per_launch()[0],
+                                  traffic_unit=f"bytes/launch (dram read+write, ncu: profiles/{gemm_traffic_per_launch()[1]})", peak_source=peaks["src"],
                                   launches_per_step=n_gemm // 2, gemm_ms_per_step=gemm_ms / 2),
                     clocks=clocks)
         if cpu is not None:

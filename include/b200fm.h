@@ -42,7 +42,8 @@ int b200fm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, 
  * "gemm_cta_pairs" (1: cta_group::2 GEMM tiles), "ln_bwd_v2" (LayerNorm-backward variant 0..3; 3 = gamma in shared memory, 2 CTAs per SM), "ln_fwd_v2" (1: LayerNorm forward with gamma / beta in shared memory, 4 CTAs per SM), "sm_reserve" (0: number
  * of SMs the persistent GEMM grids leave free, for a concurrent gradient all-reduce kernel), "gemv" (1: NT problems with <= 8 rows --
  * the linears of the K/V-cached decode loop -- run on an HBM-bound weight-streaming kernel instead of a tcgen05 tile), "gemv_prefetch"
- * (1: that kernel pulls its weight rows into L2 before it waits for the preceding kernel of the stream), "gemm_debug" (measurement
+ * (1: that kernel pulls its weight rows into L2 before it waits for the preceding kernel of the stream), "gemm_tma_store" (1: bf16 GEMM outputs are written by TMA stores), "comm_slim" (1: the gradient all-reduce runs as many
+ * 128-thread CTAs co-resident with the compute kernels instead of a few wide ones on reserved SMs), "gemm_debug" (measurement
  * only, results are WRONG when non-zero: 1 = the GEMM epilogue reads the accumulator but stores nothing, 2 = no epilogue).  Changing an
  * option affects launches issued afterwards; meant for A/B measurements inside one process.                          */
 int b200fm_set_option(const char* name, int value);

@@ -508,12 +508,20 @@ ATTN_BWD_MAX_TOKENS = 256      # b200fm_attention_bwd: query / key tiles of one 
 
 
 def _check_trainable_length(ctx, Nq, Nk):
-    """The forward accepts longer sequences (attention_fwd_long, generation contexts) than the backward kernel: fail in the FORWARD of a
-    pass that records gradients, not half-way through backward()."""
-    if any(ctx.needs_input_grad) and max(Nq, Nk) > ATTN_BWD_MAX_TOKENS:
-        raise ValueError(f"attention over {Nq} queries x {Nk} keys cannot be trained on the B200 path: the backward kernel supports at most "
-                         f"{ATTN_BWD_MAX_TOKENS} tokens per side (encoder tokens + register tokens, decoder tokens); run it under torch.no_grad() "
-                         f"or lower num_encoder_tokens / num_decoder_tokens")
+    """The forward accepts longer sequences (attention_fwd_long, generation contexts) than the backward kernel.  A forward that records
+    gradients over such a sequence is legal as long as backward() is never called (generation code that forgets torch.no_grad()), so this
+    only WARNS -- once -- that a later backward() will be refused (b200fm_attention_bwd reports the supported range)."""
+    global _warned_long
+    if not _warned_long and any(ctx.needs_input_grad) and max(Nq, Nk) > ATTN_BWD_MAX_TOKENS:
+        _warned_long = True
+        import warnings
+        warnings.warn(f"attention over {Nq} queries x {Nk} keys is recorded for autograd, but the B200 backward kernel supports at most "
+                      f"{ATTN_BWD_MAX_TOKENS} tokens per side (encoder tokens + register tokens, decoder tokens): backward() through it "
+                      f"will raise.  Use torch.no_grad() for inference, or lower num_encoder_tokens / num_decoder_tokens for training.",
+                      RuntimeWarning, stacklevel=3)
+
+
+_warned_long = False
 
 
 class AttentionFn(torch.autograd.Function):

@@ -52,6 +52,7 @@ struct GemmArgs {
     // fused masked-token head (EPI_CE_STATS / EPI_CE_GRAD, fm.py:589-600): the logits tile never leaves the SM
     const long long* targets;     // int64 [M]
     const float* lse;             // EPI_CE_GRAD: fp32 [M] log-sum-exp of every row
+    int tma_store;                // bf16 outputs leave through TMA stores (tensor maps tmap_o0..2) instead of LDS + STG
     int debug;                    // option "gemm_debug" (measurement only): 1 = epilogue reads TMEM but stores nothing, 2 = epilogue skipped
 };
 
@@ -65,8 +66,10 @@ struct GemmSmem {
     static constexpr int kBBytes = CTA2 ? BN * 64 : BN * 128;
     static constexpr int kStageBytes = kBM * 128 + kBBytes;
     static constexpr int kStages = CTA2 ? (BN == 256 ? 5 : 6) : ((BN == 256) ? 3 : 5);
-    static constexpr int kBarBytes = 256;
-    static constexpr int kEpiStageBytes = 32 * 36 * 4;                        // per epilogue warp: 32 rows x (32 + 4 pad) fp32
+    static constexpr int kBarBytes = 1024;                                    // barriers + TMEM slot; keeps the staging area 1 KB aligned
+    // per epilogue warp: fp32 staging 32 rows x (32 + 4 pad) floats (4608 B) OR three 2 KB boxes (32 rows x 32 bf16, 64B-swizzled) that
+    // rotate as sources of TMA stores
+    static constexpr int kEpiStageBytes = 3 * 2048;
     static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 8 * kEpiStageBytes + 1024;   // +1024 alignment slack
 };
 
@@ -120,9 +123,32 @@ B200FM_DEVINL void stage_write_f32(float* stg, int lane, const uint32_t (&r)[32]
     __syncwarp();
 }
 
+// bf16 through the TMA: the warp writes its 32 x 32 tile (thread = row, 64 B) into a 2 KB box with the 64B-swizzle pattern (16-byte
+// chunk index ^ ((row >> 1) & 3): conflict-free for the row-wise writes), one lane issues the bulk tensor store.  Compared with
+// stage_store_bf16 the tile crosses the shared-memory / L1 data path twice (STS + TMA read) instead of three times (STS + LDS + STG) --
+// that path, not the tensor pipe, is what bounds this kernel (tools/gemm_probe.py) -- and rows / columns beyond the tensor are clipped
+// by the hardware.  Three boxes per warp rotate: a box is rewritten only after the store issued from it three stores ago has been read.
+B200FM_DEVINL void tma_stage_store_bf16(uint32_t* stg, uint32_t& box_i, int lane, const uint32_t (&p)[16], const CUtensorMap* map, int col, int row) {
+    uint32_t* buf = stg + (box_i % 3u) * 512u;
+    ++box_i;
+    if (lane == 0) tma_store_wait_read<2>();
+    __syncwarp();
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(buf + lane * 16 + 4 * (q ^ sw)) = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_2d(map, buf, col, row);
+        tma_store_commit();
+    }
+}
+
 template <int BN, int LAYOUT, int EPI, bool CTA2>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmArgs args) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_o0,
+            const __grid_constant__ CUtensorMap tmap_o1, const __grid_constant__ CUtensorMap tmap_o2, const GemmArgs args) {
     using SM = GemmSmem<BN, CTA2>;
     constexpr int kStages = SM::kStages;
     constexpr bool A_MN = (LAYOUT == LAYOUT_TN);
@@ -281,6 +307,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         int as = 0; uint32_t aphase = 0;
         const uint32_t tempty_leader0 = CTA2 ? mapa_u32(&tempty_bar[0], 0) : 0u;
         const uint32_t tempty_leader1 = CTA2 ? mapa_u32(&tempty_bar[1], 0) : 0u;
+        uint32_t box_i = 0;                                               // TMA-store boxes this warp has used (3 rotate)
         for (int tile = my_first; tile < num_tiles; tile += my_step) {
             const int mn = tile % num_mn;
             const int m_blk = (mn / args.num_n_blocks) * cta_stride + static_cast<int>(rank);
@@ -325,9 +352,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                         const float2 ar = unpack_bf16x2(pa[j]), br = unpack_bf16x2(pb[j]);
                         pg[j] = pack_bf16x2(bf16_round(silu_f(ar.x)) * br.x, bf16_round(silu_f(ar.y)) * br.y);
                     }
-                    stage_store_bf16(stg_u, lane, pa, ab, args.ld0, row_base, n, M_, args.N, vec_ok, args.debug);
-                    stage_store_bf16(stg_u, lane, pb, ab + args.n_half, args.ld0, row_base, n, M_, args.N, vec_ok, args.debug);
-                    stage_store_bf16(stg_u, lane, pg, gg, args.ld1, row_base, n, M_, args.N, vec_ok, args.debug);
+                    if (args.tma_store) {
+                        tma_stage_store_bf16(stg_u, box_i, lane, pa, &tmap_o0, n, row_base);
+                        tma_stage_store_bf16(stg_u, box_i, lane, pb, &tmap_o1, n, row_base);
+                        tma_stage_store_bf16(stg_u, box_i, lane, pg, &tmap_o2, n, row_base);
+                    } else {
+                        stage_store_bf16(stg_u, lane, pa, ab, args.ld0, row_base, n, M_, args.N, vec_ok, args.debug);
+                        stage_store_bf16(stg_u, lane, pb, ab + args.n_half, args.ld0, row_base, n, M_, args.N, vec_ok, args.debug);
+                        stage_store_bf16(stg_u, lane, pg, gg, args.ld1, row_base, n, M_, args.N, vec_ok, args.debug);
+                    }
                 }
             } else {
                 const int n0 = n_blk * BN;
@@ -415,7 +448,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                             p[j] = pack_bf16x2(v0, v1);
                         }
                         const bool vec0 = (args.ld0 & 7) == 0;
-                        stage_store_bf16(stg_u, lane, p, reinterpret_cast<__nv_bfloat16*>(args.out0), args.ld0, row_base, n, M_, args.N, vec0, args.debug);
+                        if (EPI == B200FM_EPI_BF16 && args.tma_store) tma_stage_store_bf16(stg_u, box_i, lane, p, &tmap_o0, n, row_base);
+                        else stage_store_bf16(stg_u, lane, p, reinterpret_cast<__nv_bfloat16*>(args.out0), args.ld0, row_base, n, M_, args.N, vec0, args.debug);
                         if constexpr (EPI == B200FM_EPI_GELU) {
                             uint32_t g[16];
 #pragma unroll
@@ -481,6 +515,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
+        if (lane == 0) tma_store_wait_read<0>();                          // the boxes must outlive the TMA's reads
     }
 
     tc_fence_before();
@@ -497,7 +532,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 static int sm_count() { return usable_sm_count(); }
 
 template <int BN, int LAYOUT, int EPI, bool CTA2>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap (&to)[3], const GemmArgs& a, cudaStream_t stream) {
     auto kern = gemm_kernel<BN, LAYOUT, EPI, CTA2>;
     constexpr int smem = GemmSmem<BN, CTA2>::kTotal;
     static bool configured = false;
@@ -508,10 +543,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
     const int units = (CTA2 ? (a.num_m_blocks + 1) / 2 : a.num_m_blocks) * a.num_n_blocks * a.k_splits;
     if constexpr (CTA2) {
         const int clusters = units < sm_count() / 2 ? units : sm_count() / 2;
-        B200FM_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(kGemmThreads), smem, stream, 2, ta, tb, a));
+        B200FM_CUDA(launch_pdl(kern, dim3(2 * clusters), dim3(kGemmThreads), smem, stream, 2, ta, tb, to[0], to[1], to[2], a));
     } else {
         const int grid = units < sm_count() ? units : sm_count();
-        B200FM_CUDA(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), smem, stream, 1, ta, tb, a));
+        B200FM_CUDA(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), smem, stream, 1, ta, tb, to[0], to[1], to[2], a));
     }
     B200FM_CUDA(cudaGetLastError());
     return 0;
@@ -636,12 +671,33 @@ static int gemm_impl(int layout, int epilogue, int M, int N, int K, const void* 
     }
     if (rc) return rc;
 
+    // bf16 outputs through TMA stores (EPI_BF16: out0; EPI_SWIGLU: a | b halves of out0 and the gate): 32 x 32 boxes, 64B swizzle.
+    // Not with a device-side row count (the hardware clips at the tensor's static bounds) nor with rows that are not 16-byte multiples.
+    CUtensorMap to[3] = {ta, ta, ta};
+    a.tma_store = 0;
+    if (option(kOptGemmTmaStore) != 0 && dyn_dev == nullptr && a.debug == 0 && (epilogue == B200FM_EPI_BF16 || epilogue == B200FM_EPI_SWIGLU) &&
+        (ld0 % 8) == 0 && (reinterpret_cast<uintptr_t>(out0) & 15) == 0) {
+        if (epilogue == B200FM_EPI_BF16) {
+            rc = make_tmap_2d_sw(&to[0], out0, TmapDtype::BF16, (uint64_t)N, (uint64_t)M, (uint64_t)ld0 * 2, 32, 32, 64);
+            if (rc) return rc;
+            a.tma_store = 1;
+        } else if ((ld1 % 8) == 0 && (reinterpret_cast<uintptr_t>(out1) & 15) == 0 && (N % 8) == 0) {
+            rc = make_tmap_2d_sw(&to[0], out0, TmapDtype::BF16, (uint64_t)N, (uint64_t)M, (uint64_t)ld0 * 2, 32, 32, 64);
+            if (rc) return rc;
+            rc = make_tmap_2d_sw(&to[1], reinterpret_cast<const __nv_bfloat16*>(out0) + N, TmapDtype::BF16, (uint64_t)N, (uint64_t)M, (uint64_t)ld0 * 2, 32, 32, 64);
+            if (rc) return rc;
+            rc = make_tmap_2d_sw(&to[2], out1, TmapDtype::BF16, (uint64_t)N, (uint64_t)M, (uint64_t)ld1 * 2, 32, 32, 64);
+            if (rc) return rc;
+            a.tma_store = 1;
+        }
+    }
+
     // CTA pairs whenever there are at least two 128-row blocks (a lone block would leave the peer CTA idle)
     // (BN == 256 only: the B tensor map's 128-row box is exactly one CTA's half of the tile)
     const bool pairs = use_cta_pairs() && a.num_m_blocks >= 2 && BN == 256;
 #define B200FM_GEMM_CASE(BN_, L_, E_)                                                                  \
     if (BN == BN_ && layout == L_ && epilogue == E_)                                                    \
-        return pairs ? launch_gemm<BN_, L_, E_, true>(ta, tb, a, stream) : launch_gemm<BN_, L_, E_, false>(ta, tb, a, stream);
+        return pairs ? launch_gemm<BN_, L_, E_, true>(ta, tb, to, a, stream) : launch_gemm<BN_, L_, E_, false>(ta, tb, to, a, stream);
     B200FM_GEMM_CASE(256, LAYOUT_NT, B200FM_EPI_BF16)
     B200FM_GEMM_CASE(128, LAYOUT_NT, B200FM_EPI_BF16)
     B200FM_GEMM_CASE(256, LAYOUT_NT, B200FM_EPI_F32)

@@ -22,6 +22,7 @@ static OptionSlot g_options[kOptCount] = {
     {"gemv", "B200FM_GEMV", 1, 1, false},                      // NT GEMMs with <= 8 rows run on the weight-streaming kernel (gemv.cu)
     {"gemv_prefetch", "B200FM_GEMV_PREFETCH", 1, 1, false},    // gemv.cu: L2-prefetch the weight rows BEFORE waiting for the predecessor grid
     {"ln_fwd_v2", "B200FM_LN_FWD_V2", 0, 0, false},            // norm.cu: LayerNorm forward with gamma / beta in shared memory (4 CTAs per SM)
+    {"gemm_tma_store", "B200FM_GEMM_TMA_STORE", 1, 1, false},  // gemm.cu: bf16 outputs leave through TMA stores (2 passes over the smem / L1 data path instead of 3)
     {"gemm_debug", "B200FM_GEMM_DEBUG", 0, 0, false},          // MEASUREMENT ONLY (wrong results): 1 = GEMM epilogue stores nothing, 2 = epilogue skipped
     {"comm_slim", "B200FM_COMM_SLIM", 0, 0, false},            // comm.cu: all-reduce CTAs of 128 threads / 64 registers, co-resident with the persistent kernels (no SM reservation)
 };
@@ -80,12 +81,19 @@ static EncodeTiledFn get_encode_fn() {
 
 int make_tmap_2d(CUtensorMap* out, const void* base, TmapDtype dt, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                  uint32_t box_inner, uint32_t box_outer, bool swizzle128) {
+    return make_tmap_2d_sw(out, base, dt, inner, outer, row_stride_bytes, box_inner, box_outer, swizzle128 ? 128 : 0);
+}
+
+int make_tmap_2d_sw(CUtensorMap* out, const void* base, TmapDtype dt, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                    uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
+    const bool swizzle128 = swizzle_bytes == 128;
     EncodeTiledFn fn = get_encode_fn();
     B200FM_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
     const uint32_t es = dt == TmapDtype::BF16 ? 2 : 4;
     B200FM_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer %p not 16-byte aligned", base);
     B200FM_CHECK(row_stride_bytes % 16 == 0, "TMA row stride %llu B not a multiple of 16", (unsigned long long)row_stride_bytes);
-    B200FM_CHECK(!swizzle128 || box_inner * es == 128, "128B swizzle needs a 128-byte inner box (got %u)", box_inner * es);
+    B200FM_CHECK(swizzle_bytes == 0 || swizzle_bytes == 64 || swizzle_bytes == 128, "TMA swizzle must be 0, 64 or 128 bytes");
+    B200FM_CHECK(swizzle_bytes == 0 || box_inner * es == (uint32_t)swizzle_bytes, "%dB swizzle needs a %d-byte inner box (got %u)", swizzle_bytes, swizzle_bytes, box_inner * es);
     B200FM_CHECK(box_inner <= 256 && box_outer <= 256, "TMA box dims must be <= 256");
     cuuint64_t dims[2] = {inner, outer};
     cuuint64_t strides[1] = {row_stride_bytes};
@@ -93,8 +101,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, TmapDtype dt, uint64_t inne
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(out, dt == TmapDtype::BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200FM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu stride=%llu box=%ux%u)",
                  (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes, box_inner,
                  box_outer);

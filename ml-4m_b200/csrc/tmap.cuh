@@ -14,6 +14,10 @@ enum class TmapDtype { BF16, F32 };
 int make_tmap_2d(CUtensorMap* out, const void* base, TmapDtype dt, uint64_t inner, uint64_t outer,
                  uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, bool swizzle128);
 
+// same with an explicit swizzle width in bytes (0, 64 or 128; box_inner * elem_size must equal it when non-zero)
+int make_tmap_2d_sw(CUtensorMap* out, const void* base, TmapDtype dt, uint64_t inner, uint64_t outer,
+                    uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
+
 // 3D tensor [d2, d1, inner] (inner contiguous; stride1/stride2 in bytes); box = [1, box_d1, box_inner].  Used for
 // [batch, tokens, features] activations so that rows past the end of one sample are zero-filled (never the next sample's).
 int make_tmap_3d(CUtensorMap* out, const void* base, TmapDtype dt, uint64_t inner, uint64_t d1, uint64_t d2,
