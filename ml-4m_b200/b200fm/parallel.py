@@ -134,16 +134,16 @@ class GradSync(torch.nn.Module):
         cuda = self.device.type == "cuda"
         if transport == "auto":
             transport = os.environ.get("B200FM_COMM", "p2p" if cuda and 2 <= self.world <= 8 else "collective")
-        # during backward the reductions have ~2/3 of a step to hide in: a few CTAs (= SMs taken from the GEMM grids) are enough.  The
-        # chunks that only become ready at the END of backward (embedding tables) are on the critical path: they get many CTAs, no
-        # compute kernel competes for the SMs at that point (AdamW of the early chunks is HBM-bound and shares them)
+        # Measured on 2 B200s (4M-B, profiles/r2_bench_2gpu_*.json): the reductions have 2/3 of a step to hide in, yet INSIDE the step the
+        # kernel runs several times slower than alone (the GEMMs saturate the L2 -> SM path), so the exposed time falls with the number of
+        # CTAs: wide 6 CTAs on reserved SMs 3.4 ms, wide 12: 1.5 ms, slim 48: 2.4 ms, slim 96: 1.0 ms, slim 128: 0.9 ms.
         # "slim" all-reduce CTAs (option comm_slim / B200FM_COMM_SLIM=1): 128 threads, <= 64 registers -- co-resident with the persistent
         # backward kernels instead of on SMs reserved for them; the bytes in flight come from the CTA count
         self.slim = cuda and transport == "p2p" and lib.get_option("comm_slim") != 0
         if n_ctas is None:
-            n_ctas = int(os.environ.get("B200FM_COMM_CTAS", "48" if self.slim else "6"))
+            n_ctas = int(os.environ.get("B200FM_COMM_CTAS", "128" if self.slim else "12"))
         if n_ctas_tail is None:
-            n_ctas_tail = int(os.environ.get("B200FM_COMM_CTAS_TAIL", "64"))
+            n_ctas_tail = int(os.environ.get("B200FM_COMM_CTAS_TAIL", "128" if self.slim else "64"))
         self.n_ctas, self.n_ctas_tail = n_ctas, max(n_ctas, n_ctas_tail)
         self.small_numel = small_numel
         self._layout(params, int(chunk_mb * (1 << 20) // 4))

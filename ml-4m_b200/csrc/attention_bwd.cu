@@ -31,12 +31,14 @@ struct AttnBwdSmem {
     static constexpr int kP = kKV + 2 * 32768;                          // 32 KB  [128 q][128 keys] bf16, two 64-key swizzle atoms
     static constexpr int kDS = kP + 32768;                              // 32 KB
     static constexpr int kBar = kDS + 32768;
-    static constexpr int kStage = kBar + 256;                           // 8 warps x 2 KB store staging
-    static constexpr int kTotal = kStage + 8 * 2048 + 1024;
+    static constexpr int kStage = kBar + 256;                           // math warps x 2 KB store staging
+    static constexpr int kTotal8 = kStage + 8 * 2048 + 1024;
+    static constexpr int kTotal16 = kStage + 16 * 2048 + 1024;
 };
 constexpr int kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
-constexpr int kBwdThreads = 320;       // warps 0-7: softmax-backward math + epilogues (lane quarter = warp & 3, column half = warp >> 2)
-constexpr int kBwdMathWarps = 8;       // warp 8: TMA producer + TMEM allocator, warp 9: MMA issuer
+// MW math warps (8 or 16: softmax-backward math + epilogues; lane quarter = warp & 3, key-column group = warp >> 2), then one TMA producer
+// / TMEM allocator warp and one MMA issuer warp.  The math warps are busy ~90 % of an item at low IPC (dependent TMEM-load -> exp2 -> STS
+// chains, ncu source page r2_attn2): MW = 16 halves the work per warp and doubles the warps the schedulers can switch between.
 
 struct AttnBwdArgs {
     const uint8_t* mask;
@@ -86,8 +88,8 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ out, long long ldo, const
     }
 }
 
-template <int NQT>
-__global__ void __launch_bounds__(kBwdThreads, 1)
+template <int NQT, int MW>
+__global__ void __launch_bounds__((MW + 2) * 32, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                      const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                      const AttnBwdArgs args) {
@@ -105,6 +107,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     uint64_t* dq_full = bars + 12;  uint64_t* dq_free = bars + 13;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
+    constexpr int kBwdMathWarps = MW;
+    constexpr int CPW = 16 / MW;                 // 32-key chunks of a 128-key tile per math warp: 4 chunks over MW / 4 column groups (2 or 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkt = args.nkt;
 
@@ -200,7 +204,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
     } else {
         // ------------------------------ math + epilogue warps 0..7 ------------------------------
-        const int quarter = warp & 3, half = warp >> 2;
+        const int quarter = warp & 3, cg = warp >> 2;          // cg: column group (CPW chunks of 32 keys)
         const int r = quarter * 32 + lane;                                  // query (or key) row inside the tile == TMEM lane
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         uint8_t* sP = smem + SM::kP;
@@ -242,12 +246,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     const float shift = row_ok ? (__log2f(inv) - m) : -INFINITY;
                     const float p_masked = (row_ok && m == kMaskedScore) ? inv : 0.f;
                     const float neg_ds = -D_[qt] * args.scale;                       // ds = p * (dp*scale - D*scale)
-                    uint32_t mb[2], tail[2];
-                    uint4 mra[2], mrb[2];
-                    bool mfast[2];
+                    uint32_t mb[CPW], tail[CPW];
+                    uint4 mra[CPW], mrb[CPW];
+                    bool mfast[CPW];
 #pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
-                        const int col0 = kt * 128 + (half * 2 + cc) * 32;
+                    for (int cc = 0; cc < CPW; ++cc) {
+                        const int col0 = kt * 128 + (cg * CPW + cc) * 32;
                         mfast[cc] = attn_mask_issue32(mrow, col0, args.Nk, mra[cc], mrb[cc], mb[cc]);   // loads in flight across the wait below
                         const int valid = args.Nk - col0;
                         tail[cc] = valid >= 32 ? 0u : (valid <= 0 ? 0xffffffffu : (0xffffffffu << valid));
@@ -255,11 +259,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     mbar_wait(sdp_full, stepc & 1);
                     tc_fence_after();
 #pragma unroll
-                    for (int cc = 0; cc < 2; ++cc)
+                    for (int cc = 0; cc < CPW; ++cc)
                         if (mfast[cc]) mb[cc] = attn_mask_bits_from_raw(mra[cc], mrb[cc]);
 #pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
-                        const int c = half * 2 + cc;                          // this warp's 32-key chunk of the 128-key tile
+                    for (int cc = 0; cc < CPW; ++cc) {
+                        const int c = cg * CPW + cc;                          // this warp's 32-key chunk of the 128-key tile
                         const int col0 = kt * 128 + c * 32;
                         uint32_t pk[16], dk_[16];
                         if (col0 < args.Nk) {
@@ -310,42 +314,47 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                     tc_fence_before();
                     mbar_arrive(pds_full);
                 }
-                // dV, dK of this key tile are complete: half 0 writes dV, half 1 writes dK (64 columns = 128 B per row each)
+                // dV, dK of this key tile are complete.  MW = 8: column group 0 writes dV, 1 writes dK (64 columns = 128 B per row each);
+                // MW = 16: groups 0, 1 write the two 32-column halves of dV, groups 2, 3 those of dK.
                 mbar_wait(dkv_full, kvc & 1);
                 tc_fence_after();
                 {
-                    uint32_t a0[32], a1[32];
-                    const int key = kt * 128 + r;
-                    const uint32_t col = half == 0 ? kColDV : kColDK;
-                    tmem_ld_x32(t_lane + col, a0);
-                    tmem_ld_x32(t_lane + col + 32, a1);
+                    constexpr int EC = MW == 8 ? 2 : 1;                        // 32-column pieces per warp
+                    const bool is_dv = MW == 8 ? cg == 0 : cg < 2;
+                    const int piece0 = MW == 8 ? 0 : (cg & 1);
+                    uint32_t a[EC][32];
+                    const uint32_t col = (is_dv ? kColDV : kColDK) + piece0 * 32;
+#pragma unroll
+                    for (int e = 0; e < EC; ++e) tmem_ld_x32(t_lane + col + e * 32, a[e]);
                     tmem_ld_wait();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(dkv_free);
-                    (void)key;
-                    __nv_bfloat16* base = (half == 0 ? args.dv + static_cast<long long>(b) * args.Nk * args.lddv
-                                                     : args.dk + static_cast<long long>(b) * args.Nk * args.lddk) + h * 64;
-                    const long long ld = half == 0 ? args.lddv : args.lddk;
-                    uint32_t pk[16];
-                    pack32(a0, pk);
-                    attn_stage_store32(stg, lane, pk, base, ld, kt * 128 + quarter * 32, args.Nk);
-                    pack32(a1, pk);
-                    attn_stage_store32(stg, lane, pk, base + 32, ld, kt * 128 + quarter * 32, args.Nk);
+                    __nv_bfloat16* base = (is_dv ? args.dv + static_cast<long long>(b) * args.Nk * args.lddv
+                                                 : args.dk + static_cast<long long>(b) * args.Nk * args.lddk) + h * 64 + piece0 * 32;
+                    const long long ld = is_dv ? args.lddv : args.lddk;
+#pragma unroll
+                    for (int e = 0; e < EC; ++e) {
+                        uint32_t pk[16];
+                        pack32(a[e], pk);
+                        attn_stage_store32(stg, lane, pk, base + e * 32, ld, kt * 128 + quarter * 32, args.Nk);
+                    }
                 }
             }
             if (item + static_cast<int>(gridDim.x) < args.num_items) prefetch_rows(item + gridDim.x);   // hidden behind the dQ epilogue
             mbar_wait(dq_full, it & 1);
             tc_fence_after();
+            if (cg < 2) {                                                    // two column groups write the 2 x 32 dQ columns
 #pragma unroll
-            for (int qt = 0; qt < NQT; ++qt) {
-                uint32_t a0[32];
-                tmem_ld_x32(t_lane + kColDQ + qt * 64 + half * 32, a0);       // each half writes 32 of the 64 dQ columns
-                tmem_ld_wait();
-                uint32_t pk[16];
-                pack32(a0, pk);
-                attn_stage_store32(stg, lane, pk, args.dq + static_cast<long long>(b) * args.Nq * args.lddq + h * 64 + half * 32, args.lddq,
-                                   qt * 128 + quarter * 32, args.Nq);
+                for (int qt = 0; qt < NQT; ++qt) {
+                    uint32_t a0[32];
+                    tmem_ld_x32(t_lane + kColDQ + qt * 64 + cg * 32, a0);
+                    tmem_ld_wait();
+                    uint32_t pk[16];
+                    pack32(a0, pk);
+                    attn_stage_store32(stg, lane, pk, args.dq + static_cast<long long>(b) * args.Nq * args.lddq + h * 64 + cg * 32, args.lddq,
+                                       qt * 128 + quarter * 32, args.Nq);
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -361,11 +370,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     }
 }
 
-template <int NQT>
+template <int NQT, int MW>
 static int launch_attn_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& tk, const CUtensorMap& tv,
                            const AttnBwdArgs& a, cudaStream_t stream) {
-    auto kern = attention_bwd_kernel<NQT>;
-    constexpr int smem = AttnBwdSmem<NQT>::kTotal;
+    auto kern = attention_bwd_kernel<NQT, MW>;
+    constexpr int smem = MW == 8 ? AttnBwdSmem<NQT>::kTotal8 : AttnBwdSmem<NQT>::kTotal16;
     static bool configured = false;
     if (!configured) {
         B200FM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -373,7 +382,7 @@ static int launch_attn_bwd(const CUtensorMap& tq, const CUtensorMap& tdo, const 
     }
     const int sms = usable_sm_count();
     const int grid = a.num_items < sms ? a.num_items : sms;
-    B200FM_LAUNCH(kern, dim3(grid), dim3(kBwdThreads), smem, stream, 1, tq, tdo, tk, tv, a);
+    B200FM_LAUNCH(kern, dim3(grid), dim3((MW + 2) * 32), smem, stream, 1, tq, tdo, tk, tv, a);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -418,5 +427,7 @@ extern "C" int b200fm_attention_bwd(const void* q, long long ldq, const void* k,
         if (blocks > 148 * 16) blocks = 148 * 16;
         B200FM_LAUNCH(attn_bwd_prep_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, 1, a.out, ldo, a.dout, lddo, dsum, B, H, Nq);
     }
-    return Nq <= 128 ? launch_attn_bwd<1>(tq, tdo, tk, tv, a, stream) : launch_attn_bwd<2>(tq, tdo, tk, tv, a, stream);
+    if (option(kOptAttnBwdWarps) == 16)
+        return Nq <= 128 ? launch_attn_bwd<1, 16>(tq, tdo, tk, tv, a, stream) : launch_attn_bwd<2, 16>(tq, tdo, tk, tv, a, stream);
+    return Nq <= 128 ? launch_attn_bwd<1, 8>(tq, tdo, tk, tv, a, stream) : launch_attn_bwd<2, 8>(tq, tdo, tk, tv, a, stream);
 }

@@ -22,7 +22,7 @@
 namespace b200fm {
 
 constexpr int kCommMaxWorld = 8;
-constexpr int kCommMaxCtas = 128;
+constexpr int kCommMaxCtas = 256;
 constexpr int kCommThreads = 512;
 // flag block layout (uint32): [phase 0|1][cta][src rank]
 constexpr int kCommFlagWords = 2 * kCommMaxCtas * kCommMaxWorld;

@@ -24,7 +24,8 @@ static OptionSlot g_options[kOptCount] = {
     {"ln_fwd_v2", "B200FM_LN_FWD_V2", 0, 0, false},            // norm.cu: LayerNorm forward with gamma / beta in shared memory (4 CTAs per SM)
     {"gemm_tma_store", "B200FM_GEMM_TMA_STORE", 1, 1, false},  // gemm.cu: bf16 outputs leave through TMA stores (2 passes over the smem / L1 data path instead of 3)
     {"gemm_debug", "B200FM_GEMM_DEBUG", 0, 0, false},          // MEASUREMENT ONLY (wrong results): 1 = GEMM epilogue stores nothing, 2 = epilogue skipped
-    {"comm_slim", "B200FM_COMM_SLIM", 0, 0, false},            // comm.cu: all-reduce CTAs of 128 threads / 64 registers, co-resident with the persistent kernels (no SM reservation)
+    {"comm_slim", "B200FM_COMM_SLIM", 1, 1, false},            // comm.cu: all-reduce CTAs of 128 threads / 64 registers, co-resident with the persistent kernels (no SM reservation); 0 = few 512-thread CTAs on reserved SMs
+    {"attn_bwd_warps", "B200FM_ATTN_BWD_WARPS", 8, 8, false},  // attention_bwd.cu: softmax-backward math warps per CTA (8 or 16)
 };
 
 int option(int id) {

@@ -109,7 +109,18 @@ def test_attention_fwd_full_size_cfg2():
 
 @pytest.mark.parametrize("B,H,Nq,Nk", [(2, 2, 128, 128), (3, 6, 128, 128), (2, 3, 100, 77), (1, 2, 24, 24), (2, 2, 256, 256), (2, 4, 200, 130)])
 @pytest.mark.parametrize("mk", ["none", "key", "dense"])
-def test_attention_bwd(B, H, Nq, Nk, mk):
+@pytest.mark.parametrize("math_warps", [8, 16])
+def test_attention_bwd(B, H, Nq, Nk, mk, math_warps):
+    """vs fp32 autograd of the materialised attention; both CTA shapes (option "attn_bwd_warps": 8 or 16 softmax-backward warps)."""
+    from b200fm import lib, ops
+    lib.set_option("attn_bwd_warps", math_warps)
+    try:
+        _attention_bwd_case(B, H, Nq, Nk, mk)
+    finally:
+        lib.set_option("attn_bwd_warps", 8)
+
+
+def _attention_bwd_case(B, H, Nq, Nk, mk):
     from b200fm import ops
     q, k, v = _inputs(B, H, Nq, Nk, 5, packed=False)
     mask = _mask(mk, B, Nq, Nk, 6)
