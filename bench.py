@@ -347,16 +347,11 @@ def run_b200_arm(args):
             opt.prepare_step()
         loss, mod_loss = net(batch, num_encoder_tokens=n_tok, num_decoder_tokens=n_tok, loss_type="mod")
         loss.backward()
-        if gsync is None:
-            grads = [p.grad for p in model.parameters() if p.grad is not None]
-            gnorm = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(grads)))   # logged grad norm (native_scaler.py:56-65)
-            opt.step()
-        else:
-            # AdamW of the early chunks runs while the last chunk is still being reduced; the logged norm (no clipping in the
-            # reference config: run_training_4m.py:102 clip_grad None) reads the averaged gradients afterwards
-            opt.step()
-            grads = [p.grad for p in model.parameters() if p.grad is not None]
-            gnorm = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(grads)))
+        # AdamW of the early chunks runs while the last chunk is still being reduced; the logged gradient norm (native_scaler.py:56-65; no
+        # clipping in the reference config: run_training_4m.py:102 clip_grad None) is accumulated by the AdamW kernels themselves
+        opt.track_grad_norm = True
+        opt.step()
+        gnorm = opt.grad_norm()
         opt.zero_grad(set_to_none=True)
         return loss, mod_loss, gnorm
 

@@ -104,6 +104,12 @@ int b200fm_headnorm_bwd(const void* dy, long long lddy, const void* x, long long
 int b200fm_attention_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                          const uint8_t* mask, long long mask_b_stride, long long mask_q_stride, void* out, long long ldo,
                          float* lse, int B, int H, int Nq, int Nk, float scale, void* stream);
+/* One query row per sequence (the attention calls of the K/V-cached decode step, generate.py:886-901): q bf16 [B, >= H*64], k / v
+ * bf16 rows [B*Nk, >= H*64] (e.g. the two column halves of a [B, Nk, 2D] cache), mask uint8 [B, Nk] (1 = masked, stride
+ * mask_b_stride; may be null), out bf16 [B, >= H*64].  Exact fp32 softmax; a fully masked row is uniform (masked_fill semantics). */
+int b200fm_attention_decode(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                            const uint8_t* mask, long long mask_b_stride, void* out, long long ldo, int B, int H, int Nk,
+                            float scale, void* stream);
 int b200fm_attention_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                          const uint8_t* mask, long long mask_b_stride, long long mask_q_stride, const void* out,
                          long long ldo, const void* dout, long long lddo, const float* lse, float* dsum_ws, void* dq,
@@ -164,6 +170,12 @@ int b200fm_adamw_chunk_elems(void);
 int b200fm_adamw_multi_dev(const b200fm_adamw_tensor* table_dev, const int* chunk_tensor_dev, const long long* chunk_offset_dev,
                            int n_chunks, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                            const float* hyper_dev, void* stream);
+/* Either of the two above (hyper_dev == NULL: lr / step as arguments) plus *gnorm_sq += sum of the squared scaled gradients of the
+ * group -- the gradient norm the reference logs (utils/native_scaler.py:56-65) without another pass over the gradients.  The caller
+ * zeroes *gnorm_sq once per step.                                                                                           */
+int b200fm_adamw_multi_gnorm(const b200fm_adamw_tensor* table_dev, const int* chunk_tensor_dev, const long long* chunk_offset_dev,
+                             int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                             const float* hyper_dev, float* gnorm_sq, void* stream);
 
 /* ---- modality-masked token selection + embedding gather / scatter ------------------------------------------------
  * Replaces cat_{encoder,decoder}_tensors + forward_mask_{encoder,decoder} + adapt_decoder_attention_mask
@@ -237,6 +249,12 @@ int b200fm_gather_i64(const int64_t* src, const int32_t* rows, int64_t* out, lon
 int b200fm_gather_rows_bf16_dyn(const void* src, const int32_t* rows, void* out, long long n, int D, const int* n_dev, void* stream);
 int b200fm_gather_i64_dyn(const int64_t* src, const int32_t* rows, int64_t* out, long long n, const int* n_dev, void* stream);
 int b200fm_scatter_rows_bf16_dyn(const void* src, const int32_t* rows, void* dst, long long n, int D, const int* n_dev, void* stream);
+/* Nucleus sampling of one token per row (generate.py:332-371 top_k_top_p_filtering + softmax(. / temperature) + multinomial, per
+ * generated token): logits fp32 [rows, V] (row stride ld), u fp32 [rows] uniform in [0, 1) from the caller's generator, out int64 [rows].
+ * Keeps token i iff the probability mass ranked strictly before it is <= top_p (the reference's rule; top_p <= 0 or >= 1: all tokens),
+ * then draws from softmax(kept / temperature) by inverse CDF in index order.  temperature > 0.                          */
+int b200fm_sample_top_p(const float* logits, long long ld, int rows, int V, float top_p, float temperature, const float* u,
+                        int64_t* out, void* stream);
 /* K/V cache append of the decode loop (replaces the growing torch.cat of generate.py's per-token forward): cache bf16 [B, L, row_w];
  * cache[b, *pos_dev, col0 : col0 + width] = src[b, 0 : width] (src bf16 [B, >= width], row stride ld_src).  *pos_dev int64 on the device. */
 int b200fm_kv_append(const void* src, long long ld_src, void* cache, long long L, long long row_w, const int64_t* pos_dev, int B,

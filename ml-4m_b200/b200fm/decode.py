@@ -134,13 +134,13 @@ class CachedDecoder:
             else:
                 ops.kv_append(qkv[:, D:], cache, self.pos_dev, 0)                 # k | v are adjacent in the qkv row
             c2 = cache.view(B * L, 2 * D)
-            o, _ = ops.attention_fwd(q, c2[:, :D], c2[:, D:], B, H, 1, L, self.sa_mask, sa.scale)
+            o = ops.attention_decode(q, c2[:, :D], c2[:, D:], B, H, L, self.sa_mask, sa.scale)
             x = _lin_resid(sa.proj, o, x)                                         # x + proj(o): the add is the GEMM's epilogue
             q = _lin(xa.q, _ln(blk.query_norm, x))
             if hasattr(xa, "q_norm"):
                 q = BF.head_norm(q, H, xa.q_norm)
             kv = self.kv_ctx[li]
-            o, _ = ops.attention_fwd(q, kv[:, :D], kv[:, D:], B, H, 1, self.N, self.enc_mask, xa.scale)
+            o = ops.attention_decode(q, kv[:, :D], kv[:, D:], B, H, self.N, self.enc_mask, xa.scale)
             x = _lin_resid(xa.proj, o, x)
             h = _ln(blk.norm2, x)
             mlp = blk.mlp

@@ -54,11 +54,10 @@ class GraphedTrainStep:
         loss, mod_loss = self.net(batch, num_encoder_tokens=self.N, num_decoder_tokens=self.M, loss_type=self.loss_type)
         loss.backward()
         BF.join_side_wgrad()            # (weight-gradient GEMMs that ran on the side stream, see functional._tn_gemm)
+        # the logged gradient norm (native_scaler.py:56-65) of the averaged gradients: accumulated by the AdamW kernels while they read them
+        self.opt.track_grad_norm = bool(self.want_norm)
         self.opt.step()
-        gnorm = None
-        if self.want_norm:           # the logged gradient norm (native_scaler.py:56-65), read after the averaged gradients are final
-            grads = [p.grad for p in self._params() if p.grad is not None]
-            gnorm = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(grads)))
+        gnorm = self.opt.grad_norm() if self.want_norm else None
         self.opt.zero_grad(set_to_none=True)
         return loss.detach(), {k: v.detach() for k, v in mod_loss.items()}, gnorm
 

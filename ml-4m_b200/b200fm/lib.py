@@ -71,6 +71,7 @@ SIGNATURES = {
                              c_void_p, c_void_p, c_ll, c_float, c_void_p, c_void_p, c_int, c_void_p],
     "b200fm_cross_entropy_dyn": [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p],
     "b200fm_masked_mean": [c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p],
+    "b200fm_adamw_multi_gnorm": [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_void_p, c_void_p, c_void_p],
     "b200fm_adamw_multi_dev": [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p],
     "b200fm_select_plan_ordered": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p],
@@ -83,6 +84,8 @@ SIGNATURES = {
                              c_float, c_void_p],
     "b200fm_mask_images": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "b200fm_patchify_u8": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "b200fm_attention_decode": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_float, c_void_p],
+    "b200fm_sample_top_p": [c_void_p, c_ll, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p],
     "b200fm_kv_append": [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_int, c_int, c_int, c_void_p],
     "b200fm_head_ce_ws_slots": [c_int],
     "b200fm_head_ce": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -216,6 +216,20 @@ def attention_fwd(q, k, v, B, H, Nq, Nk, mask=None, scale=None):
     return out, stats
 
 
+def attention_decode(q, k, v, B, H, Nk, mask=None, scale=None):
+    """One query row per sequence: q bf16 [B, >=H*64], k / v bf16 [B*Nk, >=H*64] row views, mask bool / uint8 [B|1, 1, Nk] (True =
+    masked) -> out bf16 [B, H*64] (b200fm_attention_decode: plain-load kernel, exact fp32 softmax)."""
+    _need_cuda(q, k, v, mask)
+    for t in (q, k, v):
+        assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1
+    scale = 64 ** -0.5 if scale is None else scale
+    out = torch.empty(B, H * 64, device=q.device, dtype=torch.bfloat16)
+    mk, mp, mbs, _ = _mask_args(mask, B, 1, Nk)
+    lib.call("b200fm_attention_decode", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), mp, mbs, _ptr(out), out.stride(0),
+             B, H, Nk, float(scale), _stream())
+    return out
+
+
 def attention_bwd(q, k, v, out, dout, stats, B, H, Nq, Nk, mask=None, scale=None, dq=None, dk=None, dv=None):
     """Gradients w.r.t. q, k, v (bf16).  dq/dk/dv may be pre-allocated views (e.g. column slices of a packed dqkv)."""
     _need_cuda(q, k, v, out, dout, stats, mask)
@@ -276,6 +290,16 @@ def cross_entropy_dyn(logits, targets, n_dev, want_grad=True):
     lib.call("b200fm_cross_entropy_dyn", _ptr(logits), logits.stride(0), _ptr(targets), _ptr(loss), _ptr(dl), dl.stride(0) if want_grad else 0,
              n, V, n_dev.data_ptr(), _stream())
     return loss, dl
+
+
+def sample_top_p(logits, top_p, temperature, u):
+    """One nucleus-sampled token per row: logits fp32 [R, V] (unit inner stride), u fp32 [R] uniform in [0, 1) -> int64 [R]."""
+    _need_cuda(logits, u)
+    assert logits.dtype == torch.float32 and logits.dim() == 2 and logits.stride(1) == 1 and u.dtype == torch.float32 and u.is_contiguous()
+    R, V = logits.shape
+    out = torch.empty(R, device=logits.device, dtype=torch.int64)
+    lib.call("b200fm_sample_top_p", _ptr(logits), logits.stride(0), R, V, float(top_p), float(temperature), _ptr(u), _ptr(out), _stream())
+    return out
 
 
 def kv_append(src, cache, pos_dev, col0=0):

@@ -23,6 +23,10 @@ class FusedAdamW(torch.optim.Optimizer):
         self._chunk = None
         self._tables = {}       # group index -> dict(device table, chunk maps, pinned staging ring)
         self.pre_group_hook = None   # callable(params): e.g. GradSync.wait -- make the stream wait for this group's reduced gradients
+        # track_grad_norm: the AdamW kernels also accumulate sum(g^2) of everything they update (stragglers on the single-tensor kernel
+        # excluded); `grad_norm()` is the global L2 norm of the gradients of the last step() -- what run_training_4m.py logs -- for free
+        self.track_grad_norm = False
+        self._gnorm_sq = None
 
     def _group_tables(self, gi, tensors):
         """Device-side pointer table + CTA->chunk maps for one param group.  The chunk maps depend on the tensor sizes only
@@ -90,6 +94,14 @@ class FusedAdamW(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        gn = None
+        if self.track_grad_norm:
+            dev = next((p.device for g in self.param_groups for p in g["params"] if p.grad is not None), None)
+            if dev is not None:
+                if self._gnorm_sq is None or self._gnorm_sq.device != dev:
+                    self._gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
+                self._gnorm_sq.zero_()
+                gn = self._gnorm_sq
         for gi, group in enumerate(self.param_groups):
             b1, b2 = group["betas"]
             if self.pre_group_hook is not None:
@@ -130,19 +142,39 @@ class FusedAdamW(torch.optim.Optimizer):
                 if gi not in self._hyper:
                     raise RuntimeError("FusedAdamW(capturable=True): call prepare_step() before step()")
                 ent = self._group_tables(gi, tensors)
-                lib.call("b200fm_adamw_multi_dev", ent["table"].data_ptr(), ent["ct"].data_ptr(), ent["co"].data_ptr(), ent["n_chunks"], float(b1),
-                         float(b2), float(group["eps"]), float(group["weight_decay"]), float(grad_scale), self._hyper[gi].data_ptr(), ops._stream())
+                if gn is not None:
+                    lib.call("b200fm_adamw_multi_gnorm", ent["table"].data_ptr(), ent["ct"].data_ptr(), ent["co"].data_ptr(), ent["n_chunks"], 0.0, float(b1),
+                             float(b2), float(group["eps"]), float(group["weight_decay"]), 1, float(grad_scale), self._hyper[gi].data_ptr(), gn.data_ptr(),
+                             ops._stream())
+                else:
+                    lib.call("b200fm_adamw_multi_dev", ent["table"].data_ptr(), ent["ct"].data_ptr(), ent["co"].data_ptr(), ent["n_chunks"], float(b1),
+                             float(b2), float(group["eps"]), float(group["weight_decay"]), float(grad_scale), self._hyper[gi].data_ptr(), ops._stream())
             elif tensors:
                 ent = self._group_tables(gi, tensors)
-                lib.call("b200fm_adamw_multi", ent["table"].data_ptr(), ent["ct"].data_ptr(), ent["co"].data_ptr(), ent["n_chunks"], float(group["lr"]),
-                         float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), int(step_no), float(grad_scale),
-                         ops._stream())
+                if gn is not None:
+                    lib.call("b200fm_adamw_multi_gnorm", ent["table"].data_ptr(), ent["ct"].data_ptr(), ent["co"].data_ptr(), ent["n_chunks"], float(group["lr"]),
+                             float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), int(step_no), float(grad_scale), None, gn.data_ptr(),
+                             ops._stream())
+                else:
+                    lib.call("b200fm_adamw_multi", ent["table"].data_ptr(), ent["ct"].data_ptr(), ent["co"].data_ptr(), ent["n_chunks"], float(group["lr"]),
+                             float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), int(step_no), float(grad_scale),
+                             ops._stream())
             for p, view in extra_casts:          # a weight mirrored in more than one operand buffer
                 ops.cast_bf16(p.data, view)
             # the kernels wrote through raw pointers: bump the version counters (other version-keyed caches must notice) and
             # re-stamp the bf16 mirrors that were refreshed in the same pass
             BF.mark_updated(updated)
         return loss
+
+
+def _fused_grad_norm(self):
+    """Global L2 norm of the (scaled) gradients the last step() consumed, as a 0-d device tensor (track_grad_norm=True)."""
+    if self._gnorm_sq is None:
+        raise RuntimeError("FusedAdamW.grad_norm(): set track_grad_norm = True before step()")
+    return self._gnorm_sq.sqrt().reshape(())
+
+
+FusedAdamW.grad_norm = _fused_grad_norm
 
 
 def param_groups_like_reference(model, weight_decay=0.05):

@@ -220,8 +220,9 @@ constexpr int kMtChunk = 8192;      // elements per CTA (256 threads x 8 float4)
 __global__ void __launch_bounds__(256)
 adamw_multi_kernel(const b200fm_adamw_tensor* __restrict__ table, const int* __restrict__ chunk_tensor,
                    const long long* __restrict__ chunk_offset, float lr, float beta1, float beta2, float eps, float wd, float bc1,
-                   float bc2_sqrt, float grad_scale, const float* __restrict__ hyper_dev) {
+                   float bc2_sqrt, float grad_scale, const float* __restrict__ hyper_dev, float* __restrict__ gnorm_sq) {
     pdl_enter();
+    float gsq = 0.f;                 // sum of squared (scaled) gradients this thread touched: the logged gradient norm for free
     if (hyper_dev != nullptr) {      // captured in a CUDA graph: the per-step scalars live in device memory {lr, 1 - b1^t, sqrt(1 - b2^t)}
         lr = __ldg(hyper_dev); bc1 = __ldg(hyper_dev + 1); bc2_sqrt = __ldg(hyper_dev + 2);
     }
@@ -242,6 +243,7 @@ adamw_multi_kernel(const b200fm_adamw_tensor* __restrict__ table, const int* __r
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float gi = gg[e] * grad_scale;
+                gsq = fmaf(gi, gi, gsq);
                 mm[e] = beta1 * mm[e] + ob1 * gi;
                 vv[e] = beta2 * vv[e] + ob2 * gi * gi;
                 pp[e] = pp[e] * decay - step * (mm[e] / (sqrtf(vv[e]) / bc2_sqrt + eps));
@@ -251,6 +253,7 @@ adamw_multi_kernel(const b200fm_adamw_tensor* __restrict__ table, const int* __r
         }
         for (long long i = e4 + threadIdx.x; i < end; i += 256) {
             const float gi = g[i] * grad_scale;
+            gsq = fmaf(gi, gi, gsq);
             const float mi = beta1 * m[i] + ob1 * gi, vi = beta2 * v[i] + ob2 * gi * gi;
             const float pi = p[i] * decay - step * (mi / (sqrtf(vi) / bc2_sqrt + eps));
             p[i] = pi; m[i] = mi; v[i] = vi;
@@ -259,11 +262,19 @@ adamw_multi_kernel(const b200fm_adamw_tensor* __restrict__ table, const int* __r
     } else {
         for (long long i = off + threadIdx.x; i < end; i += 256) {
             const float gi = g[i] * grad_scale;
+            gsq = fmaf(gi, gi, gsq);
             const float mi = beta1 * m[i] + ob1 * gi, vi = beta2 * v[i] + ob2 * gi * gi;
             const float pi = p[i] * decay - step * (mi / (sqrtf(vi) / bc2_sqrt + eps));
             p[i] = pi; m[i] = mi; v[i] = vi;
             if (shadow) shadow[i] = __float2bfloat16_rn(pi);
         }
+    }
+    if (gnorm_sq != nullptr) {       // one atomic per CTA (order-dependent in the last bits: a logged quantity)
+        __shared__ float red[8];
+        gsq = warp_sum(gsq);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = gsq;
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(gnorm_sq, ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7])));
     }
 }
 
@@ -281,7 +292,7 @@ extern "C" int b200fm_adamw_multi(const b200fm_adamw_tensor* table_dev, const in
     const float bc1 = 1.0f - powf(beta1, (float)step);
     const float bc2s = sqrtf(1.0f - powf(beta2, (float)step));
     B200FM_LAUNCH(adamw_multi_kernel, dim3(n_chunks), dim3(256), 0, stream, 1, table_dev, chunk_tensor_dev, chunk_offset_dev, lr, beta1, beta2, eps, weight_decay, bc1,
-                                                   bc2s, grad_scale, static_cast<const float*>(nullptr));
+                                                   bc2s, grad_scale, static_cast<const float*>(nullptr), static_cast<float*>(nullptr));
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -293,7 +304,24 @@ extern "C" int b200fm_adamw_multi_dev(const b200fm_adamw_tensor* table_dev, cons
     if (n_chunks == 0) return 0;
     B200FM_CHECK(table_dev && chunk_tensor_dev && chunk_offset_dev && hyper_dev, "adamw_multi_dev: null pointer");
     B200FM_LAUNCH(adamw_multi_kernel, dim3(n_chunks), dim3(256), 0, stream, 1, table_dev, chunk_tensor_dev, chunk_offset_dev, 0.f, beta1, beta2, eps, weight_decay, 1.f,
-                                                   1.f, grad_scale, hyper_dev);
+                                                   1.f, grad_scale, hyper_dev, static_cast<float*>(nullptr));
+    B200FM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// As adamw_multi (hyper_dev == nullptr: lr / step given here) or adamw_multi_dev (hyper_dev != nullptr), and *gnorm_sq += sum of the squared
+// (scaled) gradients of the group: the gradient norm the training loop logs (native_scaler.py:56-65) without a separate pass over the gradients.
+extern "C" int b200fm_adamw_multi_gnorm(const b200fm_adamw_tensor* table_dev, const int* chunk_tensor_dev, const long long* chunk_offset_dev,
+                                        int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                                        const float* hyper_dev, float* gnorm_sq, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (n_chunks == 0) return 0;
+    B200FM_CHECK(table_dev && chunk_tensor_dev && chunk_offset_dev && gnorm_sq, "adamw_multi_gnorm: null pointer");
+    B200FM_CHECK(hyper_dev != nullptr || step >= 1, "adamw_multi_gnorm: step must be >= 1");
+    const float bc1 = hyper_dev ? 1.f : 1.0f - powf(beta1, (float)step);
+    const float bc2s = hyper_dev ? 1.f : sqrtf(1.0f - powf(beta2, (float)step));
+    B200FM_LAUNCH(adamw_multi_kernel, dim3(n_chunks), dim3(256), 0, stream, 1, table_dev, chunk_tensor_dev, chunk_offset_dev, lr, beta1, beta2, eps, weight_decay, bc1,
+                                                   bc2s, grad_scale, hyper_dev, gnorm_sq);
     B200FM_CUDA(cudaGetLastError());
     return 0;
 }

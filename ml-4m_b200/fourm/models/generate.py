@@ -224,6 +224,10 @@ class GenerationSampler(nn.Module):
         # is then cut at the first token where the condition held, so the returned tokens are the reference's.  (The extra tokens drawn
         # meanwhile advance the random stream; with rng_device = "cpu" -- the parity mode -- the check is per token like the reference's.)
         self.eos_check_every = 8
+        # AR sampling at temperature > 0 with top_k = 0: one fused kernel (b200fm_sample_top_p: nucleus cut by bisection + inverse-CDF draw
+        # from a torch.rand number) instead of sort / cumsum / scatter / 2 softmaxes / multinomial per token.  Same distribution, a different
+        # use of the random stream; rng_device = "cpu" (the parity mode) keeps the reference's torch calls.
+        self.fused_sampling = True
 
     # ------------------------------------------------------------------ sampling
     def top_k_top_p_filtering(self, logits, top_k=0.0, top_p=0.0):
@@ -557,6 +561,9 @@ class GenerationSampler(nn.Module):
             last = logits[0] if k == 1 else logits[-1] + sum(w * (logits[i] - logits[-1]) for i, w in enumerate(weights))
             if np.isclose(temperature, 0, atol=1e-10):
                 nxt = torch.argmax(last, dim=-1, keepdim=True)
+            elif self.fused_sampling and last.is_cuda and self.rng_device != "cpu" and not top_k > 0.0 and last.shape[-1] <= 51200:
+                from b200fm import ops
+                nxt = ops.sample_top_p(last.float().contiguous(), top_p, temperature, torch.rand(last.shape[0], device=last.device))[:, None]
             else:
                 probs = F.softmax(self.top_k_top_p_filtering(last, top_k, top_p) / temperature, dim=-1)
                 nxt = self._multinomial(probs)[:, None]

@@ -137,3 +137,32 @@ def _attention_bwd_case(B, H, Nq, Nk, mk):
         err = (got.float().cpu() - ref).abs().max().item()
         scale = ref.abs().max().item() + 1e-6
         assert err <= 3e-2 * scale + 2e-2, f"{name}: max err {err} vs scale {scale}"
+
+
+@pytest.mark.parametrize("B,H,Nk", [(2, 4, 1), (2, 32, 256), (3, 6, 77), (1, 12, 1500), (2, 2, 13000)])
+@pytest.mark.parametrize("mk", ["none", "key", "all"])
+def test_attention_decode_single_query(B, H, Nk, mk):
+    """b200fm_attention_decode (one query row per sequence: the attention of the K/V-cached decode step) vs fp32 torch on the same bf16
+    operands, K / V as the two column halves of a [B, Nk, 2D] cache, key masks incl. a fully masked row (uniform weights)."""
+    from b200fm import ops
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + Nk)
+    D = H * 64
+    q = torch.randn(B, D, device="cuda", generator=g).bfloat16()
+    cache = torch.randn(B, Nk, 2 * D, device="cuda", generator=g).bfloat16()
+    mask = None
+    if mk == "key":
+        mask = torch.rand(B, 1, Nk, device="cuda", generator=g) < 0.3
+        mask[:, :, 0] = False
+    elif mk == "all":
+        mask = torch.ones(B, 1, Nk, dtype=torch.bool, device="cuda")
+        mask[0] = torch.rand(1, Nk, device="cuda", generator=g) < 0.5
+    c2 = cache.view(B * Nk, 2 * D)
+    out = ops.attention_decode(q, c2[:, :D], c2[:, D:], B, H, Nk, mask, 0.125)
+    qf = q.float().view(B, H, 1, 64)
+    kf = cache[:, :, :D].float().view(B, Nk, H, 64).permute(0, 2, 1, 3)
+    vf = cache[:, :, D:].float().view(B, Nk, H, 64).permute(0, 2, 1, 3)
+    s = (qf @ kf.transpose(-1, -2)) * 0.125
+    if mask is not None:
+        s = s.masked_fill(mask[:, None], -torch.finfo(torch.float32).max)
+    ref = (torch.softmax(s, -1) @ vf).permute(0, 2, 1, 3).reshape(B, D)
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)

@@ -139,3 +139,31 @@ def test_generate_end_to_end_runs_and_is_deterministic(gen):
         sampler.batch_cfg = True
     agree = float((a['tok_normal@224']['tensor'] == c['tok_normal@224']['tensor']).float().mean())
     assert agree >= 0.9
+
+
+def test_fused_nucleus_sampling_matches_reference_rule():
+    """b200fm_sample_top_p vs the torch restatement of the reference's rule (generate.py:332-371): (1) the sampled token always lies in
+    the reference's nucleus, (2) with u swept over [0, 1) the empirical distribution equals softmax(filtered / T) (total variation),
+    (3) top_p = 0 keeps everything, a peaked row returns its arg-max."""
+    from b200fm import ops
+    from fourm.models.generate import GenerationSampler
+    g = torch.Generator(device="cuda").manual_seed(0)
+    flt = GenerationSampler.top_k_top_p_filtering
+    for V, top_p, T in ((1000, 0.8, 1.0), (30000, 0.8, 0.7), (133, 0.5, 1.3), (8192, 0.0, 1.0), (50000, 0.95, 1.0)):
+        logits = torch.randn(4, V, device="cuda", generator=g) * 2.5
+        filt = flt(None, logits.clone(), 0.0, top_p)
+        ref_p = torch.softmax(filt / T, dim=-1)
+        n = 4000
+        u = (torch.arange(n, device="cuda", dtype=torch.float32) + 0.5) / n            # a stratified sweep of the unit interval
+        for r in range(2):
+            row = logits[r:r + 1].expand(n, V).contiguous()
+            tok = ops.sample_top_p(row, top_p, T, u)
+            assert bool((ref_p[r][tok] > 0).all()), "sampled a token outside the reference's nucleus"
+            emp = torch.bincount(tok, minlength=V).float() / n
+            tv = 0.5 * float((emp - ref_p[r]).abs().sum())
+            assert tv <= 0.03 + 1.5 * (float((ref_p[r] > 0).sum()) / n) ** 0.5 * 0.5, (V, top_p, tv)
+    peaked = torch.full((2, 500), -5.0, device="cuda")
+    peaked[0, 17] = 30.0
+    peaked[1, 499] = 30.0
+    tok = ops.sample_top_p(peaked, 0.8, 1.0, torch.tensor([0.3, 0.999], device="cuda"))
+    assert tok.tolist() == [17, 499]

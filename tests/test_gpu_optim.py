@@ -41,6 +41,30 @@ def test_fused_adamw_matches_torch(wd):
     assert BF.weight_bf16(ours[0]).data_ptr() == shadow.data_ptr()
 
 
+@pytest.mark.parametrize("capturable", [False, True])
+def test_fused_adamw_tracks_gradient_norm(capturable):
+    """track_grad_norm: the AdamW kernels accumulate sum(g^2) of the gradients they consume; grad_norm() equals the global L2 norm the
+    training loop logs (utils/native_scaler.py:56-65), with the same parameter update as without tracking."""
+    from b200fm.optim import FusedAdamW
+    dev = torch.device("cuda")
+    a, b = _params(dev, 3), _params(dev, 3)
+    oa = FusedAdamW([dict(params=a[:4]), dict(params=a[4:], weight_decay=0.0)], lr=1e-3, betas=(0.9, 0.95), capturable=capturable)
+    ob = FusedAdamW([dict(params=b[:4]), dict(params=b[4:], weight_decay=0.0)], lr=1e-3, betas=(0.9, 0.95), capturable=capturable)
+    oa.track_grad_norm = True
+    g = torch.Generator().manual_seed(4)
+    for step in range(3):
+        for x, y in zip(a, b):
+            gr = torch.randn(x.shape, generator=g).to(dev) * (step + 1)
+            x.grad, y.grad = gr.clone(), gr.clone()
+        want = torch.linalg.vector_norm(torch.stack(torch._foreach_norm([x.grad for x in a])))
+        if capturable:
+            oa.prepare_step(); ob.prepare_step()
+        oa.step(); ob.step()
+        torch.testing.assert_close(oa.grad_norm(), want, rtol=1e-5, atol=0)
+    for x, y in zip(a, b):
+        assert torch.equal(x.data, y.data)
+
+
 def test_fused_adamw_grad_scale():
     from b200fm.optim import FusedAdamW
     dev = torch.device("cuda")
