@@ -66,24 +66,43 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ out, long long ldo, const
     pdl_enter();
     const long long total = static_cast<long long>(B) * Nq * H;
     const int sub = threadIdx.x & 7;
-    for (long long g = (blockIdx.x * 256ll + threadIdx.x) >> 3; g < total; g += (gridDim.x * 256ll) >> 3) {
-        const int h = static_cast<int>(g % H);
-        const long long row = g / H;                       // b * Nq + q
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(out + row * ldo + h * 64) + sub);
-        const uint4 d = __ldg(reinterpret_cast<const uint4*>(dout + row * lddo + h * 64) + sub);
-        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
-        float acc = 0.f;
+    const long long stride = (gridDim.x * 256ll) >> 3;
+    constexpr int U = 4;                                   // groups per thread in flight: 8 independent 16-byte loads
+    // the loop condition is warp-uniform (first group of the warp): the full-mask shuffles below need all 32 lanes in the loop
+    for (long long gw = (blockIdx.x * 256ll + (threadIdx.x & ~31)) >> 3; gw < total; gw += U * stride) {
+        const long long g0 = gw + ((threadIdx.x & 31) >> 3);
+        uint4 a[U], d[U];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float2 x = unpack_bf16x2(aw[e]), y = unpack_bf16x2(dw[e]);
-            acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
+        for (int u = 0; u < U; ++u) {
+            const long long g = g0 + u * stride;
+            if (g < total) {
+                const int h = static_cast<int>(g % H);
+                const long long row = g / H;                   // b * Nq + q
+                a[u] = __ldg(reinterpret_cast<const uint4*>(out + row * ldo + h * 64) + sub);
+                d[u] = __ldg(reinterpret_cast<const uint4*>(dout + row * lddo + h * 64) + sub);
+            }
         }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-        if (sub == 0) {
-            const long long b = row / Nq, q = row % Nq;
-            dsum[(b * H + h) * Nq + q] = acc;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long g = g0 + u * stride;
+            const bool ok = g < total;                         // uniform across the 8 lanes of a group
+            const uint32_t aw[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, dw[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+            float acc = 0.f;
+            if (ok) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 x = unpack_bf16x2(aw[e]), y = unpack_bf16x2(dw[e]);
+                    acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
+                }
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            if (ok && sub == 0) {
+                const int h = static_cast<int>(g % H);
+                const long long row = g / H, b = row / Nq, q = row % Nq;
+                dsum[(b * H + h) * Nq + q] = acc;
+            }
         }
     }
 }
