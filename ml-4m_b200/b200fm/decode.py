@@ -60,6 +60,16 @@ def _lin(lin, x_bf16):
     return ops.gemm(x_bf16, BF.weight_bf16(lin.weight), epilogue=ops.EPI_BF16, bias=lin.bias, n_out=lin.weight.shape[0])
 
 
+DECODE_ATTN_MAX_KEYS = 1024     # one-query kernel up to here (B x H small CTAs walk the keys); longer contexts: the tile kernels
+
+
+def _attend1(q, k, v, B, H, Nk, mask, scale):
+    """Attention of ONE query row per sequence over Nk cached keys."""
+    if Nk <= DECODE_ATTN_MAX_KEYS:
+        return ops.attention_decode(q, k, v, B, H, Nk, mask, scale)
+    return ops.attention_fwd(q, k, v, B, H, 1, Nk, mask, scale)[0]
+
+
 def _lin_resid(lin, x_bf16, resid):
     """resid (fp32) + bf16(lin(x)): the residual add as the GEMM's epilogue (no cast / add kernels between the linears, so the whole
     decode step stays one chain of programmatically dependent launches)."""
@@ -134,13 +144,13 @@ class CachedDecoder:
             else:
                 ops.kv_append(qkv[:, D:], cache, self.pos_dev, 0)                 # k | v are adjacent in the qkv row
             c2 = cache.view(B * L, 2 * D)
-            o = ops.attention_decode(q, c2[:, :D], c2[:, D:], B, H, L, self.sa_mask, sa.scale)
+            o = _attend1(q, c2[:, :D], c2[:, D:], B, H, L, self.sa_mask, sa.scale)
             x = _lin_resid(sa.proj, o, x)                                         # x + proj(o): the add is the GEMM's epilogue
             q = _lin(xa.q, _ln(blk.query_norm, x))
             if hasattr(xa, "q_norm"):
                 q = BF.head_norm(q, H, xa.q_norm)
             kv = self.kv_ctx[li]
-            o = ops.attention_decode(q, kv[:, :D], kv[:, D:], B, H, self.N, self.enc_mask, xa.scale)
+            o = _attend1(q, kv[:, :D], kv[:, D:], B, H, self.N, self.enc_mask, xa.scale)
             x = _lin_resid(xa.proj, o, x)
             h = _ln(blk.norm2, x)
             mlp = blk.mlp

@@ -1,12 +1,14 @@
 // Attention for ONE query row per sequence (head_dim 64): the shape of every attention call inside the K/V-cached autoregressive
 // decode step (b200fm/decode.py; reference: the per-token decoder forward of fourm/models/generate.py:886-901, whose attention is
 // fm_utils.py:160-180 / 197-219 over the whole prefix).  The tile kernel (attention_fwd.cu) spends a 128-query TMEM tile, TMA
-// descriptors and mbarrier round trips on a single row; here a CTA of 128 threads per (batch, head) does it with plain loads:
-//   pass 1: thread t scores the keys t, t + 128, ... (q in registers, one 128-byte K row per key), scores in shared memory;
+// descriptors and mbarrier round trips on a single row; here a CTA of 256 threads per (batch, head) does it with plain loads:
+//   pass 1: thread t scores the keys t, t + 256, ... (q in registers, one 128-byte K row per key), scores in shared memory;
 //   block max / sum (fp32, exact softmax like the reference: masked keys are filled with a large negative BEFORE the softmax, so a
 //   fully masked row becomes uniform);
-//   pass 2: thread = (output dimension d, key half): o[d] = sum_j p_j V[j][d], 64 consecutive threads read one V row (coalesced).
-// Latency-bound by construction (B x H CTAs, a few KB each): what matters is that it is ONE short kernel.  HBM bytes: Nk * 256 per (b, h).
+//   pass 2: thread = (8 output dimensions, one of 32 key groups): 8 threads read one 128-byte V row, every thread accumulates its 8
+//   dimensions over the keys of its group (Nk / 32 iterations, 16-byte loads), the 32 partial rows are summed through shared memory.
+// Latency-bound by construction (B x H CTAs, a few KB each): what matters is that it is ONE short kernel; the host side uses it up to
+// a few thousand keys (self-attention cache, short contexts) and the tile kernels beyond.  HBM bytes: Nk * 256 per (b, h).
 #include <cfloat>
 
 #include "../../include/b200fm.h"
@@ -15,7 +17,7 @@
 
 namespace b200fm {
 
-constexpr int kDecThreads = 128;
+constexpr int kDecThreads = 256;
 
 __global__ void __launch_bounds__(kDecThreads)
 attention_decode_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, const __nv_bfloat16* __restrict__ k, long long ldk,
@@ -24,7 +26,7 @@ attention_decode_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, cons
     pdl_enter();
     extern __shared__ float sc[];                         // [Nk] scores, then probabilities
     __shared__ float red[kDecThreads / 32];
-    __shared__ float part[64];
+    __shared__ float part[kDecThreads / 8][64 + 1];
     const int h = blockIdx.x, b = blockIdx.y, t = threadIdx.x, warp = t >> 5, lane = t & 31;
     // q row of this head: 64 bf16 = 8 x 16 B, pre-scaled
     float qf[64];
@@ -66,7 +68,10 @@ attention_decode_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, cons
     mx = warp_max(mx);
     if (lane == 0) red[warp] = mx;
     __syncthreads();
-    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    {
+        float m2 = lane < kDecThreads / 32 ? red[lane] : -FLT_MAX;
+        mx = warp_max(m2);
+    }
     float sum = 0.f;
     for (int j = t; j < Nk; j += kDecThreads) {
         const float p = __expf(sc[j] - mx);                               // all keys masked: every p = 1 -> uniform, like the reference
@@ -77,16 +82,44 @@ attention_decode_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, cons
     __syncthreads();                                                      // red[] reuse + sc[] complete
     if (lane == 0) red[warp] = sum;
     __syncthreads();
-    const float inv = 1.0f / (red[0] + red[1] + red[2] + red[3]);
-    // pass 2: d = t & 63, keys of parity t >> 6
-    const int d = t & 63, half = t >> 6;
-    float acc = 0.f;
-    const __nv_bfloat16* vp = v + (long long)b * Nk * ldv + h * 64 + d;
+    float tot = lane < kDecThreads / 32 ? red[lane] : 0.f;
+    tot = warp_sum(tot);
+    const float inv = 1.0f / tot;
+    // pass 2: dg = 8 output dimensions, kg = key group
+    const int dg = t & 7, kg = t >> 3;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    const __nv_bfloat16* vp = v + (long long)b * Nk * ldv + h * 64 + dg * 8;
+    const bool vec = (ldv % 8) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0;
 #pragma unroll 4
-    for (int j = half; j < Nk; j += 2) acc = fmaf(sc[j], __bfloat162float(vp[(long long)j * ldv]), acc);
-    if (half == 1) part[d] = acc;
+    for (int j = kg; j < Nk; j += kDecThreads / 8) {
+        const float p = sc[j];
+        uint32_t ww[4];
+        if (vec) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(vp + (long long)j * ldv));
+            ww[0] = w.x; ww[1] = w.y; ww[2] = w.z; ww[3] = w.w;
+        } else {
+            const uint16_t* r = reinterpret_cast<const uint16_t*>(vp + (long long)j * ldv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ww[e] = (uint32_t)r[2 * e] | ((uint32_t)r[2 * e + 1] << 16);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack_bf16x2(ww[e]);
+            acc[2 * e] = fmaf(p, f.x, acc[2 * e]);
+            acc[2 * e + 1] = fmaf(p, f.y, acc[2 * e + 1]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) part[kg][dg * 8 + e] = acc[e];
     __syncthreads();
-    if (half == 0) out[(long long)b * ldo + h * 64 + d] = __float2bfloat16_rn((acc + part[d]) * inv);
+    if (t < 64) {
+        float o = 0.f;
+#pragma unroll 8
+        for (int g = 0; g < kDecThreads / 8; ++g) o += part[g][t];
+        out[(long long)b * ldo + h * 64 + t] = __float2bfloat16_rn(o * inv);
+    }
 }
 
 }  // namespace b200fm

@@ -18,6 +18,8 @@ CPU): used by the parity tests against the CPU goldens.
 from typing import List, Optional, Union
 
 import numpy as np
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -227,7 +229,7 @@ class GenerationSampler(nn.Module):
         # AR sampling at temperature > 0 with top_k = 0: one fused kernel (b200fm_sample_top_p: nucleus cut by bisection + inverse-CDF draw
         # from a torch.rand number) instead of sort / cumsum / scatter / 2 softmaxes / multinomial per token.  Same distribution, a different
         # use of the random stream; rng_device = "cpu" (the parity mode) keeps the reference's torch calls.
-        self.fused_sampling = True
+        self.fused_sampling = os.environ.get("B200FM_FUSED_SAMPLING", "1") != "0"
 
     # ------------------------------------------------------------------ sampling
     def top_k_top_p_filtering(self, logits, top_k=0.0, top_p=0.0):
