@@ -39,7 +39,7 @@ int b200fm_abi_version(void);
 int b200fm_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* smem_optin);
 
 /* Runtime options (defaults from the environment variable B200FM_<NAME upper-case>): "pdl" (1: programmatic dependent launch),
- * "gemm_cta_pairs" (1: cta_group::2 GEMM tiles), "ln_bwd_v2" (LayerNorm-backward variant 0..3; 3 = gamma in shared memory, 2 CTAs per SM), "ln_fwd_v2" (1: LayerNorm forward with gamma / beta in shared memory, 4 CTAs per SM), "sm_reserve" (0: number
+ * "gemm_cta_pairs" (1: cta_group::2 GEMM tiles), "ln_bwd_v2" (1: LayerNorm backward with all loads of a row issued before its reductions; 0: plain kernel), "sm_reserve" (0: number
  * of SMs the persistent GEMM grids leave free, for a concurrent gradient all-reduce kernel), "gemv" (1: NT problems with <= 8 rows --
  * the linears of the K/V-cached decode loop -- run on an HBM-bound weight-streaming kernel instead of a tcgen05 tile), "gemv_prefetch"
  * (1: that kernel pulls its weight rows into L2 before it waits for the preceding kernel of the stream), "gemm_tma_store" (1: bf16 GEMM outputs are written by TMA stores), "comm_slim" (1: the gradient all-reduce runs as many

@@ -155,7 +155,7 @@ def call(name, *args):
 
 
 def set_option(name: str, value: int) -> None:
-    """Runtime option of the kernel library (include/b200fm.h: "pdl", "gemm_cta_pairs", "ln_bwd_v2", "sm_reserve", "gemv", "gemv_prefetch", "ln_fwd_v2", "gemm_tma_store", "comm_slim", "gemm_debug"); for in-process A/B measurements."""
+    """Runtime option of the kernel library (include/b200fm.h: "pdl", "gemm_cta_pairs", "ln_bwd_v2", "sm_reserve", "gemv", "gemv_prefetch", "gemm_tma_store", "comm_slim", "gemm_debug"); for in-process A/B measurements."""
     check(load().b200fm_set_option(name.encode(), int(value)), "b200fm_set_option")
 
 

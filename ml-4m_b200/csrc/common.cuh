@@ -21,7 +21,7 @@ namespace b200fm {
 B200FM_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 B200FM_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 B200FM_DEVINL void pdl_enter() { pdl_trigger(); pdl_wait(); }
-enum { kOptPdl = 0, kOptGemmCtaPairs = 1, kOptLnBwdV2 = 2, kOptSmReserve = 3, kOptGemv = 4, kOptGemvPrefetch = 5, kOptLnFwdV2 = 6, kOptGemmTmaStore = 7, kOptGemmDebug = 8, kOptCommSlim = 9, kOptAttnBwdWarps = 10, kOptCount = 11 };
+enum { kOptPdl = 0, kOptGemmCtaPairs = 1, kOptLnBwdV2 = 2, kOptSmReserve = 3, kOptGemv = 4, kOptGemvPrefetch = 5, kOptGemmTmaStore = 6, kOptGemmDebug = 7, kOptCommSlim = 8, kOptAttnBwdWarps = 9, kOptCount = 10 };
 int option(int id);      // runtime.cu: value of a runtime option (env default, b200fm_set_option override)
 bool pdl_enabled();      // option "pdl" (env B200FM_PDL, default 1)
 int usable_sm_count();   // SM count of the current device minus option "sm_reserve" (rounded up to even), at least 16

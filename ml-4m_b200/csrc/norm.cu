@@ -141,112 +141,9 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, c
     }
 }
 
-// Pipelined variant (option "ln_bwd_v2" = 2): one CTA per SM holds 8 rows in flight in the default kernel, and every row costs two
-// dependent memory phases (x, dy -> two warp reductions -> dres -> stores): 3.7 TB/s.  Here a warp requests ALL operands of its NEXT row
-// (x, dy, dres) before it reduces the current one, so two rows per warp are in flight and the reductions overlap the loads.
-template <int VEC>
-struct LnRow {
-    float4 x[VEC];
-    uint2 dy[VEC];
-    float4 r[VEC];
-    float mean, rstd;
-};
-template <int VEC>
-B200FM_DEVINL void ln_row_load(LnRow<VEC>& b, const __nv_bfloat16* dy, const float* x, const float* mean_in, const float* rstd_in,
-                               const float* dres, int row, int lane) {
-    constexpr int D = VEC * 128;
-    b.mean = mean_in[row]; b.rstd = rstd_in[row];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-        b.x[i] = reinterpret_cast<const float4*>(x + (size_t)row * D)[i * 32 + lane];
-        b.dy[i] = reinterpret_cast<const uint2*>(dy + (size_t)row * D)[i * 32 + lane];
-        b.r[i] = dres ? __ldcs(reinterpret_cast<const float4*>(dres + (size_t)row * D) + i * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-}
-template <int VEC>
-B200FM_DEVINL void ln_row_finish(const LnRow<VEC>& b, const float4 (&g)[VEC], float4 (&pg)[VEC], float4 (&pb)[VEC], float* dx_out,
-                                 __nv_bfloat16* dx_bf16, int row, int lane) {
-    constexpr int D = VEC * 128;
-    float c1 = 0.f, c2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-        const float2 a = unpack_bf16x2(b.dy[i].x), c = unpack_bf16x2(b.dy[i].y);
-        const float4 d = make_float4(a.x, a.y, c.x, c.y);
-        const float4 xh = make_float4((b.x[i].x - b.mean) * b.rstd, (b.x[i].y - b.mean) * b.rstd, (b.x[i].z - b.mean) * b.rstd, (b.x[i].w - b.mean) * b.rstd);
-        const float4 gy = make_float4(d.x * g[i].x, d.y * g[i].y, d.z * g[i].z, d.w * g[i].w);
-        c1 += (gy.x + gy.y) + (gy.z + gy.w);
-        c2 += (gy.x * xh.x + gy.y * xh.y) + (gy.z * xh.z + gy.w * xh.w);
-        pg[i].x += d.x * xh.x; pg[i].y += d.y * xh.y; pg[i].z += d.z * xh.z; pg[i].w += d.w * xh.w;
-        pb[i].x += d.x; pb[i].y += d.y; pb[i].z += d.z; pb[i].w += d.w;
-    }
-    c1 = warp_sum(c1) * (1.0f / D);
-    c2 = warp_sum(c2) * (1.0f / D);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-        const float2 a = unpack_bf16x2(b.dy[i].x), c = unpack_bf16x2(b.dy[i].y);
-        const float4 d = make_float4(a.x, a.y, c.x, c.y);
-        const float4 xh = make_float4((b.x[i].x - b.mean) * b.rstd, (b.x[i].y - b.mean) * b.rstd, (b.x[i].z - b.mean) * b.rstd, (b.x[i].w - b.mean) * b.rstd);
-        float4 o;
-        o.x = b.rstd * (d.x * g[i].x - c1 - xh.x * c2) + b.r[i].x;
-        o.y = b.rstd * (d.y * g[i].y - c1 - xh.y * c2) + b.r[i].y;
-        o.z = b.rstd * (d.z * g[i].z - c1 - xh.z * c2) + b.r[i].z;
-        o.w = b.rstd * (d.w * g[i].w - c1 - xh.w * c2) + b.r[i].w;
-        reinterpret_cast<float4*>(dx_out + (size_t)row * D)[i * 32 + lane] = o;
-        if (dx_bf16)
-            reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * D)[i * 32 + lane] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
-    }
-}
-template <int VEC>
-__global__ void __launch_bounds__(kLnWarps * 32)
-layernorm_bwd_pipe_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
-                          const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ dres,
-                          float* __restrict__ dx_out, __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma,
-                          float* __restrict__ dbeta, int rows) {
-    pdl_enter();
-    __shared__ float red[kLnWarps][128 + 4];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float4 g[VEC], pg[VEC], pb[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-        g[i] = reinterpret_cast<const float4*>(gamma)[i * 32 + lane];
-        pg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    const int stride = gridDim.x * kLnWarps;
-    int row = blockIdx.x * kLnWarps + warp;
-    LnRow<VEC> b0, b1;
-    if (row < rows) ln_row_load<VEC>(b0, dy, x, mean_in, rstd_in, dres, row, lane);
-    while (row < rows) {
-        const int r1 = row + stride;
-        if (r1 < rows) ln_row_load<VEC>(b1, dy, x, mean_in, rstd_in, dres, r1, lane);
-        ln_row_finish<VEC>(b0, g, pg, pb, dx_out, dx_bf16, row, lane);
-        if (r1 >= rows) break;
-        const int r2 = r1 + stride;
-        if (r2 < rows) ln_row_load<VEC>(b0, dy, x, mean_in, rstd_in, dres, r2, lane);
-        ln_row_finish<VEC>(b1, g, pg, pb, dx_out, dx_bf16, r1, lane);
-        row = r2;
-    }
-    if (dgamma == nullptr && dbeta == nullptr) return;
-    for (int pass = 0; pass < 2; ++pass) {
-        float* dst = pass == 0 ? dgamma : dbeta;
-        if (dst == nullptr) continue;
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            __syncthreads();
-            *reinterpret_cast<float4*>(&red[warp][lane * 4]) = pass == 0 ? pg[i] : pb[i];
-            __syncthreads();
-            if (threadIdx.x < 128) {
-                float s = 0.f;
-#pragma unroll
-                for (int w = 0; w < kLnWarps; ++w) s += red[w][threadIdx.x];
-                atomicAdd(dst + i * 128 + threadIdx.x, s);
-            }
-        }
-    }
-}
-
-// EXPERIMENTAL variant (option "ln_bwd_v2", default off, not yet measured on hardware): identical arithmetic, but the dres loads are
-// issued together with x / dy instead of after the two warp reductions, so a row costs one memory round trip instead of two.
+// Default backward (option "ln_bwd_v2" = 1; 0 selects the kernel above): the residual-gradient row is requested together with x and dy,
+// BEFORE the two warp reductions, so one row costs one memory round trip instead of two.  Stand-alone at 16384 x 768: 35.4 us = 5.68 TB/s
+// vs 47.4 us (tools/ln_bench.py); one CTA of 8 warps per SM either way (register-limited: the column partials live in registers).
 template <int VEC, bool DY_BF16>
 __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_bwd_v2_kernel(const void* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
@@ -397,146 +294,6 @@ headnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const 
 }
 
 
-// ---- high-occupancy variants (options "ln_fwd_v2" = 1, "ln_bwd_v2" = 3) ------------------------------------------------------------
-// ncu (profiles/r2_full_hot_kernels.csv): the kernels above are latency-bound, not bandwidth-bound -- gamma / beta (and the column
-// partials of the backward) live in registers, 98 / 152 per thread, so only 16 / 8 warps per SM are resident and ~36 KB per SM are in
-// flight: 4.4 / 3.85 TB/s of 6.5.  Here gamma / beta sit in shared memory (read with conflict-free LDS.128 where they are used) and dy
-// stays packed, which brings the forward to <= 64 registers (4 CTAs = 32 warps per SM) and the backward to <= 128 (2 CTAs = 16 warps).
-template <int VEC, bool OUT_BF16>
-__global__ void __launch_bounds__(kLnWarps * 32, 4)
-layernorm_fwd_occ_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ add, float* __restrict__ x_out,
-                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                         void* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, float eps) {
-    pdl_enter();
-    constexpr int D = VEC * 128;
-    __shared__ float4 sg[VEC * 32], sb[VEC * 32];
-    for (int i = threadIdx.x; i < VEC * 32; i += kLnWarps * 32) {
-        sg[i] = reinterpret_cast<const float4*>(gamma)[i];
-        sb[i] = beta ? reinterpret_cast<const float4*>(beta)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int row = blockIdx.x * kLnWarps + warp; row < rows; row += gridDim.x * kLnWarps) {
-        const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
-        float4 v[VEC];
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) v[i] = xr[i * 32 + lane];
-        if (add != nullptr) {
-            uint2 u[VEC];
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) u[i] = reinterpret_cast<const uint2*>(add + (size_t)row * D)[i * 32 + lane];
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                const float2 a = unpack_bf16x2(u[i].x), c = unpack_bf16x2(u[i].y);
-                v[i].x += a.x; v[i].y += a.y; v[i].z += c.x; v[i].w += c.y;
-                reinterpret_cast<float4*>(x_out + (size_t)row * D)[i * 32 + lane] = v[i];
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-        const float mean = warp_sum(s) * (1.0f / D);
-        float q = 0.f;
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            const float a = v[i].x - mean, c = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
-            q += (a * a + c * c) + (d * d + e * e);
-        }
-        const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
-        if (lane == 0) { if (mean_out) mean_out[row] = mean; if (rstd_out) rstd_out[row] = rstd; }
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            const float4 g = sg[i * 32 + lane], b = sb[i * 32 + lane];
-            const float o0 = (v[i].x - mean) * rstd * g.x + b.x;
-            const float o1 = (v[i].y - mean) * rstd * g.y + b.y;
-            const float o2 = (v[i].z - mean) * rstd * g.z + b.z;
-            const float o3 = (v[i].w - mean) * rstd * g.w + b.w;
-            if constexpr (OUT_BF16) {
-                reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + (size_t)row * D)[i * 32 + lane] =
-                    make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
-            } else {
-                reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + (size_t)row * D)[i * 32 + lane] = make_float4(o0, o1, o2, o3);
-            }
-        }
-    }
-}
-
-template <int VEC>
-__global__ void __launch_bounds__(kLnWarps * 32, 2)
-layernorm_bwd_occ_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
-                         const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const float* __restrict__ dres,
-                         float* __restrict__ dx_out, __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma,
-                         float* __restrict__ dbeta, int rows) {
-    pdl_enter();
-    constexpr int D = VEC * 128;
-    __shared__ float4 sg[VEC * 32];
-    __shared__ float red[kLnWarps][128 + 4];
-    for (int i = threadIdx.x; i < VEC * 32; i += kLnWarps * 32) sg[i] = reinterpret_cast<const float4*>(gamma)[i];
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float4 pg[VEC], pb[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) { pg[i] = make_float4(0.f, 0.f, 0.f, 0.f); pb[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
-    for (int row = blockIdx.x * kLnWarps + warp; row < rows; row += gridDim.x * kLnWarps) {
-        const float mean = mean_in[row], rstd = rstd_in[row];
-        float4 xh[VEC];
-        uint2 dyp[VEC];
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            xh[i] = reinterpret_cast<const float4*>(x + (size_t)row * D)[i * 32 + lane];
-            dyp[i] = reinterpret_cast<const uint2*>(dy + (size_t)row * D)[i * 32 + lane];
-        }
-        float c1 = 0.f, c2 = 0.f;
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            const float2 a = unpack_bf16x2(dyp[i].x), c = unpack_bf16x2(dyp[i].y);
-            const float4 g = sg[i * 32 + lane];
-            xh[i] = make_float4((xh[i].x - mean) * rstd, (xh[i].y - mean) * rstd, (xh[i].z - mean) * rstd, (xh[i].w - mean) * rstd);
-            const float4 gy = make_float4(a.x * g.x, a.y * g.y, c.x * g.z, c.y * g.w);
-            c1 += (gy.x + gy.y) + (gy.z + gy.w);
-            c2 += (gy.x * xh[i].x + gy.y * xh[i].y) + (gy.z * xh[i].z + gy.w * xh[i].w);
-            pg[i].x += a.x * xh[i].x; pg[i].y += a.y * xh[i].y; pg[i].z += c.x * xh[i].z; pg[i].w += c.y * xh[i].w;
-            pb[i].x += a.x; pb[i].y += a.y; pb[i].z += c.x; pb[i].w += c.y;
-        }
-        c1 = warp_sum(c1) * (1.0f / D);
-        c2 = warp_sum(c2) * (1.0f / D);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            const float2 a = unpack_bf16x2(dyp[i].x), c = unpack_bf16x2(dyp[i].y);
-            const float4 g = sg[i * 32 + lane];
-            float4 o;
-            o.x = rstd * (a.x * g.x - c1 - xh[i].x * c2);
-            o.y = rstd * (a.y * g.y - c1 - xh[i].y * c2);
-            o.z = rstd * (c.x * g.z - c1 - xh[i].z * c2);
-            o.w = rstd * (c.y * g.w - c1 - xh[i].w * c2);
-            if (dres) {
-                const float4 r = __ldcs(reinterpret_cast<const float4*>(dres + (size_t)row * D) + i * 32 + lane);
-                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-            }
-            reinterpret_cast<float4*>(dx_out + (size_t)row * D)[i * 32 + lane] = o;
-            if (dx_bf16)
-                reinterpret_cast<uint2*>(dx_bf16 + (size_t)row * D)[i * 32 + lane] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
-        }
-    }
-    if (dgamma == nullptr && dbeta == nullptr) return;
-    for (int pass = 0; pass < 2; ++pass) {
-        float* dst = pass == 0 ? dgamma : dbeta;
-        if (dst == nullptr) continue;
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            __syncthreads();
-            *reinterpret_cast<float4*>(&red[warp][lane * 4]) = pass == 0 ? pg[i] : pb[i];
-            __syncthreads();
-            if (threadIdx.x < 128) {
-                float s = 0.f;
-#pragma unroll
-                for (int w = 0; w < kLnWarps; ++w) s += red[w][threadIdx.x];
-                atomicAdd(dst + i * 128 + threadIdx.x, s);
-            }
-        }
-    }
-}
-
 }  // namespace b200fm
 
 
@@ -562,20 +319,6 @@ extern "C" int b200fm_add_layernorm_fwd(const float* x, const void* add_bf16, fl
     const __nv_bfloat16* add = reinterpret_cast<const __nv_bfloat16*>(add_bf16);
     B200FM_CHECK(D % 128 == 0 && D >= 128 && D <= 2048, "layernorm_fwd: D=%d unsupported (need multiple of 128 in [128, 2048])", D);
     const int grid = ln_grid(rows);
-    if (option(kOptLnFwdV2) != 0 && D <= 768) {      // wider rows spill at 64 registers
-#define LN_FWD_OCC(V)                                                                                                    \
-    case V:                                                                                                              \
-        if (y_is_bf16) B200FM_LAUNCH((layernorm_fwd_occ_kernel<V, true>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, x, add, x_out, gamma, beta, y, mean, rstd, rows, eps); \
-        else B200FM_LAUNCH((layernorm_fwd_occ_kernel<V, false>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, x, add, x_out, gamma, beta, y, mean, rstd, rows, eps);          \
-        break;
-        switch (D / 128) {
-            LN_FWD_OCC(1) LN_FWD_OCC(2) LN_FWD_OCC(3) LN_FWD_OCC(4) LN_FWD_OCC(5) LN_FWD_OCC(6)
-            default: B200FM_CHECK(false, "layernorm_fwd: D=%d has no instantiation", D);
-        }
-#undef LN_FWD_OCC
-        B200FM_CUDA(cudaGetLastError());
-        return 0;
-    }
 #define LN_FWD(V)                                                                                                        \
     case V:                                                                                                              \
         if (y_is_bf16) B200FM_LAUNCH((layernorm_fwd_kernel<V, true>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, x, add, x_out, gamma, beta, y, mean, rstd, rows, eps); \
@@ -599,25 +342,10 @@ extern "C" int b200fm_layernorm_bwd(const void* dy, int dy_is_bf16, const float*
     B200FM_CHECK(D % 128 == 0 && D >= 128 && D <= 2048, "layernorm_bwd: D=%d unsupported", D);
     int grid = ln_grid(rows);
     if (grid > 148 * 2) grid = 148 * 2;       // fewer blocks -> fewer column atomics
-    const bool v2 = option(kOptLnBwdV2) == 1;
-    const bool pipe = option(kOptLnBwdV2) == 2;
-    if (option(kOptLnBwdV2) == 3 && dy_is_bf16 && D <= 768) {      // wider rows spill at 128 registers
-#define LN_BWD_OCC(V)                                                                                                      \
-    case V:                                                                                                                \
-        B200FM_LAUNCH((layernorm_bwd_occ_kernel<V>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd, dres, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows); \
-        break;
-        switch (D / 128) {
-            LN_BWD_OCC(1) LN_BWD_OCC(2) LN_BWD_OCC(3) LN_BWD_OCC(4) LN_BWD_OCC(5) LN_BWD_OCC(6)
-            default: B200FM_CHECK(false, "layernorm_bwd: D=%d has no instantiation", D);
-        }
-#undef LN_BWD_OCC
-        B200FM_CUDA(cudaGetLastError());
-        return 0;
-    }
+    const bool v2 = option(kOptLnBwdV2) != 0;     // default: all loads of a row hoisted ahead of the reductions
 #define LN_BWD(V)                                                                                                          \
     case V:                                                                                                                \
-        if (pipe && dy_is_bf16) B200FM_LAUNCH((layernorm_bwd_pipe_kernel<V>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd, dres, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows); \
-        else if (v2 && dy_is_bf16) B200FM_LAUNCH((layernorm_bwd_v2_kernel<V, true>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, dy, x, gamma, mean, rstd, dres, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows); \
+        if (v2 && dy_is_bf16) B200FM_LAUNCH((layernorm_bwd_v2_kernel<V, true>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, dy, x, gamma, mean, rstd, dres, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows); \
         else if (dy_is_bf16) B200FM_LAUNCH((layernorm_bwd_kernel<V, true>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, dy, x, gamma, mean, rstd, dres, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows); \
         else B200FM_LAUNCH((layernorm_bwd_kernel<V, false>), dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, dy, x, gamma, mean, rstd, dres, dx_out, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, rows);          \
         break;

@@ -17,11 +17,10 @@ struct OptionSlot { const char* name; const char* env; int def; int value; bool 
 static OptionSlot g_options[kOptCount] = {
     {"pdl", "B200FM_PDL", 1, 1, false},                        // programmatic dependent launch on every kernel
     {"gemm_cta_pairs", "B200FM_GEMM_CTA_PAIRS", 1, 1, false},  // tcgen05 cta_group::2 GEMM tiles
-    {"ln_bwd_v2", "B200FM_LN_BWD_V2", 1, 1, false},            // LayerNorm backward: 1 = dres loads hoisted (35.4 us vs 47.4 us stand-alone at 16384 x 768: tools/ln_bench.py), 0 / 2 / 3 = other variants
+    {"ln_bwd_v2", "B200FM_LN_BWD_V2", 1, 1, false},            // LayerNorm backward: 1 = all loads of a row hoisted ahead of the reductions (35.4 us vs 47.4 us stand-alone at 16384 x 768: tools/ln_bench.py), 0 = plain
     {"sm_reserve", "B200FM_SM_RESERVE", 0, 0, false},          // SMs the persistent GEMM grids leave free (concurrent all-reduce kernel)
     {"gemv", "B200FM_GEMV", 1, 1, false},                      // NT GEMMs with <= 8 rows run on the weight-streaming kernel (gemv.cu)
     {"gemv_prefetch", "B200FM_GEMV_PREFETCH", 1, 1, false},    // gemv.cu: L2-prefetch the weight rows BEFORE waiting for the predecessor grid
-    {"ln_fwd_v2", "B200FM_LN_FWD_V2", 0, 0, false},            // norm.cu: LayerNorm forward with gamma / beta in shared memory (4 CTAs per SM)
     {"gemm_tma_store", "B200FM_GEMM_TMA_STORE", 1, 1, false},  // gemm.cu: bf16 outputs leave through TMA stores (2 passes over the smem / L1 data path instead of 3)
     {"gemm_debug", "B200FM_GEMM_DEBUG", 0, 0, false},          // MEASUREMENT ONLY (wrong results): 1 = GEMM epilogue stores nothing, 2 = epilogue skipped
     {"comm_slim", "B200FM_COMM_SLIM", 1, 1, false},            // comm.cu: all-reduce CTAs of 128 threads / 64 registers, co-resident with the persistent kernels (no SM reservation); 0 = few 512-thread CTAs on reserved SMs

@@ -51,7 +51,7 @@ def test_runtime_options_roundtrip(built):
     """b200fm_set_option / b200fm_get_option (no GPU needed): defaults, override, unknown names are errors with a message."""
     from b200fm import lib
     assert lib.get_option("pdl") == 1 and lib.get_option("gemm_cta_pairs") == 1 and lib.get_option("ln_bwd_v2") == 1
-    assert lib.get_option("gemv") == 1 and lib.get_option("gemv_prefetch") == 1 and lib.get_option("ln_fwd_v2") == 0 and lib.get_option("gemm_debug") == 0
+    assert lib.get_option("gemv") == 1 and lib.get_option("gemv_prefetch") == 1 and lib.get_option("gemm_debug") == 0
     assert lib.get_option("gemm_tma_store") == 1 and lib.get_option("comm_slim") == 1 and lib.get_option("attn_bwd_warps") == 8
     lib.set_option("pdl", 0)
     assert lib.get_option("pdl") == 0

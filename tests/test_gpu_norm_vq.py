@@ -110,9 +110,8 @@ def test_vq_scan_full_size_properties():
 
 @pytest.mark.parametrize("rows,D", [(37, 384), (16384, 768), (300, 1024), (9, 768)])
 def test_layernorm_bwd_v2_matches_v1(rows, D):
-    """The LayerNorm-backward variants (option "ln_bwd_v2": 0 = plain, 1 = dres loads hoisted ahead of the reductions -- the default --,
-    2 = two rows per warp in flight, 3 = gamma in shared memory / 16 warps per SM) agree to fp32 rounding (the compiler contracts the
-    expressions differently, so not bit for bit)."""
+    """The two LayerNorm-backward kernels (option "ln_bwd_v2": 0 = plain, 1 = all loads of a row hoisted ahead of the reductions -- the
+    default) agree to fp32 rounding (the compiler contracts the expressions differently, so not bit for bit)."""
     from b200fm import lib, ops
     g = torch.Generator().manual_seed(5)
     x = (torch.randn(rows, D, generator=g) * 2 + 0.3).cuda()
@@ -121,7 +120,7 @@ def test_layernorm_bwd_v2_matches_v1(rows, D):
     dres = torch.randn(rows, D, generator=g).cuda()
     _, mean, rstd = ops.layernorm_fwd(x, w, None, 1e-6)
     outs = []
-    for v in (0, 1, 2, 3):
+    for v in (0, 1):
         lib.set_option("ln_bwd_v2", v)
         try:
             dgamma = torch.zeros(D, device="cuda")
@@ -129,30 +128,8 @@ def test_layernorm_bwd_v2_matches_v1(rows, D):
             outs.append((dx.clone(), dxb.clone(), dgamma.clone()))
         finally:
             lib.set_option("ln_bwd_v2", 1)
-    for v in (1, 2, 3):
+    for v in (1,):
         torch.testing.assert_close(outs[0][0], outs[v][0], rtol=1e-5, atol=1e-5)
         torch.testing.assert_close(outs[0][1].float(), outs[v][1].float(), rtol=1e-2, atol=1e-2)
     for o in outs[1:]:
         torch.testing.assert_close(outs[0][2], o[2], rtol=1e-4, atol=1e-4 * rows ** 0.5)
-
-
-@pytest.mark.parametrize("rows,D", [(37, 384), (16384, 768), (300, 512)])
-def test_layernorm_fwd_v2_matches_v1(rows, D):
-    """Option "ln_fwd_v2" = 1 (gamma / beta in shared memory, 32 warps per SM) reproduces the default forward bit for bit (same
-    arithmetic in the same order), with and without the fused residual add."""
-    from b200fm import lib, ops
-    g = torch.Generator().manual_seed(6)
-    x = (torch.randn(rows, D, generator=g) * 2 + 0.3).cuda()
-    w = (torch.randn(D, generator=g) * 0.1 + 1).cuda()
-    b = (torch.randn(D, generator=g) * 0.1).cuda()
-    outs = []
-    for v in (0, 1):
-        lib.set_option("ln_fwd_v2", v)
-        try:
-            y, mean, rstd = ops.layernorm_fwd(x, w, b, 1e-6)
-            y32 = ops.layernorm_fwd(x, w, None, 1e-6, out_bf16=False)[0]
-            outs.append((y.clone(), mean.clone(), rstd.clone(), y32.clone()))
-        finally:
-            lib.set_option("ln_fwd_v2", 0)
-    for a, c in zip(outs[0], outs[1]):
-        assert torch.equal(a, c)
