@@ -361,8 +361,9 @@ def run_b200_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
-    loss_evt = [torch.cuda.Event() for _ in range(2)]
+    LAG = 2      # the host reads step i's loss while steps i+1 and i+2 are already queued (one step of slack against host hiccups)
+    loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(LAG + 1)]
+    loss_evt = [torch.cuda.Event() for _ in range(LAG + 1)]
 
     def timed(n_steps, e2e, step=step, host_batches=host_batches):
         calls0 = lib.CALLS["n"]
@@ -373,19 +374,20 @@ def run_b200_arm(args):
         t_cpu0 = time.perf_counter()
         if e2e:
             # every step's batch is copied from pinned host memory inside the timed region, one batch ahead on a side stream
-            # device -> host read of EVERY step's loss, pipelined by one step: step i's loss travels to pinned memory while step
-            # i+1 is already queued (a blocking .item() would drain the GPU once per step)
+            # device -> host read of EVERY step's loss, pipelined: step i's loss travels to pinned memory and is read by the host
+            # while the next LAG steps are already queued (a blocking .item() would drain the GPU once per step)
             i = 0
-            for batch in DevicePrefetcher((host_batches[i % 2] for i in range(n_steps)), dev):
+            for batch in DevicePrefetcher((host_batches[i % 2] for i in range(n_steps)), dev, depth=LAG + 1):
                 loss, mod_loss, gnorm = step(batch)
-                loss_host[i % 2].copy_(loss.detach().reshape(1), non_blocking=True)
-                loss_evt[i % 2].record()
-                if i > 0:
-                    loss_evt[(i - 1) % 2].synchronize()
-                    last = float(loss_host[(i - 1) % 2])
+                loss_host[i % (LAG + 1)].copy_(loss.detach().reshape(1), non_blocking=True)
+                loss_evt[i % (LAG + 1)].record()
+                if i >= LAG:
+                    loss_evt[(i - LAG) % (LAG + 1)].synchronize()
+                    last = float(loss_host[(i - LAG) % (LAG + 1)])
                 i += 1
-            loss_evt[(i - 1) % 2].synchronize()
-            last = float(loss_host[(i - 1) % 2])
+            for j in range(max(0, i - LAG), i):                       # drain: the last LAG losses
+                loss_evt[j % (LAG + 1)].synchronize()
+                last = float(loss_host[j % (LAG + 1)])
         else:
             for i in range(n_steps):
                 loss, mod_loss, gnorm = step(dev_batches[i % 2])
