@@ -699,12 +699,16 @@ def run_vq_arm(args):
         if world > 1:
             net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True, broadcast_buffers=False)
 
+        from b200fm.optim import FusedModelEma
+        model_ema = FusedModelEma(model, decay=0.9999)          # run_training_vqvae.py:224, 683-688 (--model_ema defaults to True)
+
         def step(x):
             dec, code_loss = net(x)
             loss = F.mse_loss(dec.float(), x) + code_loss.sum()
             loss.backward()
             opt.step()
             opt.zero_grad(set_to_none=True)
+            model_ema.update(model)                                # every step (run_training_vqvae.py:1169-1171), one multi-tensor launch
             return loss
     else:
         model = vq.VQ(sync_codebook=False, **VQ_KW).to(dev).eval()
@@ -807,7 +811,7 @@ def run_vq_arm(args):
         if world == 1 and not args.no_cpu_baseline and not train:
             v, sec, cores, kind = _vq_cpu_tokenize(2, 1, 1)
             cpu = dict(value=v, unit="img/s", cores=cores, kind=kind, sample=f"1 timed VQ.tokenize of 2 images 256x256 (1 warm-up), fp32, {cores} threads of {os.cpu_count()}")
-        name = ("VQ-VAE training step (ViT-B enc + dec, K=16384, EMA codebook, MSE, AdamW), BASELINE.json configs[4]" if train else
+        name = ("VQ-VAE training step (ViT-B enc + dec, K=16384, EMA codebook, MSE, AdamW, model EMA), BASELINE.json configs[4]" if train else
                 "VQ.tokenize (ViT-B encoder + codebook arg-max K=16384, d=32), 256x256, called like save_vq_tokens.py:288 (no autocast -> "
                 "fp32-faithful limb arithmetic, 3 bf16 limb products per contraction), BASELINE.json configs[4] tokenizer forward")
         mult = mult if train else 3                      # fp32-faithful: three limb GEMM terms per product

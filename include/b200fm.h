@@ -176,6 +176,12 @@ int b200fm_adamw_multi_dev(const b200fm_adamw_tensor* table_dev, const int* chun
 int b200fm_adamw_multi_gnorm(const b200fm_adamw_tensor* table_dev, const int* chunk_tensor_dev, const long long* chunk_offset_dev,
                              int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                              const float* hyper_dev, float* gnorm_sq, void* stream);
+/* Exponential moving average of a model in one launch (ModelEmaV2.update, fourm/utils/timm/model_ema.py:123-127; every step of
+ * run_training_vqvae.py:1169-1171): per table entry p (EMA tensor) = decay * p + (1 - decay) * g (model tensor), optional bf16 mirror
+ * of p refreshed; m / v of the entries are ignored.  one_minus_decay is passed separately because the reference computes 1 - decay in
+ * double before rounding it to fp32; products and sum are rounded like the torch expression (bit-identical).        */
+int b200fm_ema_multi(const b200fm_adamw_tensor* table_dev, const int* chunk_tensor_dev, const long long* chunk_offset_dev, int n_chunks,
+                     float decay, float one_minus_decay, void* stream);
 
 /* ---- modality-masked token selection + embedding gather / scatter ------------------------------------------------
  * Replaces cat_{encoder,decoder}_tensors + forward_mask_{encoder,decoder} + adapt_decoder_attention_mask

@@ -72,6 +72,7 @@ SIGNATURES = {
     "b200fm_cross_entropy_dyn": [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_int, c_void_p, c_void_p],
     "b200fm_masked_mean": [c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p],
     "b200fm_adamw_multi_gnorm": [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_void_p, c_void_p, c_void_p],
+    "b200fm_ema_multi": [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p],
     "b200fm_adamw_multi_dev": [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p],
     "b200fm_select_plan_ordered": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p],

@@ -278,9 +278,53 @@ adamw_multi_kernel(const b200fm_adamw_tensor* __restrict__ table, const int* __r
     }
 }
 
+// ---- multi-tensor exponential moving average of a model (ModelEmaV2.update, fourm/utils/timm/model_ema.py:123-127, called every
+// step by run_training_vqvae.py:1169-1171): ema = decay * ema + (1 - decay) * model over every fp32 entry of the state_dict in ONE
+// launch (the reference issues 3 element-wise kernels per tensor).  Same table / chunk maps as the AdamW kernel: p = EMA tensor,
+// g = model tensor, shadow_bf16 = optional bf16 mirror of the EMA weight.  The two products and the sum are rounded separately
+// (no fma contraction): bit-identical to the torch expression.  12 B per element (+2 with a mirror): HBM-bound.
+__global__ void __launch_bounds__(256)
+ema_multi_kernel(const b200fm_adamw_tensor* __restrict__ table, const int* __restrict__ chunk_tensor, const long long* __restrict__ chunk_offset,
+                 float decay, float one_minus_decay) {
+    pdl_enter();
+    const b200fm_adamw_tensor t = table[chunk_tensor[blockIdx.x]];
+    const long long off = chunk_offset[blockIdx.x];
+    const long long end = off + kMtChunk < t.n ? off + kMtChunk : t.n;
+    float* e = t.p; const float* m = t.g;
+    __nv_bfloat16* shadow = reinterpret_cast<__nv_bfloat16*>(t.shadow_bf16);
+    const bool vec = ((reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(m)) & 15) == 0 && (shadow == nullptr || (reinterpret_cast<uintptr_t>(shadow) & 7) == 0);
+    long long i = off + threadIdx.x * 4ll;
+    const long long e4 = vec ? off + ((end - off) & ~3ll) : off;
+    for (; i < e4; i += 1024) {
+        float4 a = *reinterpret_cast<float4*>(e + i);
+        const float4 b = *reinterpret_cast<const float4*>(m + i);
+        a.x = __fadd_rn(__fmul_rn(decay, a.x), __fmul_rn(one_minus_decay, b.x));
+        a.y = __fadd_rn(__fmul_rn(decay, a.y), __fmul_rn(one_minus_decay, b.y));
+        a.z = __fadd_rn(__fmul_rn(decay, a.z), __fmul_rn(one_minus_decay, b.z));
+        a.w = __fadd_rn(__fmul_rn(decay, a.w), __fmul_rn(one_minus_decay, b.w));
+        *reinterpret_cast<float4*>(e + i) = a;
+        if (shadow) *reinterpret_cast<uint2*>(shadow + i) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+    }
+    for (long long j = e4 + threadIdx.x; j < end; j += 256) {
+        const float a = __fadd_rn(__fmul_rn(decay, e[j]), __fmul_rn(one_minus_decay, m[j]));
+        e[j] = a;
+        if (shadow) shadow[j] = __float2bfloat16_rn(a);
+    }
+}
+
 }  // namespace b200fm
 
 using namespace b200fm;
+
+extern "C" int b200fm_ema_multi(const b200fm_adamw_tensor* table_dev, const int* chunk_tensor_dev, const long long* chunk_offset_dev, int n_chunks,
+                                float decay, float one_minus_decay, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (n_chunks == 0) return 0;
+    B200FM_CHECK(table_dev && chunk_tensor_dev && chunk_offset_dev, "ema_multi: null pointer");
+    B200FM_LAUNCH(ema_multi_kernel, dim3(n_chunks), dim3(256), 0, stream, 1, table_dev, chunk_tensor_dev, chunk_offset_dev, decay, one_minus_decay);
+    B200FM_CUDA(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int b200fm_adamw_multi(const b200fm_adamw_tensor* table_dev, const int* chunk_tensor_dev, const long long* chunk_offset_dev,
                                   int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay, int step,

@@ -188,3 +188,29 @@ def test_training_loop_reduces_loss_and_tolerates_autocast():
     assert abs(amp[0] - fused[0]) <= 1e-3 and abs(amp[-1] - fused[-1]) <= 0.6, (amp[0], fused[0], amp[-1], fused[-1])
     ref_opt = run(lambda m: torch.optim.AdamW(param_groups_like_reference(m, 0.05), lr=1e-3, betas=(0.9, 0.95)), autocast=False)
     assert abs(ref_opt[-1] - fused[-1]) <= 0.6, (ref_opt[-1], fused[-1])
+
+
+def test_fused_model_ema_matches_reference_expression():
+    """FusedModelEma (one multi-tensor launch) vs the reference's ModelEmaV2.update expression (fourm/utils/timm/model_ema.py:123-127)
+    applied entry by entry: fp32 entries bit-identical, integer buffers through the same torch expression; `.module` stays usable."""
+    import copy
+    from b200fm.optim import FusedModelEma
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(37, 64), torch.nn.BatchNorm1d(64), torch.nn.Linear(64, 8193)).cuda()
+    ema = FusedModelEma(model, decay=0.999)
+    ref = copy.deepcopy(model).eval()
+    for step in range(3):
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(torch.randn_like(p) * 0.1)
+            model[1].running_mean.add_(0.5)
+            model[1].num_batches_tracked.add_(1)
+            for e, m in zip(ref.state_dict().values(), model.state_dict().values()):
+                e.copy_(0.999 * e + (1. - 0.999) * m)
+        ema.update(model)
+    for (k, a), b in zip(ema.module.state_dict().items(), ref.state_dict().values()):
+        assert torch.equal(a, b), k
+    assert not ema.module.training and ema.module(torch.randn(4, 37, device="cuda")).shape == (4, 8193)
+    ema.set(model)
+    for a, b in zip(ema.module.state_dict().values(), model.state_dict().values()):
+        assert torch.equal(a, b)
