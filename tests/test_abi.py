@@ -59,3 +59,33 @@ def test_runtime_options_roundtrip(built):
     assert lib.get_option("pdl") == 1
     with pytest.raises(lib.B200FMError, match="unknown option"):
         lib.set_option("no_such_option", 1)
+
+
+def test_library_is_tcgen05_tma_code(built):
+    """The shipped library is sm_100a code that uses the Blackwell tensor path: tcgen05.mma (SASS UTCHMMA), TMA tensor loads (UTMALDG),
+    TMA tensor stores in the GEMM epilogue (UTMASTG), TMEM read-out (LDTM) -- and no legacy mma.sync (HMMA) anywhere."""
+    import re
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    from b200fm import lib
+    sass = subprocess.run(["cuobjdump", "-sass", lib.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
+    assert "sm_100a" in sass or "SM100" in sass.upper()
+    per_fn, cur = {}, None
+    for line in sass.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per_fn[cur] = set()
+            continue
+        if cur is not None:
+            for k in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "HMMA"):
+                if re.search(r"(?<![A-Z])" + k + r"(?![A-Z])", line):
+                    per_fn[cur].add(k)
+    gemm = [v for f, v in per_fn.items() if "gemm_kernel" in f]
+    attn = [v for f, v in per_fn.items() if "attention_fwd_kernel" in f or "attention_bwd_kernel" in f]
+    assert gemm and all({"UTCHMMA", "UTMALDG", "LDTM"} <= v for v in gemm)
+    assert any("UTMASTG" in v for v in gemm)
+    assert attn and all({"UTCHMMA", "UTMALDG", "LDTM"} <= v for v in attn)
+    assert not any("HMMA" in v for v in per_fn.values())

@@ -17,7 +17,7 @@ for line in sass.splitlines():
     if cur is None:
         continue
     for k in KEYS:
-        if re.search(r"\b" + k + r"\b|\b" + k + r"\.", line):
+        if re.search(r"(?<![A-Z])" + k + r"(?![A-Z])", line):
             counts[cur][k] += 1
 dem = subprocess.run(["c++filt"], input="\n".join(counts), capture_output=True, text=True).stdout.splitlines()
 print("# SASS evidence per kernel of ml-4m_b200/b200fm/libb200fm.so (cuobjdump -sass, sm_100a); counts of instruction sites")
