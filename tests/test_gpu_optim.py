@@ -214,3 +214,27 @@ def test_fused_model_ema_matches_reference_expression():
     ema.set(model)
     for a, b in zip(ema.module.state_dict().values(), model.state_dict().values()):
         assert torch.equal(a, b)
+
+
+def test_fused_model_ema_matches_reference_golden():
+    """FusedModelEma vs the UNMODIFIED reference's ModelEmaV2 (golden from tests/golden/make_golden_ema.py: 3 updates on CPU): every
+    state_dict entry bit-identical after every update (fp32 mul / mul / add are IEEE on both sides; the integer buffer goes through
+    the same torch expression)."""
+    import os
+    import sys
+    from b200fm.optim import FusedModelEma
+    from tests import helpers as H
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_ema as G                      # build_model / perturbations: the recipe the golden was made with
+    gold = H.load_golden("ema_golden.pt")
+    model = G.build_model().cuda()
+    ema = FusedModelEma(model, decay=gold["decay"])
+    for step in range(3):
+        with torch.no_grad():
+            for p, d in zip(model.parameters(), G.perturbations(model, step)):
+                p.add_(d.cuda())
+            model[1].running_mean.add_(0.5)
+            model[1].num_batches_tracked.add_(1)
+        ema.update(model)
+        for k, v in ema.module.state_dict().items():
+            assert torch.equal(v.cpu(), gold["states"][step][k]), (step, k)

@@ -289,3 +289,36 @@ def test_hub_wrapper_fm_config_matches_reference():
         with mod.MGP.no_init():
             m = FM(cfg)
         assert mod.MGP.digest(m) == gold[tag], (tag, mod.MGP.digest(m), gold[tag])
+
+
+def test_model_ema_rule_matches_reference_golden():
+    """The EMA rule the GPU kernel implements -- decay * ema + (1 - decay) * model, each product and the sum rounded to fp32, 1 - decay
+    formed in double -- replayed with torch on the CPU reproduces the UNMODIFIED reference's ModelEmaV2 (tests/golden/ema_golden.pt) bit
+    for bit; and FusedModelEma refuses the configurations it does not implement instead of silently averaging elsewhere."""
+    import copy
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_ema as G
+    import torch
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ema_golden.pt"), weights_only=False)
+    model = G.build_model()
+    ema = copy.deepcopy(model).eval()
+    decay = gold["decay"]
+    for step in range(3):
+        with torch.no_grad():
+            for p, d in zip(model.parameters(), G.perturbations(model, step)):
+                p.add_(d)
+            model[1].running_mean.add_(0.5)
+            model[1].num_batches_tracked.add_(1)
+            for e, m in zip(ema.state_dict().values(), model.state_dict().values()):
+                if e.dtype == torch.float32:
+                    e.copy_(torch.tensor(decay, dtype=torch.float32) * e + torch.tensor(1. - decay, dtype=torch.float32) * m)
+                else:
+                    e.copy_(decay * e + (1. - decay) * m)
+        for k, v in ema.state_dict().items():
+            assert torch.equal(v, gold["states"][step][k]), (step, k)
+    from b200fm.optim import FusedModelEma
+    import pytest as _pt
+    with _pt.raises(NotImplementedError):
+        FusedModelEma(model, device="cpu")
+    with _pt.raises(NotImplementedError):
+        FusedModelEma(model, resume="ckpt.pth")
