@@ -58,3 +58,30 @@ def test_local_modality_info_matches_reference_fields():
                 want.pop("sincos_pos_emb", None) if want.get("sincos_pos_emb") is True else None      # the default
                 kw.pop("sincos_pos_emb", None) if kw.get("sincos_pos_emb") is True else None
                 assert kw == want, (name, side, kw, want)
+
+
+def test_sampling_rule_matches_reference():
+    """`top_k_top_p_filtering` of the overlay (torch, the path `rng_device="cpu"` and the fallback use) and the oracle's sort-free statement
+    of the nucleus rule (the one csrc/sampling.cu evaluates by bisection) keep exactly the tokens the UNMODIFIED reference keeps
+    (tests/golden/sampling_golden.pt: 9 cases incl. top-k as int / fraction, top-k + top-p, top_p = 1)."""
+    import os
+    import sys
+    import numpy as np
+    import torch
+    from oracle import sampling_oracle as S
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_golden_sampling as G
+    from fourm.models.generate import GenerationSampler
+    gold = torch.load(os.path.join(here, "golden", "sampling_golden.pt"), weights_only=False)
+    assert len(gold["cases"]) == len(G.CASES)
+    for c in gold["cases"]:
+        logits = G.case_logits(c["rows"], c["V"], c["scale"], c["seed"])
+        ours = torch.isfinite(GenerationSampler.top_k_top_p_filtering(None, logits.clone(), c["top_k"], c["top_p"]))
+        assert torch.equal(ours, c["kept"]), (c["V"], c["top_k"], c["top_p"])
+        x = logits.numpy()
+        keep = S.top_k_keep(x, c["top_k"])
+        keep &= S.nucleus_keep(np.where(keep, x, -np.inf), c["top_p"])
+        diff = int((keep != c["kept"].numpy()).sum())
+        # the sort-free statement may differ from the sorted cumulative sum only by float32 summation order at the cut: at most one token a row
+        assert diff <= c["rows"] and (diff == 0 or c["V"] >= 8192), (c["V"], c["top_k"], c["top_p"], diff)
