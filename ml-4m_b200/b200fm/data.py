@@ -18,14 +18,16 @@ _END = object()
 class DevicePrefetcher:
     """Iterate `batches` (an iterable of {modality: {key: CPU tensor, ideally pinned}}) as device-resident mod_dicts."""
 
-    def __init__(self, batches, device, depth=2):
+    def __init__(self, batches, device, depth=2, stream=None):
+        """stream: reuse a side stream across several prefetchers (the caching allocator keeps one pool per stream: a fresh stream pays
+        cudaMalloc for every staged tensor again)."""
         self.batches = batches
         dev = torch.device(device)
         if dev.type == "cuda" and dev.index is None:        # the worker thread pins itself to an explicit device
             dev = torch.device("cuda", torch.cuda.current_device())
         self.device = dev
         self.depth = max(1, int(depth))
-        self.stream = torch.cuda.Stream(device=self.device)
+        self.stream = stream if stream is not None else torch.cuda.Stream(device=self.device)
 
     def _stage(self, host_batch):
         with torch.cuda.stream(self.stream):
